@@ -1,0 +1,87 @@
+// surya_b200 — extern "C" surface (op level). Engine-level entry points live in rec_engine.cu / det_engine.cu.
+#include "../../include/surya_b200.h"
+#include "ops.cuh"
+
+using namespace sb;
+
+extern "C" {
+
+const char* sb_last_error(void) { return last_error(); }
+int sb_version(void) { return 1; }
+long long sb_launch_count(void) { return launch_count(); }
+
+int sb_gemm(int dtype, const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
+            const float* bias, const void* residual, int ldr, int act, int swiglu, int out_f32, int force_bn,
+            void* stream) {
+  GemmArgs a;
+  a.dtype = dtype; a.A = A; a.lda = lda; a.W = W; a.ldw = ldw; a.C = C; a.ldc = ldc;
+  a.M = M; a.N = N; a.K = K; a.bias = bias; a.residual = residual; a.ldr = ldr;
+  a.act = act; a.swiglu = swiglu; a.out_f32 = out_f32; a.force_bn = force_bn;
+  return gemm_launch(a, static_cast<cudaStream_t>(stream));
+}
+
+int sb_rmsnorm(int dtype, const void* x, int ldx, const void* w, void* y, int ldy, int rows, int H, float eps,
+               const int* src_rows, void* stream) {
+  return rmsnorm(dtype, x, ldx, w, y, ldy, rows, H, eps, src_rows, static_cast<cudaStream_t>(stream));
+}
+
+int sb_gather_pad_rows(int dtype, const void* src, int src_is_f32, int lds, const int* perm, void* dst, int ldd,
+                       int rows, int K, int Kp, void* stream) {
+  return gather_pad_rows(dtype, src, src_is_f32, lds, perm, dst, ldd, rows, K, Kp, static_cast<cudaStream_t>(stream));
+}
+
+int sb_rope_vision(int dtype, void* qkv, int ld, const int* pos_rc, const float* inv_freq, int n_tok, int nh, int d,
+                   void* stream) {
+  return rope_vision(dtype, qkv, ld, pos_rc, inv_freq, n_tok, nh, d, static_cast<cudaStream_t>(stream));
+}
+
+int sb_rope_kv_append(int dtype, void* qkv, int ld, const int* tok_pos, const int* tok_slot, const float* inv_freq,
+                      void* kcache, void* vcache, int n_tok, int nh, int nkv, int d, int s_max, void* stream) {
+  return rope_kv_append(dtype, qkv, ld, tok_pos, tok_slot, inv_freq, kcache, vcache, n_tok, nh, nkv, d, s_max,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int sb_attn_varlen(int dtype, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
+                   int ldo, const int* seq_start, const int* seq_len, int n_seq, int max_len, int n_heads,
+                   int n_kv_heads, int head_dim, int causal, float scale, void* stream) {
+  AttnArgs a;
+  a.dtype = dtype; a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.out = out; a.ldo = ldo;
+  a.seq_start = seq_start; a.seq_len = seq_len; a.n_seq = n_seq; a.max_len = max_len;
+  a.n_heads = n_heads; a.n_kv_heads = n_kv_heads; a.head_dim = head_dim; a.causal = causal; a.scale = scale;
+  return attn_varlen(a, static_cast<cudaStream_t>(stream));
+}
+
+int sb_decode_attn(int dtype, const void* qkv, int ld, void* kcache, void* vcache, const int* slot, const int* pos,
+                   const float* inv_freq, void* out, int ldo, int batch, int n_heads, int n_kv_heads, int head_dim,
+                   int s_max, float scale, void* stream) {
+  DecodeAttnArgs a;
+  a.dtype = dtype; a.qkv = qkv; a.ld = ld; a.kcache = kcache; a.vcache = vcache; a.slot = slot; a.pos = pos;
+  a.inv_freq = inv_freq; a.out = out; a.ldo = ldo; a.batch = batch; a.n_heads = n_heads; a.n_kv_heads = n_kv_heads;
+  a.head_dim = head_dim; a.s_max = s_max; a.scale = scale;
+  return decode_attn(a, static_cast<cudaStream_t>(stream));
+}
+
+int sb_embed_splice(int dtype, const long long* ids, const int* feat_row, const int* hidx, const int* widx,
+                    const void* embed, const void* feat, int ldf, const void* h_embed, const void* w_embed,
+                    void* out, int ldo, int n_tok, int H, void* stream) {
+  return embed_splice(dtype, ids, feat_row, hidx, widx, embed, feat, ldf, h_embed, w_embed, out, ldo, n_tok, H,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int sb_embed_rows(int dtype, const long long* ids, const void* embed, void* out, int ldo, int n, int H, void* stream) {
+  return embed_rows(dtype, ids, embed, out, ldo, n, H, static_cast<cudaStream_t>(stream));
+}
+
+int sb_argmax_score(int dtype, const void* logits, int ld, int rows, int V, long long* tok, float* score,
+                    unsigned char* done, long long* next_ids, int eos, int pad, void* stream) {
+  return argmax_score(dtype, logits, ld, rows, V, tok, score, done, next_ids, eos, pad,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int sb_small_head(int dtype, const void* x, int ldx, const void* w, const void* b, int rows, int H, int n_out,
+                  int sigmoid, float* out_f, long long* out_box, float box_scale, void* stream) {
+  return small_head(dtype, x, ldx, w, b, rows, H, n_out, sigmoid, out_f, out_box, box_scale,
+                    static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

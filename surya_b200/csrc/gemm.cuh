@@ -1,0 +1,40 @@
+// surya_b200 — tcgen05 GEMM interface (host side). See gemm_tcgen05.cu.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+enum Act : int { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_SILU = 2, ACT_HARDSWISH = 3, ACT_RELU = 4, ACT_GELU_TANH = 5 };
+enum DType : int { DT_BF16 = 0, DT_F16 = 1 };
+
+// C[M, Nout] = epilogue( A[M,K] @ W[N,K]^T ), 16-bit in / fp32 accumulate / 16-bit out.
+//   epilogue: x = acc (+ bias[n]) -> round -> act -> round (+ residual[m,n]) -> round
+//   swiglu=1: weight rows are interleaved (gate_0, up_0, gate_1, up_1, ...); Nout = N/2 and
+//             out[m,j] = round(round(act(g)) * u).
+struct GemmArgs {
+  int dtype = DT_BF16;
+  const void* A = nullptr; int lda = 0;   // [M, K], row stride lda (elements), lda*2 % 16 == 0
+  const void* W = nullptr; int ldw = 0;   // [N, K], row stride ldw
+  void* C = nullptr;       int ldc = 0;   // [M, Nout]
+  int M = 0, N = 0, K = 0;
+  const float* bias = nullptr;            // [N] fp32 or null
+  const void* residual = nullptr; int ldr = 0;
+  int act = ACT_NONE;
+  int swiglu = 0;
+  int out_f32 = 0;                        // C is float32 (no final rounding) when set
+  int force_bn = 0;                       // 0 = heuristic, else 32/64/128/256
+};
+
+// Returns cudaSuccess or an error; sets a message retrievable through sb_last_error().
+int gemm_launch(const GemmArgs& a, cudaStream_t stream);
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+// Counts one kernel launch and converts cudaGetLastError() into a return code (+ error string).
+int launch_ok();
+long long launch_count();
+int num_sms();
+
+}  // namespace sb

@@ -1,0 +1,411 @@
+// surya_b200 — persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M, Nout] = epilogue(A[M, K] @ W[N, K]^T)      (torch nn.Linear layout: both operands K-major)
+//
+// Replaces every cuBLAS call the reference makes through nn.Linear / 1x1 Conv2d on the hot path
+// (SURVEY.md §2.2 K1, K3, K5-K7, K9-K11).  Design:
+//   * one CTA per SM, persistent over a grouped tile raster (A/W tiles stay L2 resident);
+//   * warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, BK = 64 elements per stage);
+//   * warp 1 = MMA issuer: tcgen05.mma kind::f16, UMMA 128 x BN x 16, fp32 accumulators in TMEM,
+//     two accumulator buffers so the epilogue of tile i overlaps the main loop of tile i+1;
+//   * warp 2 = TMEM allocator; warps 4-7 = epilogue (tcgen05.ld -> bias/act/residual/SwiGLU -> global).
+// Rounding to the storage type happens exactly where eager PyTorch has an op boundary (after the
+// Linear, after the activation, after the residual add) so results track the reference path.
+#include "gemm.cuh"
+#include "sb_ptx.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <atomic>
+#include <mutex>
+
+namespace sb {
+
+struct GemmKParams {
+  int M, N, K;
+  void* C;
+  int ldc;
+  const float* bias;
+  const void* residual;
+  int ldr;
+  int act;
+  int swiglu;
+  int out_f32;
+  int group_m;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case ACT_GELU_ERF: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    case ACT_SILU: return x / (1.0f + expf(-x));
+    case ACT_HARDSWISH: return x * fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) / 6.0f;
+    case ACT_RELU: return fmaxf(x, 0.0f);
+    case ACT_GELU_TANH: {
+      const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+      float inner = k0 * (x + k1 * x * x * x);
+      return 0.5f * x * (1.0f + tanhf(inner));
+    }
+    default: return x;
+  }
+}
+
+__device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks, int gm, int& mb, int& nb) {
+  int per_group = gm * n_blocks;
+  int g = tile / per_group;
+  int first = g * gm;
+  int gsz = min(m_blocks - first, gm);
+  int r = tile - g * per_group;
+  mb = first + r % gsz;
+  nb = r / gsz;
+}
+
+template <typename T, int BN, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const GemmKParams p) {
+  constexpr int BM = 128, BK = 64;
+  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_blocks = (p.M + BM - 1) / BM;
+  const int n_blocks = (p.N + BN - 1) / BN;
+  const int k_blocks = (p.K + BK - 1) / BK;
+  const int num_tiles = m_blocks * n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int mb, nb;
+        tile_coords(tile, m_blocks, n_blocks, p.group_m, mb, nb);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sbp = sa + A_BYTES;
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          tma_load_2d(sa, &tma_a, &full_bar[s], kb * BK, mb * BM);
+          tma_load_2d(sbp, &tma_b, &full_bar[s], kb * BK, nb * BN);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(TypeInfo<T>::umma_fmt, BM, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t da = umma_desc_k128(sa);
+          const uint64_t db = umma_desc_k128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes (= 2 x 16B units) per UMMA_K step inside the 128B swizzle atom
+            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);
+        as ^= 1;
+        if (as == 0) aph ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int as = 0;
+    uint32_t aph = 0;
+    const bool vec_ok = (p.ldc % 8 == 0) && (!p.residual || p.ldr % 8 == 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int mb, nb;
+      tile_coords(tile, m_blocks, n_blocks, p.group_m, mb, nb);
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const int row = mb * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge lanes that skipped the previous chunk
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = nb * BN + c * 32;
+        if (col0 >= p.N) continue;
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (col0 + j < p.N) x[j] += __ldg(p.bias + col0 + j);
+          }
+        }
+        if (!row_ok) continue;
+        if (p.swiglu) {
+          // columns (2i, 2i+1) = (gate_i, up_i)
+          const int oc0 = col0 >> 1;
+          const int n_out = p.N >> 1;
+          T* crow = reinterpret_cast<T*>(p.C) + static_cast<size_t>(row) * p.ldc;
+          T o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float g = rnd<T>(x[2 * i]);
+            float u = rnd<T>(x[2 * i + 1]);
+            float sact = rnd<T>(apply_act(g, p.act));
+            o[i] = from_f<T>(sact * u);
+          }
+          if (vec_ok && oc0 + 16 <= n_out) {
+            uint4* dst = reinterpret_cast<uint4*>(crow + oc0);
+            const uint4* src = reinterpret_cast<const uint4*>(o);
+            dst[0] = src[0];
+            dst[1] = src[1];
+          } else {
+            for (int i = 0; i < 16; ++i)
+              if (oc0 + i < n_out) crow[oc0 + i] = o[i];
+          }
+        } else if (p.out_f32) {
+          float* crow = reinterpret_cast<float*>(p.C) + static_cast<size_t>(row) * p.ldc;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float y = apply_act(x[j], p.act);
+            if (col0 + j < p.N) crow[col0 + j] = y;
+          }
+        } else {
+          T* crow = reinterpret_cast<T*>(p.C) + static_cast<size_t>(row) * p.ldc;
+          const T* rrow = p.residual ? reinterpret_cast<const T*>(p.residual) + static_cast<size_t>(row) * p.ldr : nullptr;
+          const bool full = (col0 + 32 <= p.N) && vec_ok;
+          T r[32];
+          if (rrow) {
+            if (full) {
+              const uint4* src = reinterpret_cast<const uint4*>(rrow + col0);
+              uint4* dst = reinterpret_cast<uint4*>(r);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dst[i] = src[i];
+            } else {
+              for (int j = 0; j < 32; ++j) r[j] = (col0 + j < p.N) ? rrow[col0 + j] : from_f<T>(0.f);
+            }
+          }
+          T o[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float y = rnd<T>(x[j]);
+            if (p.act != ACT_NONE) y = rnd<T>(apply_act(y, p.act));
+            if (rrow) y = y + to_f<T>(r[j]);
+            o[j] = from_f<T>(y);
+          }
+          if (full) {
+            uint4* dst = reinterpret_cast<uint4*>(crow + col0);
+            const uint4* src = reinterpret_cast<const uint4*>(o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = src[i];
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) crow[col0 + j] = o[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      as ^= 1;
+      if (as == 0) aph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------------- host side
+static thread_local char g_err[512] = {0};
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+long long launch_count() { return g_launches.load(); }
+int launch_ok() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("kernel launch failed: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// 2-D K-major operand map: global [rows, K] with row stride ld (elements); box = 64 x box_rows; 128B swizzle.
+int make_tma_2d(CUtensorMap* map, int dtype, const void* base, int rows, int K, int ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return -1;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (static_cast<size_t>(ld) * 2) % 16 != 0) {
+    set_error("TMA operand must be 16B aligned with a 16B-multiple row pitch (ptr=%p ld=%d)", base, ld);
+    return -2;
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: %d (rows=%d K=%d ld=%d box_rows=%d)", (int)r, rows, K, ld, box_rows);
+    return -3;
+  }
+  return 0;
+}
+
+template <typename T, int BN, int STAGES>
+static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
+  constexpr uint32_t STAGE_BYTES = 128 * 64 * 2 + BN * 64 * 2;
+  constexpr size_t SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static bool attr_set = false;
+  auto kern = gemm_tn_kernel<T, BN, STAGES>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", SMEM, cudaGetErrorString(e));
+      return -10;
+    }
+    attr_set = true;
+  }
+  CUtensorMap ma, mb;
+  int rc = make_tma_2d(&ma, a.dtype, a.A, a.M, a.K, a.lda, 128);
+  if (rc) return rc;
+  rc = make_tma_2d(&mb, a.dtype, a.W, a.N, a.K, a.ldw, BN);
+  if (rc) return rc;
+  GemmKParams p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.C = a.C; p.ldc = a.ldc;
+  p.bias = a.bias;
+  p.residual = a.residual; p.ldr = a.ldr;
+  p.act = a.act; p.swiglu = a.swiglu; p.out_f32 = a.out_f32;
+  p.group_m = 8;
+  int m_blocks = (a.M + 127) / 128, n_blocks = (a.N + BN - 1) / BN;
+  int tiles = m_blocks * n_blocks;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, 256, SMEM, stream>>>(ma, mb, p);
+  return launch_ok();
+}
+
+template <typename T>
+static int launch_typed(const GemmArgs& a, cudaStream_t stream) {
+  int bn = a.force_bn;
+  if (bn == 0) {
+    // Largest tile that still yields about one wave of CTAs; small problems fall to narrower tiles so
+    // that more SMs stream the weight matrix.
+    const int sms = num_sms();
+    const int m_blocks = (a.M + 127) / 128;
+    bn = 32;
+    const int cands[4] = {256, 128, 64, 32};
+    for (int i = 0; i < 4; ++i) {
+      int nb = (a.N + cands[i] - 1) / cands[i];
+      if (m_blocks * nb >= (sms * 3) / 4 || i == 3) { bn = cands[i]; break; }
+    }
+    if (a.swiglu && bn < 32) bn = 32;
+  }
+  switch (bn) {
+    case 256: return launch_cfg<T, 256, 4>(a, stream);
+    case 128: return launch_cfg<T, 128, 6>(a, stream);
+    case 64: return launch_cfg<T, 64, 8>(a, stream);
+    case 32: return launch_cfg<T, 32, 8>(a, stream);
+    default: set_error("unsupported BN %d", bn); return -12;
+  }
+}
+
+int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) return 0;
+  if (a.swiglu && (a.N % 2 != 0)) {
+    set_error("swiglu epilogue needs an even N");
+    return -13;
+  }
+  if (a.dtype == DT_BF16) return launch_typed<__nv_bfloat16>(a, stream);
+  if (a.dtype == DT_F16) return launch_typed<__half>(a, stream);
+  set_error("unsupported dtype %d", a.dtype);
+  return -14;
+}
+
+}  // namespace sb

@@ -1,0 +1,423 @@
+// surya_b200 — row-wise / gather / rotary / head kernels (CUDA-core, HBM-bound; warp-shuffle reductions).
+//
+// Reference semantics (file:line relative to the reference checkout):
+//   rmsnorm            surya/common/surya/decoder/__init__.py:241-258, encoder/__init__.py:90-104
+//   rope_vision        surya/common/surya/encoder/__init__.py:188-199, 523-550
+//   rope_decoder       surya/common/surya/decoder/__init__.py:53-84, 346-361
+//   embed_splice       surya/common/surya/__init__.py:197-272
+//   argmax / score     surya/recognition/__init__.py:294-324
+//   bbox head          surya/common/surya/__init__.py:329
+#include "ops.cuh"
+#include "sb_ptx.cuh"
+
+namespace sb {
+
+// ------------------------------------------------------------------------------------------ rmsnorm
+// One warp per row. y = weight * T(x * rsqrt(mean(x^2) + eps)); optional row gather (src_rows).
+template <typename T>
+__global__ void rmsnorm_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ w, T* __restrict__ y, int ldy,
+                               int rows, int H, float eps, const int* __restrict__ src_rows) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  int srow = src_rows ? src_rows[row] : row;
+  const T* xr = x + static_cast<size_t>(srow) * ldx;
+  T* yr = y + static_cast<size_t>(row) * ldy;
+  float ss = 0.f;
+  const int nv = H >> 3;
+  for (int i = lane; i < nv; i += 32) {
+    uint4 u = *reinterpret_cast<const uint4*>(xr + i * 8);
+    const T* e = reinterpret_cast<const T*>(&u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float f = to_f<T>(e[j]);
+      ss += f * f;
+    }
+  }
+  for (int i = (nv << 3) + lane; i < H; i += 32) {
+    float f = to_f<T>(xr[i]);
+    ss += f * f;
+  }
+  ss = warp_sum(ss);
+  float inv = rsqrtf(ss / static_cast<float>(H) + eps);
+  for (int i = lane; i < nv; i += 32) {
+    uint4 u = *reinterpret_cast<const uint4*>(xr + i * 8);
+    uint4 wv = *reinterpret_cast<const uint4*>(w + i * 8);
+    const T* e = reinterpret_cast<const T*>(&u);
+    const T* we = reinterpret_cast<const T*>(&wv);
+    uint4 o;
+    T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float n = rnd<T>(to_f<T>(e[j]) * inv);
+      oe[j] = from_f<T>(to_f<T>(we[j]) * n);
+    }
+    *reinterpret_cast<uint4*>(yr + i * 8) = o;
+  }
+  for (int i = (nv << 3) + lane; i < H; i += 32) {
+    float n = rnd<T>(to_f<T>(xr[i]) * inv);
+    yr[i] = from_f<T>(to_f<T>(w[i]) * n);
+  }
+}
+
+int rmsnorm(int dtype, const void* x, int ldx, const void* w, void* y, int ldy, int rows, int H, float eps,
+            const int* src_rows, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  if (ldx % 8 || ldy % 8) { set_error("rmsnorm: row pitch must be a multiple of 8 elements"); return -1; }
+  int wpb = 4;
+  dim3 grid((rows + wpb - 1) / wpb), block(32 * wpb);
+  if (dtype == DT_BF16)
+    rmsnorm_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w,
+                                                         (__nv_bfloat16*)y, ldy, rows, H, eps, src_rows);
+  else
+    rmsnorm_kernel<__half><<<grid, block, 0, st>>>((const __half*)x, ldx, (const __half*)w, (__half*)y, ldy, rows, H,
+                                                  eps, src_rows);
+  return launch_ok();
+}
+
+// ------------------------------------------------------------------------------------------ gather + pad rows
+// dst[i, 0:K] = src[perm[i], 0:K] (converted from SrcT), dst[i, K:Kp] = 0.
+template <typename T, typename SrcT>
+__global__ void gather_pad_kernel(const SrcT* __restrict__ src, int lds, const int* __restrict__ perm,
+                                  T* __restrict__ dst, int ldd, int rows, int K, int Kp) {
+  int row = blockIdx.x;
+  if (row >= rows) return;
+  int s = perm ? perm[row] : row;
+  const SrcT* sr = src + static_cast<size_t>(s) * lds;
+  T* dr = dst + static_cast<size_t>(row) * ldd;
+  for (int i = threadIdx.x; i < Kp; i += blockDim.x) {
+    float v = 0.f;
+    if (i < K) {
+      if constexpr (sizeof(SrcT) == 4) v = static_cast<float>(sr[i]);
+      else v = to_f<SrcT>(sr[i]);
+    }
+    dr[i] = from_f<T>(v);
+  }
+}
+
+int gather_pad_rows(int dtype, const void* src, int src_is_f32, int lds, const int* perm, void* dst, int ldd, int rows,
+                    int K, int Kp, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  dim3 grid(rows), block(128);
+  if (dtype == DT_BF16) {
+    if (src_is_f32)
+      gather_pad_kernel<__nv_bfloat16, float><<<grid, block, 0, st>>>((const float*)src, lds, perm,
+                                                                      (__nv_bfloat16*)dst, ldd, rows, K, Kp);
+    else
+      gather_pad_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>(
+          (const __nv_bfloat16*)src, lds, perm, (__nv_bfloat16*)dst, ldd, rows, K, Kp);
+  } else {
+    if (src_is_f32)
+      gather_pad_kernel<__half, float><<<grid, block, 0, st>>>((const float*)src, lds, perm, (__half*)dst, ldd, rows,
+                                                               K, Kp);
+    else
+      gather_pad_kernel<__half, __half><<<grid, block, 0, st>>>((const __half*)src, lds, perm, (__half*)dst, ldd,
+                                                                rows, K, Kp);
+  }
+  return launch_ok();
+}
+
+// ------------------------------------------------------------------------------------------ vision 2-D RoPE
+// qkv row = [q(nh*d) | k(nh*d) | v(nh*d)]; rotates q and k in place, fp32 math, one rounding at the end.
+// freq index i < d/2: i < d/4 -> row_pos * inv_freq[i], else col_pos * inv_freq[i - d/4].
+template <typename T>
+__global__ void rope_vision_kernel(T* __restrict__ qkv, int ld, const int2* __restrict__ pos,
+                                   const float* __restrict__ inv_freq, int n_tok, int nh, int d) {
+  int tok = blockIdx.x;
+  if (tok >= n_tok) return;
+  const int half = d >> 1, quarter = d >> 2;
+  int2 p = pos[tok];
+  T* row = qkv + static_cast<size_t>(tok) * ld;
+  const int total = 2 * nh * half;  // (q|k) x heads x pairs
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    int i = idx % half;
+    int hh = idx / half;  // 0 .. 2*nh-1 (q heads then k heads; contiguous in memory)
+    float f = (i < quarter) ? static_cast<float>(p.x) * inv_freq[i] : static_cast<float>(p.y) * inv_freq[i - quarter];
+    float c = cosf(f), s = sinf(f);
+    T* h = row + hh * d;
+    float x1 = to_f<T>(h[i]), x2 = to_f<T>(h[i + half]);
+    float o1 = __fadd_rn(__fmul_rn(x1, c), __fmul_rn(-x2, s));
+    float o2 = __fadd_rn(__fmul_rn(x2, c), __fmul_rn(x1, s));
+    h[i] = from_f<T>(o1);
+    h[i + half] = from_f<T>(o2);
+  }
+}
+
+int rope_vision(int dtype, void* qkv, int ld, const int* pos_rc, const float* inv_freq, int n_tok, int nh, int d,
+                cudaStream_t st) {
+  if (n_tok <= 0) return 0;
+  dim3 grid(n_tok), block(128);
+  if (dtype == DT_BF16)
+    rope_vision_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((__nv_bfloat16*)qkv, ld, (const int2*)pos_rc, inv_freq,
+                                                             n_tok, nh, d);
+  else
+    rope_vision_kernel<__half><<<grid, block, 0, st>>>((__half*)qkv, ld, (const int2*)pos_rc, inv_freq, n_tok, nh, d);
+  return launch_ok();
+}
+
+// ------------------------------------------------------------------------------------------ decoder RoPE + KV append
+// qkv row = [q(nh*d) | k(nkv*d) | v(nkv*d)].  cos/sin are computed in fp32, cast to T, and the rotation is
+// evaluated in T arithmetic with three roundings (mul, mul, add) like the eager reference.  q and k are rotated
+// in place; rotated k and v are also written to the slot cache at index `pos`.
+template <typename T>
+__device__ __forceinline__ void rope_pair_T(float x1, float x2, float c, float s, float& o1, float& o2) {
+  // o1 = x1*c + (-x2)*s ; o2 = x2*c + x1*s   (each product and the sum rounded to T)
+  o1 = rnd<T>(rnd<T>(x1 * c) + rnd<T>(-x2 * s));
+  o2 = rnd<T>(rnd<T>(x2 * c) + rnd<T>(x1 * s));
+}
+
+template <typename T>
+__global__ void rope_kv_append_kernel(T* __restrict__ qkv, int ld, const int* __restrict__ tok_pos,
+                                      const int* __restrict__ tok_slot, const float* __restrict__ inv_freq,
+                                      T* __restrict__ kcache, T* __restrict__ vcache, int n_tok, int nh, int nkv,
+                                      int d, int s_max) {
+  int tok = blockIdx.x;
+  if (tok >= n_tok) return;
+  const int half = d >> 1;
+  const int pos = tok_pos[tok];
+  const int slot = tok_slot[tok];
+  T* row = qkv + static_cast<size_t>(tok) * ld;
+  const int n_rot = (nh + nkv) * half;
+  for (int idx = threadIdx.x; idx < n_rot; idx += blockDim.x) {
+    int i = idx % half;
+    int hh = idx / half;
+    float f = static_cast<float>(pos) * inv_freq[i];
+    float c = rnd<T>(cosf(f)), s = rnd<T>(sinf(f));
+    T* h = row + hh * d;
+    float x1 = to_f<T>(h[i]), x2 = to_f<T>(h[i + half]);
+    float o1, o2;
+    rope_pair_T<T>(x1, x2, c, s, o1, o2);
+    h[i] = from_f<T>(o1);
+    h[i + half] = from_f<T>(o2);
+    if (hh >= nh) {
+      int kvh = hh - nh;
+      T* kc = kcache + ((static_cast<size_t>(slot) * nkv + kvh) * s_max + pos) * d;
+      kc[i] = from_f<T>(o1);
+      kc[i + half] = from_f<T>(o2);
+    }
+  }
+  const T* vrow = row + (nh + nkv) * d;
+  for (int idx = threadIdx.x; idx < nkv * d; idx += blockDim.x) {
+    int kvh = idx / d, i = idx % d;
+    vcache[((static_cast<size_t>(slot) * nkv + kvh) * s_max + pos) * d + i] = vrow[idx];
+  }
+}
+
+int rope_kv_append(int dtype, void* qkv, int ld, const int* tok_pos, const int* tok_slot, const float* inv_freq,
+                   void* kcache, void* vcache, int n_tok, int nh, int nkv, int d, int s_max, cudaStream_t st) {
+  if (n_tok <= 0) return 0;
+  dim3 grid(n_tok), block(128);
+  if (dtype == DT_BF16)
+    rope_kv_append_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((__nv_bfloat16*)qkv, ld, tok_pos, tok_slot, inv_freq,
+                                                                (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, n_tok,
+                                                                nh, nkv, d, s_max);
+  else
+    rope_kv_append_kernel<__half><<<grid, block, 0, st>>>((__half*)qkv, ld, tok_pos, tok_slot, inv_freq,
+                                                         (__half*)kcache, (__half*)vcache, n_tok, nh, nkv, d, s_max);
+  return launch_ok();
+}
+
+// ------------------------------------------------------------------------------------------ embed + image splice
+// out[t] = tok_feat_row[t] >= 0 ? T( feat[tok_feat_row[t]] + T(h_embed[hidx] + w_embed[widx]) ) : embed[ids[t]]
+template <typename T>
+__global__ void embed_splice_kernel(const long long* __restrict__ ids, const int* __restrict__ feat_row,
+                                    const int* __restrict__ hidx, const int* __restrict__ widx,
+                                    const T* __restrict__ embed, const T* __restrict__ feat, int ldf,
+                                    const T* __restrict__ h_embed, const T* __restrict__ w_embed, T* __restrict__ out,
+                                    int ldo, int n_tok, int H) {
+  int t = blockIdx.x;
+  if (t >= n_tok) return;
+  T* o = out + static_cast<size_t>(t) * ldo;
+  int fr = feat_row ? feat_row[t] : -1;
+  if (fr >= 0) {
+    const T* f = feat + static_cast<size_t>(fr) * ldf;
+    const T* he = h_embed + static_cast<size_t>(hidx[t]) * H;
+    const T* we = w_embed + static_cast<size_t>(widx[t]) * H;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+      float pe = rnd<T>(to_f<T>(he[i]) + to_f<T>(we[i]));
+      o[i] = from_f<T>(to_f<T>(f[i]) + pe);
+    }
+  } else {
+    const T* e = embed + static_cast<size_t>(ids[t]) * H;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) o[i] = e[i];
+  }
+}
+
+int embed_splice(int dtype, const long long* ids, const int* feat_row, const int* hidx, const int* widx,
+                 const void* embed, const void* feat, int ldf, const void* h_embed, const void* w_embed, void* out,
+                 int ldo, int n_tok, int H, cudaStream_t st) {
+  if (n_tok <= 0) return 0;
+  dim3 grid(n_tok), block(128);
+  if (dtype == DT_BF16)
+    embed_splice_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(
+        ids, feat_row, hidx, widx, (const __nv_bfloat16*)embed, (const __nv_bfloat16*)feat, ldf,
+        (const __nv_bfloat16*)h_embed, (const __nv_bfloat16*)w_embed, (__nv_bfloat16*)out, ldo, n_tok, H);
+  else
+    embed_splice_kernel<__half><<<grid, block, 0, st>>>(ids, feat_row, hidx, widx, (const __half*)embed,
+                                                       (const __half*)feat, ldf, (const __half*)h_embed,
+                                                       (const __half*)w_embed, (__half*)out, ldo, n_tok, H);
+  return launch_ok();
+}
+
+// ------------------------------------------------------------------------------------------ greedy head
+// Per row: token = argmax(float(logits)) (first index on ties), score = max softmax = 1 / sum exp(l - max),
+// done = token in {eos, pad}; score forced to 0 when done; next input id = pad when done.
+template <typename T>
+__global__ void argmax_score_kernel(const T* __restrict__ logits, int ld, int V, long long* __restrict__ tok,
+                                    float* __restrict__ score, unsigned char* __restrict__ done,
+                                    long long* __restrict__ next_ids, int eos, int pad) {
+  int row = blockIdx.x;
+  const T* l = logits + static_cast<size_t>(row) * ld;
+  float m = -INFINITY;
+  int mi = 0x7fffffff;
+  float s = 0.f;  // running sum of exp(l - m)
+  const int nv = V >> 3;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    uint4 u = *reinterpret_cast<const uint4*>(l + i * 8);
+    const T* e = reinterpret_cast<const T*>(&u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = to_f<T>(e[j]);
+      if (v > m) {
+        s = s * __expf(m - v) + 1.f;
+        m = v;
+        mi = i * 8 + j;
+      } else {
+        s += __expf(v - m);
+      }
+    }
+  }
+  for (int i = (nv << 3) + threadIdx.x; i < V; i += blockDim.x) {
+    float v = to_f<T>(l[i]);
+    if (v > m) { s = s * __expf(m - v) + 1.f; m = v; mi = i; }
+    else s += __expf(v - m);
+  }
+  // block reduction of (m, mi, s)
+  __shared__ float sm[32];
+  __shared__ int si[32];
+  __shared__ float ss[32];
+  auto combine = [](float& m1, int& i1, float& s1, float m2, int i2, float s2) {
+    if (m2 > m1 || (m2 == m1 && i2 < i1)) {
+      s1 = s1 * __expf(m1 - m2) + s2;
+      m1 = m2;
+      i1 = i2;
+    } else {
+      s1 += s2 * __expf(m2 - m1);
+    }
+  };
+  if (m == -INFINITY) s = 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    int i2 = __shfl_xor_sync(0xffffffffu, mi, o);
+    float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    if (m2 != -INFINITY) {
+      if (m == -INFINITY) { m = m2; mi = i2; s = s2; }
+      else combine(m, mi, s, m2, i2, s2);
+    }
+  }
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sm[warp] = m; si[warp] = mi; ss[warp] = s; }
+  __syncthreads();
+  if (warp == 0) {
+    int nw = blockDim.x >> 5;
+    m = lane < nw ? sm[lane] : -INFINITY;
+    mi = lane < nw ? si[lane] : 0x7fffffff;
+    s = lane < nw ? ss[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+      int i2 = __shfl_xor_sync(0xffffffffu, mi, o);
+      float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      if (m2 != -INFINITY) {
+        if (m == -INFINITY) { m = m2; mi = i2; s = s2; }
+        else combine(m, mi, s, m2, i2, s2);
+      }
+    }
+    if (lane == 0) {
+      bool d = (mi == eos) || (mi == pad);
+      tok[row] = mi;
+      score[row] = d ? 0.f : 1.f / s;
+      if (done) done[row] = d ? 1 : 0;
+      if (next_ids) next_ids[row] = d ? pad : mi;
+    }
+  }
+}
+
+int argmax_score(int dtype, const void* logits, int ld, int rows, int V, long long* tok, float* score,
+                 unsigned char* done, long long* next_ids, int eos, int pad, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  if (ld % 8) { set_error("argmax_score: logits pitch must be a multiple of 8"); return -1; }
+  dim3 grid(rows), block(512);
+  if (dtype == DT_BF16)
+    argmax_score_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)logits, ld, V, tok, score, done,
+                                                              next_ids, eos, pad);
+  else
+    argmax_score_kernel<__half><<<grid, block, 0, st>>>((const __half*)logits, ld, V, tok, score, done, next_ids, eos,
+                                                       pad);
+  return launch_ok();
+}
+
+// ------------------------------------------------------------------------------------------ small dense head
+// out[r, o] = act(T(x[r] . w[o] + b[o])); one warp per (row, output).  Used for the 6-wide bbox head:
+// sig = T(sigmoid(T(lin))) ; box = trunc(float(sig) * bbox_size) as int64.
+template <typename T>
+__global__ void small_head_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ w, const T* __restrict__ b,
+                                  int rows, int H, int n_out, int sigmoid, float* __restrict__ out_f,
+                                  long long* __restrict__ out_box, float box_scale) {
+  int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (gw >= rows * n_out) return;
+  int r = gw / n_out, o = gw % n_out;
+  const T* xr = x + static_cast<size_t>(r) * ldx;
+  const T* wr = w + static_cast<size_t>(o) * H;
+  float acc = 0.f;
+  for (int i = lane; i < H; i += 32) acc += to_f<T>(xr[i]) * to_f<T>(wr[i]);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float v = rnd<T>(acc + (b ? to_f<T>(b[o]) : 0.f));
+    if (sigmoid) v = rnd<T>(1.f / (1.f + expf(-v)));
+    if (out_f) out_f[gw] = v;
+    if (out_box) out_box[gw] = static_cast<long long>(v * box_scale);
+  }
+}
+
+int small_head(int dtype, const void* x, int ldx, const void* w, const void* b, int rows, int H, int n_out,
+               int sigmoid, float* out_f, long long* out_box, float box_scale, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  int warps = rows * n_out;
+  dim3 grid((warps + 3) / 4), block(128);
+  if (dtype == DT_BF16)
+    small_head_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w,
+                                                            (const __nv_bfloat16*)b, rows, H, n_out, sigmoid, out_f,
+                                                            out_box, box_scale);
+  else
+    small_head_kernel<__half><<<grid, block, 0, st>>>((const __half*)x, ldx, (const __half*)w, (const __half*)b, rows,
+                                                     H, n_out, sigmoid, out_f, out_box, box_scale);
+  return launch_ok();
+}
+
+// ------------------------------------------------------------------------------------------ embedding rows
+template <typename T>
+__global__ void embed_rows_kernel(const long long* __restrict__ ids, const T* __restrict__ embed, T* __restrict__ out,
+                                  int ldo, int n, int H) {
+  int t = blockIdx.x;
+  if (t >= n) return;
+  const uint4* e = reinterpret_cast<const uint4*>(embed + static_cast<size_t>(ids[t]) * H);
+  uint4* o = reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * ldo);
+  for (int i = threadIdx.x; i < (H >> 3); i += blockDim.x) o[i] = e[i];
+}
+
+int embed_rows(int dtype, const long long* ids, const void* embed, void* out, int ldo, int n, int H, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (H % 8 || ldo % 8) { set_error("embed_rows: H and pitch must be multiples of 8"); return -1; }
+  dim3 grid(n), block(128);
+  if (dtype == DT_BF16)
+    embed_rows_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(ids, (const __nv_bfloat16*)embed, (__nv_bfloat16*)out, ldo,
+                                                            n, H);
+  else
+    embed_rows_kernel<__half><<<grid, block, 0, st>>>(ids, (const __half*)embed, (__half*)out, ldo, n, H);
+  return launch_ok();
+}
+
+}  // namespace sb

@@ -1,0 +1,58 @@
+// surya_b200 — host-side launchers for the non-GEMM kernels (ops.cu, attention.cu).
+#pragma once
+#include "gemm.cuh"
+
+namespace sb {
+
+int rmsnorm(int dtype, const void* x, int ldx, const void* w, void* y, int ldy, int rows, int H, float eps,
+            const int* src_rows, cudaStream_t st);
+int gather_pad_rows(int dtype, const void* src, int src_is_f32, int lds, const int* perm, void* dst, int ldd, int rows,
+                    int K, int Kp, cudaStream_t st);
+int rope_vision(int dtype, void* qkv, int ld, const int* pos_rc, const float* inv_freq, int n_tok, int nh, int d,
+                cudaStream_t st);
+int rope_kv_append(int dtype, void* qkv, int ld, const int* tok_pos, const int* tok_slot, const float* inv_freq,
+                   void* kcache, void* vcache, int n_tok, int nh, int nkv, int d, int s_max, cudaStream_t st);
+int embed_splice(int dtype, const long long* ids, const int* feat_row, const int* hidx, const int* widx,
+                 const void* embed, const void* feat, int ldf, const void* h_embed, const void* w_embed, void* out,
+                 int ldo, int n_tok, int H, cudaStream_t st);
+int argmax_score(int dtype, const void* logits, int ld, int rows, int V, long long* tok, float* score,
+                 unsigned char* done, long long* next_ids, int eos, int pad, cudaStream_t st);
+int small_head(int dtype, const void* x, int ldx, const void* w, const void* b, int rows, int H, int n_out,
+               int sigmoid, float* out_f, long long* out_box, float box_scale, cudaStream_t st);
+int embed_rows(int dtype, const long long* ids, const void* embed, void* out, int ldo, int n, int H, cudaStream_t st);
+
+// Variable-length (block-diagonal) attention over packed sequences, tensor-core (mma.sync) flash kernel.
+//   q/k/v: row-major token matrices with per-tensor row pitch and column offset of head 0; head h at col_off + h*d
+//   seq_start[s], seq_len[s]: token range of sequence s (same for q and k); causal: key j <= query i (in-sequence)
+//   n_kv_heads <= n_heads (GQA: kv head = h / (n_heads / n_kv_heads)); out[token, h*d + c], pitch ldo.
+struct AttnArgs {
+  int dtype = DT_BF16;
+  const void* q = nullptr; int ldq = 0;
+  const void* k = nullptr; int ldk = 0;
+  const void* v = nullptr; int ldv = 0;
+  void* out = nullptr;     int ldo = 0;
+  const int* seq_start = nullptr;
+  const int* seq_len = nullptr;
+  int n_seq = 0, max_len = 0;
+  int n_heads = 0, n_kv_heads = 0, head_dim = 0;
+  int causal = 0;
+  float scale = 1.f;
+};
+int attn_varlen(const AttnArgs& a, cudaStream_t st);
+
+// Single-token decode attention over the slot KV cache, fused with RoPE(q,k) and the in-place cache append.
+//   qkv[b] = [q(nh*d) | k(nkv*d) | v(nkv*d)] for batch row b; slot[b], pos[b] (= number of cached tokens) on device.
+//   cache layout: [slot][kv_head][s_max][d]; writes rotated k / v at index pos[b], then attends over 0..pos[b].
+struct DecodeAttnArgs {
+  int dtype = DT_BF16;
+  const void* qkv = nullptr; int ld = 0;
+  void* kcache = nullptr; void* vcache = nullptr;
+  const int* slot = nullptr; const int* pos = nullptr;
+  const float* inv_freq = nullptr;
+  void* out = nullptr; int ldo = 0;
+  int batch = 0, n_heads = 0, n_kv_heads = 0, head_dim = 0, s_max = 0;
+  float scale = 1.f;
+};
+int decode_attn(const DecodeAttnArgs& a, cudaStream_t st);
+
+}  // namespace sb

@@ -1,0 +1,153 @@
+"""Torch-tensor wrappers over the op-level C ABI (include/surya_b200.h).
+
+torch is used for device memory and streams only; every function launches hand-written sm_100a kernels from
+libsurya_b200.so on torch's current CUDA stream and raises if the library or a GPU is missing.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import c_float, c_int, check, ptr, stream_ptr
+
+ACT = {"none": 0, "gelu": 1, "gelu_erf": 1, "silu": 2, "hardswish": 3, "relu": 4, "gelu_tanh": 5}
+
+
+def dt_code(dtype: torch.dtype) -> int:
+    if dtype == torch.bfloat16:
+        return 0
+    if dtype == torch.float16:
+        return 1
+    raise _lib.SuryaB200Error(f"surya_b200 kernels compute in bf16 or fp16, got {dtype}")
+
+
+def _rowmajor(t: torch.Tensor) -> int:
+    assert t.dim() == 2 and t.stride(1) == 1, "expected a row-major 2-D tensor"
+    return t.stride(0)
+
+
+def gemm(a, w, bias=None, residual=None, act="none", swiglu=False, out=None, out_f32=False, force_bn=0):
+    """out[M, Nout] = epi(a[M,K] @ w[N,K]^T); bias fp32 [N]; see sb_gemm."""
+    lib = _lib.load()
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    n_out = N // 2 if swiglu else N
+    if out is None:
+        out = torch.empty((M, n_out), device=a.device, dtype=torch.float32 if out_f32 else a.dtype)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() >= N
+    check(lib.sb_gemm(dt_code(a.dtype), ptr(a), c_int(_rowmajor(a)), ptr(w), c_int(_rowmajor(w)), ptr(out),
+                      c_int(_rowmajor(out)), c_int(M), c_int(N), c_int(K), ptr(bias), ptr(residual),
+                      c_int(_rowmajor(residual) if residual is not None else 0), c_int(ACT[act]),
+                      c_int(1 if swiglu else 0), c_int(1 if out_f32 else 0), c_int(force_bn), stream_ptr()), "sb_gemm")
+    return out
+
+
+def rmsnorm(x, w, eps=1e-6, src_rows=None, out=None):
+    lib = _lib.load()
+    rows = x.shape[0] if src_rows is None else src_rows.numel()
+    H = x.shape[1]
+    if out is None:
+        out = torch.empty((rows, H), device=x.device, dtype=x.dtype)
+    check(lib.sb_rmsnorm(dt_code(x.dtype), ptr(x), c_int(_rowmajor(x)), ptr(w), ptr(out), c_int(_rowmajor(out)),
+                         c_int(rows), c_int(H), c_float(eps), ptr(src_rows), stream_ptr()), "sb_rmsnorm")
+    return out
+
+
+def gather_pad_rows(src, perm, Kp, dtype):
+    lib = _lib.load()
+    rows = src.shape[0] if perm is None else perm.numel()
+    K = src.shape[1]
+    out = torch.empty((rows, Kp), device=src.device, dtype=dtype)
+    check(lib.sb_gather_pad_rows(dt_code(dtype), ptr(src), c_int(1 if src.dtype == torch.float32 else 0),
+                                 c_int(_rowmajor(src)), ptr(perm), ptr(out), c_int(Kp), c_int(rows), c_int(K),
+                                 c_int(Kp), stream_ptr()), "sb_gather_pad_rows")
+    return out
+
+
+def rope_vision_(qkv, pos_rc, inv_freq, nh, d):
+    lib = _lib.load()
+    check(lib.sb_rope_vision(dt_code(qkv.dtype), ptr(qkv), c_int(_rowmajor(qkv)), ptr(pos_rc), ptr(inv_freq),
+                             c_int(qkv.shape[0]), c_int(nh), c_int(d), stream_ptr()), "sb_rope_vision")
+    return qkv
+
+
+def rope_kv_append_(qkv, tok_pos, tok_slot, inv_freq, kcache, vcache, nh, nkv, d):
+    lib = _lib.load()
+    s_max = kcache.shape[2]
+    check(lib.sb_rope_kv_append(dt_code(qkv.dtype), ptr(qkv), c_int(_rowmajor(qkv)), ptr(tok_pos), ptr(tok_slot),
+                                ptr(inv_freq), ptr(kcache), ptr(vcache), c_int(qkv.shape[0]), c_int(nh), c_int(nkv),
+                                c_int(d), c_int(s_max), stream_ptr()), "sb_rope_kv_append")
+    return qkv
+
+
+def attn_varlen(q, k, v, seq_start, seq_len, max_len, n_heads, n_kv_heads, head_dim, causal, scale, out=None):
+    """q/k/v are 2-D row-major *views* whose column 0 is head 0 (e.g. qkv[:, 0:H], qkv[:, H:2H], ...)."""
+    lib = _lib.load()
+    n_tok = q.shape[0]
+    if out is None:
+        out = torch.empty((n_tok, n_heads * head_dim), device=q.device, dtype=q.dtype)
+    check(lib.sb_attn_varlen(dt_code(q.dtype), ptr(q), c_int(q.stride(0)), ptr(k), c_int(k.stride(0)), ptr(v),
+                             c_int(v.stride(0)), ptr(out), c_int(out.stride(0)), ptr(seq_start), ptr(seq_len),
+                             c_int(seq_start.numel()), c_int(max_len), c_int(n_heads), c_int(n_kv_heads),
+                             c_int(head_dim), c_int(1 if causal else 0), c_float(scale), stream_ptr()),
+          "sb_attn_varlen")
+    return out
+
+
+def decode_attn(qkv, kcache, vcache, slot, pos, inv_freq, n_heads, n_kv_heads, head_dim, scale, out=None):
+    lib = _lib.load()
+    B = qkv.shape[0]
+    if out is None:
+        out = torch.empty((B, n_heads * head_dim), device=qkv.device, dtype=qkv.dtype)
+    check(lib.sb_decode_attn(dt_code(qkv.dtype), ptr(qkv), c_int(_rowmajor(qkv)), ptr(kcache), ptr(vcache), ptr(slot),
+                             ptr(pos), ptr(inv_freq), ptr(out), c_int(_rowmajor(out)), c_int(B), c_int(n_heads),
+                             c_int(n_kv_heads), c_int(head_dim), c_int(kcache.shape[2]), c_float(scale),
+                             stream_ptr()), "sb_decode_attn")
+    return out
+
+
+def embed_splice(ids, feat_row, hidx, widx, embed, feat, h_embed, w_embed):
+    lib = _lib.load()
+    n, H = ids.numel(), embed.shape[1]
+    out = torch.empty((n, H), device=embed.device, dtype=embed.dtype)
+    check(lib.sb_embed_splice(dt_code(embed.dtype), ptr(ids), ptr(feat_row), ptr(hidx), ptr(widx), ptr(embed),
+                              ptr(feat), c_int(_rowmajor(feat) if feat is not None else 0), ptr(h_embed), ptr(w_embed),
+                              ptr(out), c_int(H), c_int(n), c_int(H), stream_ptr()), "sb_embed_splice")
+    return out
+
+
+def embed_rows(ids, embed):
+    lib = _lib.load()
+    n, H = ids.numel(), embed.shape[1]
+    out = torch.empty((n, H), device=embed.device, dtype=embed.dtype)
+    check(lib.sb_embed_rows(dt_code(embed.dtype), ptr(ids), ptr(embed), ptr(out), c_int(H), c_int(n), c_int(H),
+                            stream_ptr()), "sb_embed_rows")
+    return out
+
+
+def argmax_score(logits, eos, pad):
+    lib = _lib.load()
+    rows, V = logits.shape
+    dev = logits.device
+    tok = torch.empty(rows, device=dev, dtype=torch.int64)
+    score = torch.empty(rows, device=dev, dtype=torch.float32)
+    done = torch.empty(rows, device=dev, dtype=torch.uint8)
+    nxt = torch.empty(rows, device=dev, dtype=torch.int64)
+    check(lib.sb_argmax_score(dt_code(logits.dtype), ptr(logits), c_int(_rowmajor(logits)), c_int(rows), c_int(V),
+                              ptr(tok), ptr(score), ptr(done), ptr(nxt), c_int(eos), c_int(pad), stream_ptr()),
+          "sb_argmax_score")
+    return tok, score, done, nxt
+
+
+def small_head(x, w, b, sigmoid=True, box_scale=None):
+    lib = _lib.load()
+    rows, H = x.shape
+    n_out = w.shape[0]
+    out_f = torch.empty((rows, n_out), device=x.device, dtype=torch.float32)
+    out_box = torch.empty((rows, n_out), device=x.device, dtype=torch.int64) if box_scale is not None else None
+    check(lib.sb_small_head(dt_code(x.dtype), ptr(x), c_int(_rowmajor(x)), ptr(w), ptr(b), c_int(rows), c_int(H),
+                            c_int(n_out), c_int(1 if sigmoid else 0), ptr(out_f), ptr(out_box),
+                            c_float(box_scale if box_scale is not None else 0.0), stream_ptr()), "sb_small_head")
+    return out_f, out_box

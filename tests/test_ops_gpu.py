@@ -1,0 +1,318 @@
+"""Kernel-level parity (GPU): each hand-written kernel vs a plain PyTorch fp32 restatement of the same op
+with the storage-dtype roundings at the eager op boundaries.  Runs through the C ABI (ctypes)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DT = [torch.bfloat16, torch.float16]
+
+
+def _ulp(dtype):
+    return 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+
+
+def _close(got, ref, dtype, ulps=2.0, what=""):
+    got = got.float()
+    ref = ref.float()
+    tol = ulps * _ulp(dtype) * ref.abs().clamp(min=1.0)
+    bad = (got - ref).abs() > tol
+    frac = bad.float().mean().item()
+    assert frac == 0.0, f"{what}: {bad.sum().item()} / {bad.numel()} beyond {ulps} ulp, max abs err {(got - ref).abs().max().item():.4g}"
+
+
+def _act_ref(x, act):
+    if act == "none":
+        return x
+    if act == "gelu":
+        return torch.nn.functional.gelu(x)
+    if act == "silu":
+        return torch.nn.functional.silu(x)
+    if act == "hardswish":
+        return torch.nn.functional.hardswish(x)
+    if act == "relu":
+        return torch.relu(x)
+    if act == "gelu_tanh":
+        return torch.nn.functional.gelu(x, approximate="tanh")
+    raise ValueError(act)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize(
+    "M,N,K,bn",
+    [
+        (128, 256, 64, 256), (128, 128, 128, 128), (256, 64, 1280, 64), (200, 96, 592, 32),
+        (1000, 1280, 592, 0), (640, 3840, 1280, 0), (256, 1280, 3456, 0), (333, 520, 1280, 128),
+        (4096, 1280, 1280, 256),
+    ],
+)
+def test_gemm_plain(built_lib, dtype, M, N, K, bn):
+    from surya_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(dtype)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(dtype)
+    out = ops.gemm(a, w, force_bn=bn)
+    torch.cuda.synchronize()
+    ref = (a.float() @ w.float().t()).to(dtype)
+    _close(out, ref, dtype, what=f"gemm {M}x{N}x{K} bn={bn}")
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("act", ["none", "gelu", "silu", "hardswish", "relu", "gelu_tanh"])
+def test_gemm_epilogue(built_lib, dtype, act):
+    from surya_b200 import ops
+
+    M, N, K = 300, 392, 320
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a = (torch.randn(M, K, device="cuda", generator=g)).to(dtype)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.08).to(dtype)
+    bias = torch.randn(N, device="cuda", generator=g).to(dtype).float()
+    res = torch.randn(M, N, device="cuda", generator=g).to(dtype)
+    out = ops.gemm(a, w, bias=bias, residual=res, act=act)
+    torch.cuda.synchronize()
+    lin = (a.float() @ w.float().t() + bias).to(dtype)
+    y = _act_ref(lin.float(), act).to(dtype) if act != "none" else lin
+    ref = (y.float() + res.float()).to(dtype)
+    _close(out, ref, dtype, ulps=3.0, what=f"gemm epilogue {act}")
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_gemm_swiglu(built_lib, dtype):
+    from surya_b200 import ops
+
+    M, I, K = 260, 216, 256  # N = 2*I interleaved
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+    wg = (torch.randn(I, K, device="cuda", generator=g) * 0.08).to(dtype)
+    wu = (torch.randn(I, K, device="cuda", generator=g) * 0.08).to(dtype)
+    bg = torch.randn(I, device="cuda", generator=g).to(dtype).float()
+    bu = torch.randn(I, device="cuda", generator=g).to(dtype).float()
+    w = torch.stack([wg, wu], dim=1).reshape(2 * I, K).contiguous()
+    b = torch.stack([bg, bu], dim=1).reshape(2 * I).contiguous()
+    out = ops.gemm(a, w, bias=b, act="silu", swiglu=True)
+    torch.cuda.synchronize()
+    gate = (a.float() @ wg.float().t() + bg).to(dtype)
+    up = (a.float() @ wu.float().t() + bu).to(dtype)
+    ref = (torch.nn.functional.silu(gate.float()).to(dtype).float() * up.float()).to(dtype)
+    _close(out, ref, dtype, ulps=3.0, what="swiglu")
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_gemm_f32_out(built_lib, dtype):
+    from surya_b200 import ops
+
+    M, N, K = 130, 200, 192
+    g = torch.Generator(device="cuda").manual_seed(9)
+    a = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.1).to(dtype)
+    out = ops.gemm(a, w, out_f32=True)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t()
+    assert (out - ref).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_rmsnorm(built_lib, dtype):
+    from surya_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = (torch.randn(77, 1280, device="cuda", generator=g) * 3).to(dtype)
+    w = (1 + 0.1 * torch.randn(1280, device="cuda", generator=g)).to(dtype)
+    out = ops.rmsnorm(x, w, eps=1e-6)
+    xf = x.float()
+    n = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).to(dtype)
+    ref = w * n
+    _close(out, ref, dtype, ulps=1.01, what="rmsnorm")
+    rows = torch.tensor([5, 0, 76, 5], device="cuda", dtype=torch.int32)
+    out2 = ops.rmsnorm(x, w, eps=1e-6, src_rows=rows)
+    _close(out2, ref[rows.long()], dtype, ulps=1.01, what="rmsnorm gather")
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_gather_pad(built_lib, dtype):
+    from surya_b200 import ops
+
+    src = torch.randn(64, 588, device="cuda")
+    perm = torch.randperm(64, device="cuda").to(torch.int32)
+    out = ops.gather_pad_rows(src, perm, 592, dtype)
+    ref = torch.zeros(64, 592, device="cuda", dtype=dtype)
+    ref[:, :588] = src[perm.long()].to(dtype)
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_rope_vision(built_lib, dtype):
+    from surya_b200 import ops
+
+    nh, d, n = 4, 80, 50
+    g = torch.Generator(device="cuda").manual_seed(2)
+    qkv = torch.randn(n, 3 * nh * d, device="cuda", generator=g).to(dtype)
+    pos = torch.stack([torch.arange(n, device="cuda") % 7, torch.arange(n, device="cuda") % 13], 1).to(torch.int32).contiguous()
+    inv_freq = 1.0 / (10000.0 ** (torch.arange(0, d // 2, 2, dtype=torch.float) / (d // 2)))
+    inv_freq = inv_freq.cuda()
+    ref_in = qkv.clone()
+    ops.rope_vision_(qkv, pos, inv_freq, nh, d)
+    freqs = torch.cat([pos[:, 0:1].float() * inv_freq[None], pos[:, 1:2].float() * inv_freq[None]], -1)  # [n, d/2]
+    emb = torch.cat([freqs, freqs], -1)
+    cos, sin = emb.cos()[:, None, :], emb.sin()[:, None, :]
+
+    def rot(x):
+        x1, x2 = x[..., : d // 2], x[..., d // 2:]
+        return torch.cat([-x2, x1], -1)
+
+    qk = ref_in[:, : 2 * nh * d].reshape(n, 2 * nh, d).float()
+    ref_qk = (qk * cos + rot(qk) * sin).to(dtype).reshape(n, -1)
+    _close(qkv[:, : 2 * nh * d], ref_qk, dtype, ulps=1.01, what="rope_vision")
+    assert torch.equal(qkv[:, 2 * nh * d:], ref_in[:, 2 * nh * d:])
+
+
+def _attn_ref(q, k, v, lens, causal, scale, group):
+    # q [T, nh, d], k/v [T, nkv, d] fp32; block-diagonal by lens
+    outs = []
+    s = 0
+    for L in lens:
+        qq, kk, vv = q[s:s + L], k[s:s + L], v[s:s + L]
+        kk = kk.repeat_interleave(group, dim=1)
+        vv = vv.repeat_interleave(group, dim=1)
+        sc = torch.einsum("qhd,khd->hqk", qq, kk) * scale
+        if causal:
+            mask = torch.ones(L, L, device=q.device, dtype=torch.bool).tril()
+            sc = sc.masked_fill(~mask, float("-inf"))
+        p = sc.softmax(-1)
+        outs.append(torch.einsum("hqk,khd->qhd", p, vv))
+        s += L
+    return torch.cat(outs, 0)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("d,nh,nkv,causal,lens", [
+    (80, 4, 4, False, [32, 32, 64, 17, 160, 1]),
+    (80, 8, 2, True, [46, 46, 5, 130, 64]),
+    (64, 4, 1, True, [100, 3]),
+    (128, 2, 2, False, [70, 200]),
+    (32, 4, 4, False, [64, 64, 9]),
+])
+def test_attn_varlen(built_lib, dtype, d, nh, nkv, causal, lens):
+    from surya_b200 import ops
+
+    T = sum(lens)
+    g = torch.Generator(device="cuda").manual_seed(d + nh)
+    width = (nh + 2 * nkv) * d
+    qkv = torch.randn(T, width, device="cuda", generator=g).to(dtype)
+    q, k, v = qkv[:, : nh * d], qkv[:, nh * d: (nh + nkv) * d], qkv[:, (nh + nkv) * d:]
+    starts = torch.tensor([sum(lens[:i]) for i in range(len(lens))], device="cuda", dtype=torch.int32)
+    lens_t = torch.tensor(lens, device="cuda", dtype=torch.int32)
+    scale = d ** -0.5
+    out = ops.attn_varlen(q, k, v, starts, lens_t, max(lens), nh, nkv, d, causal, scale)
+    torch.cuda.synchronize()
+    ref = _attn_ref(q.float().reshape(T, nh, d), k.float().reshape(T, nkv, d), v.float().reshape(T, nkv, d), lens,
+                    causal, scale, nh // nkv).reshape(T, nh * d)
+    err = (out.float() - ref).abs().max().item()
+    assert err < (0.03 if dtype == torch.bfloat16 else 0.005), f"attn_varlen max err {err}"
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("d,nh,nkv", [(80, 16, 4), (64, 8, 8), (128, 8, 1)])
+def test_decode_attn_and_rope_append(built_lib, dtype, d, nh, nkv):
+    from surya_b200 import ops
+
+    B, slots, s_max = 5, 8, 256
+    g = torch.Generator(device="cuda").manual_seed(d)
+    kc = torch.zeros(slots, nkv, s_max, d, device="cuda", dtype=dtype)
+    vc = torch.zeros_like(kc)
+    inv_freq = (1.0 / (10000.0 ** (torch.arange(0, d, 2, dtype=torch.float) / d))).cuda()
+    width = (nh + 2 * nkv) * d
+    # prefill: sequences with different lengths in slots 1..B via rope_kv_append
+    lens = [46, 7, 100, 1, 63]
+    slot_ids = [1, 3, 0, 7, 5]
+    tok_pos = torch.tensor([p for L in lens for p in range(L)], device="cuda", dtype=torch.int32)
+    tok_slot = torch.tensor([s for L, s in zip(lens, slot_ids) for _ in range(L)], device="cuda", dtype=torch.int32)
+    Tn = sum(lens)
+    qkv = torch.randn(Tn, width, device="cuda", generator=g).to(dtype)
+    raw = qkv.clone()
+    ops.rope_kv_append_(qkv, tok_pos, tok_slot, inv_freq, kc, vc, nh, nkv, d)
+
+    def rope_T(x, pos):  # x [n, heads, d] in dtype; 3-rounding reference
+        freqs = pos[:, None].float() * inv_freq[None]
+        emb = torch.cat([freqs, freqs], -1)
+        cos, sin = emb.cos().to(dtype)[:, None, :], emb.sin().to(dtype)[:, None, :]
+        x1, x2 = x[..., : d // 2], x[..., d // 2:]
+        rot = torch.cat([-x2, x1], -1)
+        return (x * cos) + (rot * sin)
+
+    qk_ref = rope_T(raw[:, : (nh + nkv) * d].reshape(Tn, nh + nkv, d), tok_pos)
+    _close(qkv[:, : (nh + nkv) * d], qk_ref.reshape(Tn, -1), dtype, ulps=1.01, what="rope_kv_append q,k")
+    # cache contents
+    off = 0
+    for L, s in zip(lens, slot_ids):
+        kref = qk_ref[off:off + L, nh:, :].permute(1, 0, 2)
+        vref = raw[off:off + L, (nh + nkv) * d:].reshape(L, nkv, d).permute(1, 0, 2)
+        _close(kc[s, :, :L], kref, dtype, ulps=1.01, what="kcache")
+        assert torch.equal(vc[s, :, :L], vref)
+        off += L
+    # decode step
+    slot = torch.tensor(slot_ids, device="cuda", dtype=torch.int32)
+    pos = torch.tensor(lens, device="cuda", dtype=torch.int32)
+    qkv1 = torch.randn(B, width, device="cuda", generator=g).to(dtype)
+    out = ops.decode_attn(qkv1, kc, vc, slot, pos, inv_freq, nh, nkv, d, d ** -0.5)
+    torch.cuda.synchronize()
+    qk1 = rope_T(qkv1[:, : (nh + nkv) * d].reshape(B, nh + nkv, d), pos)
+    group = nh // nkv
+    for b in range(B):
+        L, s = lens[b], slot_ids[b]
+        _close(kc[s, :, L], qk1[b, nh:], dtype, ulps=1.01, what="decode k append")
+        assert torch.equal(vc[s, :, L], qkv1[b, (nh + nkv) * d:].reshape(nkv, d))
+        K = kc[s, :, : L + 1].float().repeat_interleave(group, 0)  # [nh, L+1, d]
+        V = vc[s, :, : L + 1].float().repeat_interleave(group, 0)
+        q = qk1[b, :nh].float()  # [nh, d]
+        sc = torch.einsum("hd,hkd->hk", q, K) * d ** -0.5
+        ref = torch.einsum("hk,hkd->hd", sc.softmax(-1), V).reshape(-1)
+        err = (out[b].float() - ref).abs().max().item()
+        assert err < (0.03 if dtype == torch.bfloat16 else 0.005), f"decode_attn row {b} err {err}"
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_embed_splice_and_heads(built_lib, dtype):
+    from surya_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    V, H = 1000, 256
+    embed = torch.randn(V, H, device="cuda", generator=g).to(dtype)
+    feat = torch.randn(20, H, device="cuda", generator=g).to(dtype)
+    he = torch.randn(64, H, device="cuda", generator=g).to(dtype)
+    we = torch.randn(64, H, device="cuda", generator=g).to(dtype)
+    ids = torch.tensor([3, 3, 3, 10, 999, 3], device="cuda", dtype=torch.int64)
+    fr = torch.tensor([4, 0, 19, -1, -1, 7], device="cuda", dtype=torch.int32)
+    hi = torch.tensor([0, 63, 5, 0, 0, 9], device="cuda", dtype=torch.int32)
+    wi = torch.tensor([1, 2, 3, 0, 0, 63], device="cuda", dtype=torch.int32)
+    out = ops.embed_splice(ids, fr, hi, wi, embed, feat, he, we)
+    ref = embed[ids].clone()
+    for t in [0, 1, 2, 5]:
+        ref[t] = feat[fr[t]] + (he[hi[t]] + we[wi[t]])
+    assert torch.equal(out, ref)
+    assert torch.equal(ops.embed_rows(ids, embed), embed[ids])
+
+    logits = (torch.randn(9, 65792, device="cuda", generator=g) * 2).to(dtype)
+    logits[2, 1] = 50.0   # eos
+    logits[4, 100] = logits[4, 200] = 40.0  # tie -> first index
+    tok, score, done, nxt = ops.argmax_score(logits, eos=1, pad=2)
+    lf = logits.float()
+    assert torch.equal(tok, lf.argmax(-1))
+    ref_score = lf.softmax(-1).max(-1).values
+    ref_done = (tok == 1) | (tok == 2)
+    assert torch.equal(done.bool(), ref_done)
+    assert torch.allclose(score, ref_score.masked_fill(ref_done, 0), rtol=1e-4, atol=1e-6)
+    assert torch.equal(nxt, torch.where(ref_done, torch.full_like(tok, 2), tok))
+    assert tok[4].item() == 100
+
+    x = torch.randn(9, H, device="cuda", generator=g).to(dtype)
+    w = (torch.randn(6, H, device="cuda", generator=g) * 0.1).to(dtype)
+    b = torch.randn(6, device="cuda", generator=g).to(dtype)
+    sig, box = ops.small_head(x, w, b, sigmoid=True, box_scale=1025.0)
+    lin = (x.float() @ w.float().t() + b.float()).to(dtype)
+    ref_sig = torch.sigmoid(lin.float()).to(dtype).float()
+    assert (sig - ref_sig).abs().max().item() <= 2 * _ulp(dtype)
+    assert (box - (sig * 1025.0).to(torch.int64)).abs().max().item() == 0
