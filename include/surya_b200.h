@@ -90,6 +90,92 @@ int sb_argmax_score(int dtype, const void* logits, int ld, int rows, int V, long
 int sb_small_head(int dtype, const void* x, int ldx, const void* w, const void* b, int rows, int H, int n_out,
                   int sigmoid, float* out_f, long long* out_box, float box_scale, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------ recognition engine
+ * Replaces SuryaModel.forward (surya/common/surya/__init__.py:274-338) as driven by RecognitionPredictor.prefill /
+ * decode (surya/recognition/__init__.py:326-352, 354-471) and the ContinuousBatchingCache
+ * (surya/recognition/cache.py:7-105): the engine owns a slot-indexed KV cache [layer][slot][kv_head][s_max][d];
+ * sequences are processed ragged (no left padding), which is observationally equivalent because RoPE uses
+ * per-row position_ids.  All tensor/array pointers are DEVICE pointers unless named *_host. */
+typedef struct sb_rec_engine sb_rec_engine;
+
+typedef struct {
+  int dtype;                 /* SB_DT_BF16 / SB_DT_F16 */
+  /* vision tower (surya/common/surya/encoder/config.py:16-34) */
+  int enc_depth, enc_hidden, enc_heads, enc_inter, enc_inter_pad;
+  int patch_dim, patch_dim_pad, merge_unit /* spatial_merge_size^2 */, enc_out_hidden;
+  unsigned int fullatt_mask; /* bit i set -> block i attends per image, else per window */
+  /* decoder (surya/common/surya/decoder/config.py:30-49) */
+  int dec_layers, dec_hidden, dec_heads, dec_kv_heads, dec_head_dim, dec_inter, dec_inter_pad;
+  float rms_eps;
+  int vocab, eos_id, pad_id;
+  float bbox_size;
+  /* capacities */
+  int max_slots, s_max, max_patches, max_tokens, max_seqs;
+} sb_rec_config;
+
+/* Weight table: device pointers in the order given by the SB_RW_* indices (16-bit weights in cfg.dtype unless
+ * noted fp32).  Per-layer entries are strided: index = base + layer * stride + k. */
+enum {
+  SB_RW_PATCH_W = 0,      /* [enc_hidden, patch_dim_pad] */
+  SB_RW_MERGER_LN,        /* [enc_hidden] */
+  SB_RW_MERGER_W0, SB_RW_MERGER_B0 /* fp32 */, SB_RW_MERGER_W2, SB_RW_MERGER_B2 /* fp32 */,
+  SB_RW_ENC_INV_FREQ,     /* fp32 [head_dim/4] */
+  SB_RW_DEC_NORM,         /* [dec_hidden] */
+  SB_RW_EMBED,            /* [vocab, dec_hidden]  (tied lm_head weight) */
+  SB_RW_LM_BIAS,          /* fp32 [vocab] */
+  SB_RW_BBOX_W, SB_RW_BBOX_B, /* [6, dec_hidden], [6] */
+  SB_RW_H_EMBED, SB_RW_W_EMBED, /* [enc_size, dec_hidden] */
+  SB_RW_DEC_INV_FREQ,     /* fp32 [head_dim/2] */
+  SB_RW_ENC_BASE,         /* first per-block entry of the vision tower */
+  SB_RW_COUNT_FIXED = SB_RW_ENC_BASE
+};
+enum { /* per vision block */
+  SB_RWE_NORM1 = 0, SB_RWE_QKV_W, SB_RWE_QKV_B /* fp32 */, SB_RWE_PROJ_W, SB_RWE_PROJ_B /* fp32 */, SB_RWE_NORM2,
+  SB_RWE_GU_W /* [2*inter_pad, hidden] gate/up interleaved */, SB_RWE_GU_B /* fp32 */, SB_RWE_DOWN_W /* [hidden, inter_pad] */,
+  SB_RWE_DOWN_B /* fp32 */, SB_RWE_STRIDE
+};
+enum { /* per decoder layer (base = SB_RW_ENC_BASE + enc_depth * SB_RWE_STRIDE) */
+  SB_RWD_IN_NORM = 0, SB_RWD_QKV_W /* [(nh+2nkv)*d, hidden] */, SB_RWD_QKV_B /* fp32 */, SB_RWD_O_W, SB_RWD_POST_NORM,
+  SB_RWD_GU_W /* interleaved */, SB_RWD_DOWN_W, SB_RWD_STRIDE
+};
+
+int sb_rec_create(const sb_rec_config* cfg, const void* const* weights, int n_weights, sb_rec_engine** out);
+void sb_rec_destroy(sb_rec_engine* eng);
+size_t sb_rec_workspace_bytes(const sb_rec_engine* eng);
+
+/* Vision tower + decoder prefill for n_seq new sequences (= RecognitionPredictor.prefill's model call).
+ *   tiles [n_patches, patch_dim] (cfg.dtype, or fp32 when tiles_f32), patch_perm = window order source rows,
+ *   patch_pos_rc = int2 (row, col) per permuted patch; windows / images given as (start, len) in permuted rows;
+ *   input_ids: the n_tok REAL tokens of all sequences back to back; tok_feat_row[t] = merged-feature row for an
+ *   image token (in permuted/merged order) or -1; tok_hidx/tok_widx = learned 2-D embedding rows;
+ *   tok_pos = position id, tok_slot = KV slot; seqs as (start, len); last_tok[s] = index of the last token.
+ * Outputs per sequence (any may be NULL): logits [n_seq, vocab] cfg.dtype, token i64, score f32,
+ *   bbox i64 [n_seq,6] = trunc(sigmoid * bbox_size), bbox_sig f32 [n_seq,6], done u8, next_ids i64. */
+int sb_rec_prefill(sb_rec_engine* eng, const void* tiles, int tiles_f32, int n_patches, const int* patch_perm,
+                   const int* patch_pos_rc, const int* win_start, const int* win_len, int n_win, int max_win_len,
+                   const int* img_start, const int* img_len, int n_img, int max_img_len, const long long* input_ids,
+                   int n_tok, const int* tok_feat_row, const int* tok_hidx, const int* tok_widx, const int* tok_pos,
+                   const int* tok_slot, const int* seq_start, const int* seq_len, int n_seq, int max_seq_len,
+                   const int* last_tok, void* logits, long long* tok, float* score, long long* bbox, float* bbox_sig,
+                   unsigned char* done, long long* next_ids, void* stream);
+
+/* One decode step for `batch` rows (= RecognitionPredictor.decode's model call + process_outputs):
+ * row b feeds input_ids[b] at position pos[b] of KV slot slot[b]. */
+int sb_rec_decode(sb_rec_engine* eng, const long long* input_ids, const int* slot, const int* pos, int batch,
+                  void* logits, long long* tok, float* score, long long* bbox, float* bbox_sig, unsigned char* done,
+                  long long* next_ids, void* stream);
+
+/* n_steps greedy steps kept on the device (CUDA-graph replay): ids_io/pos_io are updated in place
+ * (ids <- next input id, pos += 1); outputs are step-major [n_steps, batch(,6)]. */
+int sb_rec_decode_steps(sb_rec_engine* eng, long long* ids_io, const int* slot, int* pos_io, int batch, int n_steps,
+                        long long* tok_hist, float* score_hist, long long* bbox_hist, unsigned char* done_hist,
+                        int use_graph, void* stream);
+
+/* Parity taps: copy `bytes` of a named workspace ("feat" = merged image features in window order before the
+ * 2-D position embedding, "x", "xl", "logits", "qkv") into dst (device). */
+int sb_rec_debug_copy(sb_rec_engine* eng, const char* name, void* dst, size_t bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

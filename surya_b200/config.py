@@ -1,0 +1,99 @@
+"""Shape configs for the recognition path (mirror of the reference's config classes).
+
+Field names follow surya/common/surya/{config.py:8-71, encoder/config.py:7-53, decoder/config.py:8-85}.
+The shipped hyper-parameters live in an S3 checkpoint that is not available offline, so the
+benchmark uses the *declared synthetic* config SYN_REC; kernels are shape-generic.
+"""
+from __future__ import annotations
+
+from dataclasses import asdict, dataclass, field
+from typing import Tuple
+
+
+@dataclass
+class RecEncoderConfig:
+    depth: int = 8
+    hidden_size: int = 1280
+    intermediate_size: int = 3420
+    num_heads: int = 16
+    in_channels: int = 3
+    patch_size: int = 14
+    spatial_merge_size: int = 2
+    temporal_patch_size: int = 1
+    window_size: int = 112
+    out_hidden_size: int = 1280
+    fullatt_block_indexes: Tuple[int, ...] = (3, 7)
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_heads
+
+    @property
+    def patch_dim(self) -> int:
+        return self.in_channels * self.temporal_patch_size * self.patch_size * self.patch_size
+
+
+@dataclass
+class RecDecoderConfig:
+    hidden_size: int = 1280
+    intermediate_size: int = 3420
+    num_hidden_layers: int = 12
+    num_attention_heads: int = 16
+    num_key_value_heads: int = 4
+    rope_theta: float = 10000.0
+    rms_norm_eps: float = 1e-6
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_attention_heads
+
+
+@dataclass
+class RecConfig:
+    vocab_size: int = 65792
+    bbox_size: int = 1025
+    bos_token_id: int = 0
+    eos_token_id: int = 1
+    pad_token_id: int = 2
+    image_token_id: int = 3
+    register_token_ids: Tuple[int, ...] = (4, 5, 6, 7)
+    num_register_tokens: int = 4
+    # synthetic stand-ins for ids that the real tokenizer table defines (processor/__init__.py:73-96)
+    ocr_with_boxes_bos_id: int = 8
+    eoi_token_id: int = 9
+    no_output_token_id: int = 10
+    nomath_token_id: int = 11
+    image_embed_encoding_size: int = 1024
+    image_embed_encoding_multiplier: int = 256
+    max_sequence_length: int = 1536
+    vision_encoder: RecEncoderConfig = field(default_factory=RecEncoderConfig)
+    decoder: RecDecoderConfig = field(default_factory=RecDecoderConfig)
+
+    @property
+    def hidden_size(self) -> int:
+        return self.decoder.hidden_size
+
+    @property
+    def merge_size(self) -> int:
+        return self.vision_encoder.spatial_merge_size
+
+    def to_dict(self) -> dict:
+        return asdict(self)
+
+
+def syn_rec() -> RecConfig:
+    """SYN-REC: the declared synthetic recognition config of SURVEY.md §8(d) (BASELINE config 2)."""
+    return RecConfig()
+
+
+def tiny_rec() -> RecConfig:
+    """Small config for fast CPU oracle / golden tests (same code paths: GQA 4:1, head_dim 80, odd I)."""
+    enc = RecEncoderConfig(depth=2, hidden_size=160, intermediate_size=210, num_heads=2, out_hidden_size=320,
+                           fullatt_block_indexes=(1,))
+    dec = RecDecoderConfig(hidden_size=320, intermediate_size=428, num_hidden_layers=2, num_attention_heads=4,
+                           num_key_value_heads=1)
+    return RecConfig(vocab_size=1000, vision_encoder=enc, decoder=dec, image_embed_encoding_size=1024)
+
+
+def align(x: int, m: int) -> int:
+    return (x + m - 1) // m * m

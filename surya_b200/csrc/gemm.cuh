@@ -35,6 +35,7 @@ const char* last_error();
 // Counts one kernel launch and converts cudaGetLastError() into a return code (+ error string).
 int launch_ok();
 long long launch_count();
+void count_launches(long long n);  // kernels replayed through a CUDA graph
 int num_sms();
 
 }  // namespace sb

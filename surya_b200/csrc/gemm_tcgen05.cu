@@ -276,6 +276,7 @@ const char* last_error() { return g_err; }
 
 static std::atomic<long long> g_launches{0};
 long long launch_count() { return g_launches.load(); }
+void count_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int launch_ok() {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();

@@ -1,0 +1,656 @@
+"""Recognition path: host-side mirror of the reference's model / predictor surface over the CUDA engine.
+
+  * pack_rec_weights      state_dict (reference names) -> kernel-friendly device tensors (SB_RW_* order)
+  * plan_vision / plan_tokens   integer index plans (window permutation, RoPE ids, ragged token layout)
+  * RecEngine             ctypes wrapper of sb_rec_* (include/surya_b200.h)
+  * B200SuryaModel        quacks like `RecognitionPredictor.model` (surya/recognition/__init__.py:332-339,
+                          398-409): __call__(input_ids, image_tiles, grid_thw, attention_mask, position_ids,
+                          past_key_values=SlotCache, ...) -> {"lm_logits", "bbox_logits"}
+  * SlotCache             quacks like ContinuousBatchingCache (surya/recognition/cache.py:7-105): merge / trim_left
+  * RecognitionRunner     mirror of RecognitionPredictor.prediction_loop (:501-607) on engine slots
+
+Host code is Python/NumPy/torch plumbing only; every tensor op on the forward path is a kernel from
+libsurya_b200.so.  Nothing here imports oracle/ and nothing falls back to PyTorch math.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from collections import deque
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import c_int, c_void_p, check, ptr, stream_ptr
+from .config import RecConfig, align
+from .ops import dt_code
+
+
+# ------------------------------------------------------------------------------------------------ C structs
+class _RecCfgC(ctypes.Structure):
+    _fields_ = [
+        ("dtype", c_int),
+        ("enc_depth", c_int), ("enc_hidden", c_int), ("enc_heads", c_int), ("enc_inter", c_int), ("enc_inter_pad", c_int),
+        ("patch_dim", c_int), ("patch_dim_pad", c_int), ("merge_unit", c_int), ("enc_out_hidden", c_int),
+        ("fullatt_mask", ctypes.c_uint),
+        ("dec_layers", c_int), ("dec_hidden", c_int), ("dec_heads", c_int), ("dec_kv_heads", c_int),
+        ("dec_head_dim", c_int), ("dec_inter", c_int), ("dec_inter_pad", c_int),
+        ("rms_eps", ctypes.c_float),
+        ("vocab", c_int), ("eos_id", c_int), ("pad_id", c_int),
+        ("bbox_size", ctypes.c_float),
+        ("max_slots", c_int), ("s_max", c_int), ("max_patches", c_int), ("max_tokens", c_int), ("max_seqs", c_int),
+    ]
+
+
+# ------------------------------------------------------------------------------------------------ weight packing
+def _interleave_rows(gate: torch.Tensor, up: torch.Tensor, rows_pad: int) -> torch.Tensor:
+    """[I, K] x2 -> [2*rows_pad, K] with rows (gate_0, up_0, gate_1, up_1, ...), zero padded."""
+    I, K = gate.shape
+    out = torch.zeros((rows_pad, 2, K), dtype=gate.dtype)
+    out[:I, 0] = gate
+    out[:I, 1] = up
+    return out.reshape(2 * rows_pad, K)
+
+
+def _pad_cols(w: torch.Tensor, cols: int) -> torch.Tensor:
+    if w.shape[1] == cols:
+        return w
+    out = torch.zeros((w.shape[0], cols), dtype=w.dtype)
+    out[:, : w.shape[1]] = w
+    return out
+
+
+def pack_rec_weights(sd: Dict[str, torch.Tensor], cfg: RecConfig, dtype: torch.dtype, device) -> List[torch.Tensor]:
+    """Pack a reference-named fp32 state dict into the SB_RW_* table (see include/surya_b200.h).
+
+    16-bit tensors are rounded once from fp32 (= model.to(dtype)); Linear biases are kept as the fp32 image of
+    the rounded 16-bit bias so the GEMM epilogue adds exactly the value the reference adds."""
+    e, d = cfg.vision_encoder, cfg.decoder
+
+    def T(x):
+        return x.to(dtype).contiguous().to(device)
+
+    def B32(x):  # bias: round to model dtype, keep fp32 container
+        return x.to(dtype).float().contiguous().to(device)
+
+    def F32(x):
+        return x.float().contiguous().to(device)
+
+    ip_e, ip_d = align(e.intermediate_size, 8), align(d.intermediate_size, 8)
+    pdp = align(e.patch_dim, 8)
+    hd_e, hd_d = e.head_dim, d.head_dim
+    p = "vision_encoder."
+    fixed = [
+        T(_pad_cols(sd[p + "patch_embed.proj.weight"].reshape(e.hidden_size, -1), pdp)),
+        T(sd[p + "merger.ln_q.weight"]),
+        T(sd[p + "merger.mlp.0.weight"]), B32(sd[p + "merger.mlp.0.bias"]),
+        T(sd[p + "merger.mlp.2.weight"]), B32(sd[p + "merger.mlp.2.bias"]),
+        F32(1.0 / (10000.0 ** (torch.arange(0, hd_e // 2, 2, dtype=torch.float) / (hd_e // 2)))),
+        T(sd["decoder.norm.weight"]),
+        T(sd["embedder.token_embed.weight"]),
+        B32(sd["lm_head.bias"]),
+        T(sd["bbox_head.weight"]), T(sd["bbox_head.bias"]),
+        T(sd["img_h_embed.weight"]), T(sd["img_w_embed.weight"]),
+        F32(1.0 / (d.rope_theta ** (torch.arange(0, hd_d, 2, dtype=torch.int64).float() / hd_d))),
+    ]
+    enc = []
+    for i in range(e.depth):
+        b = f"{p}blocks.{i}."
+
+        def pad_bias(g, u):
+            out = torch.zeros((ip_e, 2), dtype=torch.float32)
+            out[: e.intermediate_size, 0] = g
+            out[: e.intermediate_size, 1] = u
+            return out.reshape(-1)
+
+        enc += [
+            T(sd[b + "norm1.weight"]),
+            T(sd[b + "attn.qkv.weight"]), B32(sd[b + "attn.qkv.bias"]),
+            T(sd[b + "attn.proj.weight"]), B32(sd[b + "attn.proj.bias"]),
+            T(sd[b + "norm2.weight"]),
+            T(_interleave_rows(sd[b + "mlp.gate_proj.weight"], sd[b + "mlp.up_proj.weight"], ip_e)),
+            B32(pad_bias(sd[b + "mlp.gate_proj.bias"], sd[b + "mlp.up_proj.bias"])),
+            T(_pad_cols(sd[b + "mlp.down_proj.weight"], ip_e)), B32(sd[b + "mlp.down_proj.bias"]),
+        ]
+    dec = []
+    for i in range(d.num_hidden_layers):
+        b = f"decoder.layers.{i}."
+        qkv_w = torch.cat([sd[b + "self_attn.q_proj.weight"], sd[b + "self_attn.k_proj.weight"],
+                           sd[b + "self_attn.v_proj.weight"]], 0)
+        qkv_b = torch.cat([sd[b + "self_attn.q_proj.bias"], sd[b + "self_attn.k_proj.bias"],
+                           sd[b + "self_attn.v_proj.bias"]], 0)
+        dec += [
+            T(sd[b + "input_layernorm.weight"]),
+            T(qkv_w), B32(qkv_b),
+            T(sd[b + "self_attn.o_proj.weight"]),
+            T(sd[b + "post_attention_layernorm.weight"]),
+            T(_interleave_rows(sd[b + "mlp.gate_proj.weight"], sd[b + "mlp.up_proj.weight"], ip_d)),
+            T(_pad_cols(sd[b + "mlp.down_proj.weight"], ip_d)),
+        ]
+    return fixed + enc + dec
+
+
+# ------------------------------------------------------------------------------------------------ index plans
+_GRID_CACHE: Dict[Tuple[int, int, int, int, int], dict] = {}
+
+
+def _grid_plan(h: int, w: int, merge: int, window: int, patch: int) -> dict:
+    """Per-image integer plan for a (1, h, w) patch grid — mirrors rot_pos_emb / get_window_index
+    (surya/common/surya/encoder/__init__.py:523-597) and get_2d_learned_embeddings' index math
+    (surya/common/surya/__init__.py:240-259).  All arrays are local to the image (offset by the caller)."""
+    key = (h, w, merge, window, patch)
+    hit = _GRID_CACHE.get(key)
+    if hit is not None:
+        return hit
+    unit = merge * merge
+    lh, lw = h // merge, w // merge
+    # (row, col) of every patch in merge-block-major order
+    hp = np.arange(h)[:, None].repeat(w, 1).reshape(lh, merge, lw, merge).transpose(0, 2, 1, 3).reshape(-1)
+    wp = np.arange(w)[None, :].repeat(h, 0).reshape(lh, merge, lw, merge).transpose(0, 2, 1, 3).reshape(-1)
+    pos = np.stack([hp, wp], -1).astype(np.int32)
+    # window order of merged units
+    vws = window // merge // patch
+    index = np.arange(lh * lw).reshape(lh, lw)
+    pad_h, pad_w = vws - lh % vws, vws - lw % vws
+    nwh, nww = (lh + pad_h) // vws, (lw + pad_w) // vws
+    padded = np.pad(index, ((0, pad_h), (0, pad_w)), constant_values=-100)
+    padded = padded.reshape(nwh, vws, nww, vws).transpose(0, 2, 1, 3).reshape(nwh * nww, vws * vws)
+    seqlens = (padded != -100).sum(1)
+    flat = padded.reshape(-1)
+    widx = flat[flat != -100].astype(np.int64)            # window position -> original merged unit
+    win_len = (seqlens[seqlens > 0] * unit).astype(np.int32)
+    win_start = (np.concatenate([[0], np.cumsum(win_len)[:-1]])).astype(np.int32)
+    patch_perm = (widx[:, None] * unit + np.arange(unit)[None, :]).reshape(-1).astype(np.int32)
+    inv = np.argsort(widx).astype(np.int32)                # original merged unit -> window position
+    # learned 2-D embedding rows (fp32 arithmetic then truncation, as torch does)
+    mult = np.float32(256)
+
+    def emb_idx(n):
+        v = np.arange(n, dtype=np.float32) / np.float32(max(1, n - 1)) * mult
+        return v.astype(np.int64).astype(np.int32)
+
+    hi = np.repeat(emb_idx(lh), lw)
+    wi = np.tile(emb_idx(lw), lh)
+    plan = dict(n_patches=h * w, n_units=lh * lw, patch_perm=patch_perm, pos_perm=pos[patch_perm],
+                win_start=win_start, win_len=win_len, inv=inv, hidx=hi, widx=wi)
+    _GRID_CACHE[key] = plan
+    return plan
+
+
+@dataclass
+class PrefillPlan:
+    ints: torch.Tensor            # pinned int32 buffer with every array below back to back
+    off: Dict[str, Tuple[int, int]]
+    ids: torch.Tensor             # pinned int64 [n_tok]
+    n_patches: int
+    n_win: int
+    max_win: int
+    n_img: int
+    max_img: int
+    n_tok: int
+    n_seq: int
+    max_seq: int
+
+
+def build_prefill_plan(cfg: RecConfig, grid_thw: np.ndarray, seq_tokens: Sequence[np.ndarray],
+                       slots: Sequence[int], image_multiplier: Optional[int] = None) -> PrefillPlan:
+    """grid_thw [n_img, 3]; seq_tokens = per-sequence REAL token ids (no padding); slots = KV slot per sequence."""
+    e = cfg.vision_encoder
+    merge, unit = e.spatial_merge_size, e.spatial_merge_size ** 2
+    mult = image_multiplier or cfg.image_embed_encoding_multiplier
+    assert mult == 256, "index math assumes image_embed_encoding_multiplier == 256"
+    parts = {k: [] for k in ("patch_perm", "pos_perm", "win_start", "win_len", "img_start", "img_len", "inv", "hidx", "widx")}
+    p_off = u_off = 0
+    for t, h, w in np.asarray(grid_thw).reshape(-1, 3):
+        assert t == 1, "temporal grids are not used by surya (temporal_patch_size = 1)"
+        g = _grid_plan(int(h), int(w), merge, e.window_size, e.patch_size)
+        parts["patch_perm"].append(g["patch_perm"] + p_off)
+        parts["pos_perm"].append(g["pos_perm"])
+        parts["win_start"].append(g["win_start"] + p_off)
+        parts["win_len"].append(g["win_len"])
+        parts["img_start"].append(np.array([p_off], np.int32))
+        parts["img_len"].append(np.array([g["n_patches"]], np.int32))
+        parts["inv"].append(g["inv"] + u_off)
+        parts["hidx"].append(g["hidx"])
+        parts["widx"].append(g["widx"])
+        p_off += g["n_patches"]
+        u_off += g["n_units"]
+    cat = {k: (np.concatenate(v).astype(np.int32) if v else np.zeros(0, np.int32)) for k, v in parts.items()}
+    ids = np.concatenate([np.asarray(s, dtype=np.int64) for s in seq_tokens])
+    lens = np.array([len(s) for s in seq_tokens], dtype=np.int32)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    tok_pos = np.concatenate([np.arange(n, dtype=np.int32) for n in lens])
+    tok_slot = np.repeat(np.asarray(slots, dtype=np.int32), lens)
+    is_img = ids == cfg.image_token_id
+    n_img_tok = int(is_img.sum())
+    assert n_img_tok == u_off, f"image tokens ({n_img_tok}) and image features ({u_off}) do not match"
+    feat_row = np.full(ids.shape, -1, np.int32)
+    hi = np.zeros(ids.shape, np.int32)
+    wi = np.zeros(ids.shape, np.int32)
+    feat_row[is_img] = cat["inv"]
+    hi[is_img] = cat["hidx"]
+    wi[is_img] = cat["widx"]
+    arrays = {
+        "patch_perm": cat["patch_perm"], "pos_rc": cat["pos_perm"].reshape(-1), "win_start": cat["win_start"],
+        "win_len": cat["win_len"], "img_start": cat["img_start"], "img_len": cat["img_len"], "feat_row": feat_row,
+        "hidx": hi, "widx": wi, "tok_pos": tok_pos, "tok_slot": tok_slot, "seq_start": starts, "seq_len": lens,
+        "last_tok": (starts + lens - 1).astype(np.int32),
+    }
+    total = sum(a.size for a in arrays.values())
+    buf = torch.empty(max(total, 1), dtype=torch.int32).pin_memory() if torch.cuda.is_available() else torch.empty(max(total, 1), dtype=torch.int32)
+    off, o = {}, 0
+    nb = buf.numpy()
+    for k, a in arrays.items():
+        nb[o:o + a.size] = a
+        off[k] = (o, a.size)
+        o += a.size
+    ids_t = torch.from_numpy(ids)
+    if torch.cuda.is_available():
+        ids_t = ids_t.pin_memory()
+    return PrefillPlan(ints=buf, off=off, ids=ids_t, n_patches=p_off, n_win=cat["win_len"].size,
+                       max_win=int(cat["win_len"].max()) if cat["win_len"].size else 0, n_img=cat["img_len"].size,
+                       max_img=int(cat["img_len"].max()) if cat["img_len"].size else 0, n_tok=ids.size,
+                       n_seq=lens.size, max_seq=int(lens.max()))
+
+
+# ------------------------------------------------------------------------------------------------ engine wrapper
+class RecEngine:
+    """Owns one sb_rec_engine (weights + KV slots + workspaces) on the current CUDA device."""
+
+    def __init__(self, cfg: RecConfig, state_dict: Dict[str, torch.Tensor], dtype: torch.dtype = torch.bfloat16,
+                 device: str | torch.device = "cuda", max_slots: int = 256, s_max: Optional[int] = None,
+                 max_patches: int = 65536, max_tokens: int = 32768, max_seqs: Optional[int] = None):
+        self.lib = _lib.load()
+        self.cfg, self.dtype, self.device = cfg, dtype, torch.device(device)
+        e, d = cfg.vision_encoder, cfg.decoder
+        self.weights = pack_rec_weights(state_dict, cfg, dtype, self.device)
+        self.s_max = s_max or cfg.max_sequence_length
+        self.max_slots = max_slots
+        mask = 0
+        for i in e.fullatt_block_indexes:
+            mask |= 1 << i
+        c = _RecCfgC(
+            dtype=dt_code(dtype), enc_depth=e.depth, enc_hidden=e.hidden_size, enc_heads=e.num_heads,
+            enc_inter=e.intermediate_size, enc_inter_pad=align(e.intermediate_size, 8), patch_dim=e.patch_dim,
+            patch_dim_pad=align(e.patch_dim, 8), merge_unit=e.spatial_merge_size ** 2, enc_out_hidden=e.out_hidden_size,
+            fullatt_mask=mask, dec_layers=d.num_hidden_layers, dec_hidden=d.hidden_size, dec_heads=d.num_attention_heads,
+            dec_kv_heads=d.num_key_value_heads, dec_head_dim=d.head_dim, dec_inter=d.intermediate_size,
+            dec_inter_pad=align(d.intermediate_size, 8), rms_eps=d.rms_norm_eps, vocab=cfg.vocab_size,
+            eos_id=cfg.eos_token_id, pad_id=cfg.pad_token_id, bbox_size=float(cfg.bbox_size), max_slots=max_slots,
+            s_max=self.s_max, max_patches=max_patches, max_tokens=max_tokens, max_seqs=max_seqs or max_slots)
+        self._c = c
+        arr = (c_void_p * len(self.weights))(*[w.data_ptr() for w in self.weights])
+        self._h = c_void_p()
+        self.lib.sb_rec_workspace_bytes.restype = ctypes.c_size_t
+        with torch.cuda.device(self.device):
+            check(self.lib.sb_rec_create(ctypes.byref(c), arr, c_int(len(self.weights)), ctypes.byref(self._h)),
+                  "sb_rec_create")
+        self.free_slots = deque(range(max_slots))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.sb_rec_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.sb_rec_workspace_bytes(self._h))
+
+    # ---- slots
+    def alloc_slots(self, n: int) -> List[int]:
+        if n > len(self.free_slots):
+            raise _lib.SuryaB200Error(f"out of KV slots: need {n}, free {len(self.free_slots)}")
+        return [self.free_slots.popleft() for _ in range(n)]
+
+    def release_slots(self, slots: Sequence[int]):
+        self.free_slots.extend(int(s) for s in slots)
+
+    # ---- calls
+    def prefill(self, tiles: torch.Tensor, plan: PrefillPlan, want_logits: bool = False):
+        """tiles: device or pinned-host [n_patches, patch_dim] (fp32 or engine dtype). Returns dict of device tensors."""
+        dev = self.device
+        if not tiles.is_cuda:
+            tiles = tiles.to(dev, non_blocking=True)
+        ints = plan.ints.to(dev, non_blocking=True)
+        ids = plan.ids.to(dev, non_blocking=True)
+
+        def ip(name):
+            o, n = plan.off[name]
+            return c_void_p(ints.data_ptr() + 4 * o) if n else c_void_p(0)
+
+        n = plan.n_seq
+        out = {
+            "tok": torch.empty(n, dtype=torch.int64, device=dev), "score": torch.empty(n, dtype=torch.float32, device=dev),
+            "bbox": torch.empty((n, 6), dtype=torch.int64, device=dev),
+            "bbox_sig": torch.empty((n, 6), dtype=torch.float32, device=dev),
+            "done": torch.empty(n, dtype=torch.uint8, device=dev), "next_ids": torch.empty(n, dtype=torch.int64, device=dev),
+        }
+        if want_logits:
+            out["logits"] = torch.empty((n, self.cfg.vocab_size), dtype=self.dtype, device=dev)
+        tiles_f32 = 1 if tiles.dtype == torch.float32 else 0
+        if not tiles_f32 and tiles.dtype != self.dtype:
+            raise _lib.SuryaB200Error(f"tiles must be float32 or {self.dtype}")
+        check(self.lib.sb_rec_prefill(
+            self._h, ptr(tiles), c_int(tiles_f32), c_int(plan.n_patches), ip("patch_perm"), ip("pos_rc"),
+            ip("win_start"), ip("win_len"), c_int(plan.n_win), c_int(plan.max_win), ip("img_start"), ip("img_len"),
+            c_int(plan.n_img), c_int(plan.max_img), ptr(ids), c_int(plan.n_tok), ip("feat_row"), ip("hidx"), ip("widx"),
+            ip("tok_pos"), ip("tok_slot"), ip("seq_start"), ip("seq_len"), c_int(plan.n_seq), c_int(plan.max_seq),
+            ip("last_tok"), ptr(out.get("logits")), ptr(out["tok"]), ptr(out["score"]), ptr(out["bbox"]),
+            ptr(out["bbox_sig"]), ptr(out["done"]), ptr(out["next_ids"]), stream_ptr()), "sb_rec_prefill")
+        out["_keep"] = (tiles, ints, ids)
+        return out
+
+    def decode(self, input_ids: torch.Tensor, slot: torch.Tensor, pos: torch.Tensor, want_logits: bool = False):
+        dev = self.device
+        B = input_ids.numel()
+        out = {
+            "tok": torch.empty(B, dtype=torch.int64, device=dev), "score": torch.empty(B, dtype=torch.float32, device=dev),
+            "bbox": torch.empty((B, 6), dtype=torch.int64, device=dev),
+            "bbox_sig": torch.empty((B, 6), dtype=torch.float32, device=dev),
+            "done": torch.empty(B, dtype=torch.uint8, device=dev), "next_ids": torch.empty(B, dtype=torch.int64, device=dev),
+        }
+        if want_logits:
+            out["logits"] = torch.empty((B, self.cfg.vocab_size), dtype=self.dtype, device=dev)
+        check(self.lib.sb_rec_decode(self._h, ptr(input_ids), ptr(slot), ptr(pos), c_int(B), ptr(out.get("logits")),
+                                     ptr(out["tok"]), ptr(out["score"]), ptr(out["bbox"]), ptr(out["bbox_sig"]),
+                                     ptr(out["done"]), ptr(out["next_ids"]), stream_ptr()), "sb_rec_decode")
+        return out
+
+    def decode_steps(self, ids_io: torch.Tensor, slot: torch.Tensor, pos_io: torch.Tensor, n_steps: int,
+                     hist: Optional[dict] = None, use_graph: bool = True):
+        """n_steps greedy steps on the device; ids_io / pos_io advance in place. Returns step-major histories."""
+        dev = self.device
+        B = ids_io.numel()
+        if hist is None:
+            hist = {
+                "tok": torch.empty((n_steps, B), dtype=torch.int64, device=dev),
+                "score": torch.empty((n_steps, B), dtype=torch.float32, device=dev),
+                "bbox": torch.empty((n_steps, B, 6), dtype=torch.int64, device=dev),
+                "done": torch.empty((n_steps, B), dtype=torch.uint8, device=dev),
+            }
+        check(self.lib.sb_rec_decode_steps(self._h, ptr(ids_io), ptr(slot), ptr(pos_io), c_int(B), c_int(n_steps),
+                                           ptr(hist["tok"]), ptr(hist["score"]), ptr(hist["bbox"]), ptr(hist["done"]),
+                                           c_int(1 if use_graph else 0), stream_ptr()), "sb_rec_decode_steps")
+        return hist
+
+    def debug_tensor(self, name: str, rows: int, cols: int) -> torch.Tensor:
+        """Copy of an engine workspace (parity taps): feat / x / xl / logits / qkv."""
+        out = torch.empty((rows, cols), dtype=self.dtype, device=self.device)
+        check(self.lib.sb_rec_debug_copy(self._h, name.encode(), ptr(out),
+                                         ctypes.c_size_t(rows * cols * out.element_size()), stream_ptr()),
+              "sb_rec_debug_copy")
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ model / cache mirrors
+class SlotCache:
+    """ContinuousBatchingCache stand-in (surya/recognition/cache.py:7-105): the KV data lives in engine slots,
+    so merge() re-points batch rows at the new sequences' slots and trim_left() has nothing to move."""
+
+    def __init__(self, engine: RecEngine):
+        self.engine = engine
+        self.slots: Optional[torch.Tensor] = None  # int32 [B] on device
+        self._host: List[int] = []
+
+    def __bool__(self):
+        return self.slots is not None
+
+    def __len__(self):
+        return 0 if self.slots is None else int(self.slots.numel())
+
+    def assign(self, slots: Sequence[int]):
+        self._host = [int(s) for s in slots]
+        self.slots = torch.tensor(self._host, dtype=torch.int32, device=self.engine.device)
+
+    def merge(self, new_cache: "SlotCache", merge_idxs: Sequence[int], device=None) -> int:
+        """cache.py:57-105 — rows merge_idxs now hold the new sequences; their previous slots are recycled."""
+        old = [self._host[i] for i in merge_idxs]
+        for i, s in zip(merge_idxs, new_cache._host):
+            self._host[i] = s
+        self.engine.release_slots(old)
+        self.slots = torch.tensor(self._host, dtype=torch.int32, device=self.engine.device)
+        new_cache.slots, new_cache._host = None, []
+        return 0  # no padding offset exists in a slot cache
+
+    def trim_left(self, n: int):
+        """cache.py:39-46 — left padding is never materialised, nothing to trim."""
+        return None
+
+    def release(self):
+        if self._host:
+            self.engine.release_slots(self._host)
+        self._host, self.slots = [], None
+
+
+class _Cfg:
+    def __init__(self, cfg: RecConfig):
+        self.__dict__.update(cfg.to_dict())
+        self.bbox_size = cfg.bbox_size
+
+
+class B200SuryaModel:
+    """Call-compatible with the attributes RecognitionPredictor touches on `self.model`
+    (surya/recognition/__init__.py:112, 296-297, 315, 332-339, 398-409): __call__, .config.bbox_size, .device, .dtype."""
+
+    def __init__(self, engine: RecEngine):
+        self.engine = engine
+        self.config = _Cfg(engine.cfg)
+        self.device = engine.device
+        self.dtype = engine.dtype
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+    def new_cache(self) -> SlotCache:
+        return SlotCache(self.engine)
+
+    def __call__(self, input_ids=None, image_tiles=None, grid_thw=None, inputs_embeds=None, attention_mask=None,
+                 position_ids=None, past_key_values: Optional[SlotCache] = None, use_cache=True, logits_to_keep=1,
+                 encoder_chunk_size=None, **kwargs):
+        if inputs_embeds is not None:
+            raise NotImplementedError("inputs_embeds is not part of the predictor call surface")
+        if past_key_values is None:
+            raise _lib.SuryaB200Error("B200SuryaModel needs a SlotCache as past_key_values (use model.new_cache())")
+        eng, cfg = self.engine, self.engine.cfg
+        B, S = input_ids.shape
+        if S > 1 or image_tiles is not None:      # ---- prefill
+            ids_h = input_ids.detach().cpu().numpy()
+            m_h = attention_mask.detach().cpu().numpy().astype(bool)
+            seqs = [ids_h[b][m_h[b]] for b in range(B)]
+            slots = eng.alloc_slots(B)
+            past_key_values.assign(slots)
+            g = grid_thw.detach().cpu().numpy() if grid_thw is not None else np.zeros((0, 3), np.int64)
+            plan = build_prefill_plan(cfg, g, seqs, slots)
+            out = eng.prefill(image_tiles if image_tiles is not None else torch.empty((0, cfg.vision_encoder.patch_dim), dtype=self.dtype, device=self.device),
+                              plan, want_logits=True)
+        else:                                     # ---- decode
+            ids = input_ids.reshape(-1).to(torch.int64).contiguous()
+            pos = position_ids.reshape(-1).to(torch.int32).contiguous()
+            out = eng.decode(ids, past_key_values.slots, pos, want_logits=True)
+        return {
+            "lm_logits": out["logits"].unsqueeze(1),
+            "bbox_logits": out["bbox_sig"].to(self.dtype).unsqueeze(1),
+            "past_key_values": past_key_values,
+        }
+
+
+# ------------------------------------------------------------------------------------------------ host processor mirror
+IMAGE_MEAN = np.array((0.485, 0.456, 0.406), dtype=np.float32)
+IMAGE_STD = np.array((0.229, 0.224, 0.225), dtype=np.float32)
+
+
+def scale_to_fit(img: np.ndarray, max_size=(1024, 256), min_size=(168, 168)) -> np.ndarray:
+    """Mirror of SuryaOCRProcessor.scale_to_fit (surya/common/surya/processor/__init__.py:140-178)."""
+    import cv2
+
+    h, w = img.shape[:2]
+    if w == 0 or h == 0:
+        return img
+    cur, mx, mn = w * h, max_size[0] * max_size[1], min_size[0] * min_size[1]
+    if cur > mx:
+        s = (mx / cur) ** 0.5
+        nw, nh = math.floor(w * s), math.floor(h * s)
+    elif cur < mn:
+        s = (mn / cur) ** 0.5
+        nw, nh = math.ceil(w * s), math.ceil(h * s)
+    else:
+        return img
+    return cv2.resize(img, (nw, nh), interpolation=cv2.INTER_LANCZOS4)
+
+
+def tile_image(image: np.ndarray, patch: int = 14, merge: int = 2) -> Tuple[np.ndarray, Tuple[int, int, int]]:
+    """Mirror of _process_and_tile (processor/__init__.py:185-230): resize to x28, normalise, merge-block-major tiles."""
+    import cv2
+
+    factor = patch * merge
+    h, w = image.shape[:2]
+    hb, wb = math.ceil(h / factor) * factor, math.ceil(w / factor) * factor
+    if hb != h or wb != w:
+        image = cv2.resize(image, (wb, hb), interpolation=cv2.INTER_CUBIC)
+    image = image.astype(np.float64) * (1 / 255.0)
+    image = (image.astype(np.float32) - IMAGE_MEAN) / IMAGE_STD
+    h, w = image.shape[:2]
+    gh, gw = h // patch, w // patch
+    x = image.transpose(2, 0, 1).reshape(3, gh // merge, merge, patch, gw // merge, merge, patch)
+    x = x.transpose(1, 4, 2, 5, 0, 3, 6)          # [gh/m, gw/m, m, m, C, P, P]
+    return np.ascontiguousarray(x).reshape(gh * gw, 3 * patch * patch), (1, gh, gw)
+
+
+def prompt_tokens(cfg: RecConfig, n_image_tokens: int, math_mode: bool = True, text_ids: Sequence[int] = ()) -> np.ndarray:
+    """Token layout of one ocr_with_boxes prompt (processor/__init__.py:247-248, 260-274, 312)."""
+    ids = [cfg.image_token_id] * n_image_tokens + list(cfg.register_token_ids[: cfg.num_register_tokens])
+    ids += [cfg.ocr_with_boxes_bos_id] + ([] if math_mode else [cfg.nomath_token_id]) + list(text_ids) + [cfg.eoi_token_id]
+    return np.asarray(ids, dtype=np.int64)
+
+
+def detect_repeat_token(tokens: List[int], max_repeats: int = 40) -> bool:
+    """Mirror of surya/recognition/util.py:59-69."""
+    if len(tokens) < max_repeats:
+        return False
+    last_n = tokens[-max_repeats:]
+    u = len(set(last_n))
+    if u > 5:
+        return False
+    return last_n[-u:] == last_n[-u * 2: -u]
+
+
+class RecognitionRunner:
+    """Mirror of RecognitionPredictor.prediction_loop (surya/recognition/__init__.py:501-607) on engine slots.
+
+    Same scheduling rule (prefill when more than `min_prefill_ratio` of the slots are free and prompts wait,
+    else decode), same stop rules (EOS / NO_OUTPUT after prefill; EOS / PAD / max_tokens / repeat during
+    decode), same outputs (token list, score list, bbox [max_tokens, 6] per crop).  Differences are internal:
+    ragged prefill instead of left padding, slot cache instead of merge/trim, `poll` decode steps per host
+    round-trip instead of one (tokens generated past a stop are dropped; per-prompt results are unchanged
+    because rows are independent)."""
+
+    min_prefill_ratio = 0.2
+
+    def __init__(self, engine: RecEngine, batch_size: int = 256, max_tokens: int = 128, poll: int = 8):
+        self.engine, self.batch_size, self.max_tokens, self.poll = engine, batch_size, max_tokens, max(1, poll)
+
+    def preprocess(self, crops: Sequence[np.ndarray], math_mode: bool = True):
+        cfg = self.engine.cfg
+        tiles, grids, seqs = [], [], []
+        for crop in crops:
+            img = scale_to_fit(np.asarray(crop, dtype=np.float32), (1024, 256))
+            t, g = tile_image(img, cfg.vision_encoder.patch_size, cfg.merge_size)
+            tiles.append(t)
+            grids.append(g)
+            seqs.append(prompt_tokens(cfg, t.shape[0] // cfg.merge_size ** 2, math_mode))
+        return tiles, grids, seqs
+
+    def run_preprocessed(self, tiles, grids, seqs, fixed_steps: bool = False):
+        """Returns (tokens: List[List[int]], scores: List[List[float]], bboxes: np.ndarray [N, max_tokens, 6])."""
+        eng, cfg = self.engine, self.engine.cfg
+        dev = eng.device
+        N = len(seqs)
+        tokens: List[List[int]] = [[] for _ in range(N)]
+        scores: List[List[float]] = [[] for _ in range(N)]
+        bboxes = np.zeros((N, self.max_tokens, 6), dtype=np.int64)
+        queue = deque(range(N))
+        Bsz = self.batch_size
+        scratch = eng.alloc_slots(1)[0]      # idle rows decode into a scratch slot (the reference decodes every row too)
+        row_prompt: List[Optional[int]] = [None] * Bsz
+        row_slot = [scratch] * Bsz
+        ids_io = torch.full((Bsz,), cfg.pad_token_id, dtype=torch.int64, device=dev)
+        pos_host = torch.zeros(Bsz, dtype=torch.int32).pin_memory()
+        slot_host = torch.zeros(Bsz, dtype=torch.int32).pin_memory()
+        pos_io = torch.zeros(Bsz, dtype=torch.int32, device=dev)
+        slot_t = torch.zeros(Bsz, dtype=torch.int32, device=dev)
+
+        def finish(row):
+            eng.release_slots([row_slot[row]])
+            row_slot[row] = scratch
+            row_prompt[row] = None
+
+        try:
+            while queue or any(p is not None for p in row_prompt):
+                empty = [r for r in range(Bsz) if row_prompt[r] is None]
+                if queue and len(empty) / Bsz > self.min_prefill_ratio:
+                    take = [queue.popleft() for _ in range(min(len(empty), len(queue)))]
+                    rows = empty[: len(take)]
+                    new_slots = eng.alloc_slots(len(take))
+                    plan = build_prefill_plan(cfg, np.array([grids[i] for i in take]), [seqs[i] for i in take], new_slots)
+                    tl = torch.from_numpy(np.concatenate([tiles[i] for i in take], 0)).pin_memory()
+                    out = eng.prefill(tl, plan)
+                    ids_io[torch.tensor(rows, dtype=torch.int64, device=dev)] = out["next_ids"]
+                    tok_h, sc_h, bb_h = out["tok"].cpu().numpy(), out["score"].cpu().numpy(), out["bbox"].cpu().numpy()
+                    for j, (r, p) in enumerate(zip(rows, take)):
+                        row_prompt[r], row_slot[r] = p, new_slots[j]
+                        tokens[p].append(int(tok_h[j]))
+                        scores[p].append(float(sc_h[j]))
+                        bboxes[p, 0] = bb_h[j]
+                        stop = (not fixed_steps) and tokens[p][-1] in (cfg.eos_token_id, cfg.no_output_token_id)
+                        if stop or self.max_tokens <= 1:
+                            finish(r)
+                else:
+                    active = [r for r in range(Bsz) if row_prompt[r] is not None]
+                    remaining = min(self.max_tokens - len(tokens[row_prompt[r]]) for r in active)
+                    n = max(1, remaining if fixed_steps else min(self.poll, remaining))
+                    for r in range(Bsz):
+                        p = row_prompt[r]
+                        pos_host[r] = 0 if p is None else len(seqs[p]) + len(tokens[p]) - 1
+                        slot_host[r] = row_slot[r]
+                    pos_io.copy_(pos_host, non_blocking=True)
+                    slot_t.copy_(slot_host, non_blocking=True)
+                    hist = eng.decode_steps(ids_io, slot_t, pos_io, n)
+                    th, sh, bh = hist["tok"].cpu().numpy(), hist["score"].cpu().numpy(), hist["bbox"].cpu().numpy()
+                    for r in active:
+                        p = row_prompt[r]
+                        for s in range(n):
+                            k = len(tokens[p])
+                            tokens[p].append(int(th[s, r]))
+                            scores[p].append(float(sh[s, r]))
+                            bboxes[p, k] = bh[s, r]
+                            full = len(tokens[p]) >= self.max_tokens
+                            if fixed_steps:
+                                stop = full
+                            else:
+                                stop = tokens[p][-1] in (cfg.eos_token_id, cfg.pad_token_id) or full or \
+                                    detect_repeat_token(tokens[p])
+                            if stop:
+                                finish(r)
+                                break
+        finally:
+            for r in range(Bsz):
+                if row_prompt[r] is not None:
+                    finish(r)
+            eng.release_slots([scratch])
+        return tokens, scores, bboxes
+
+    def run(self, crops: Sequence[np.ndarray], math_mode: bool = True, fixed_steps: bool = False):
+        tiles, grids, seqs = self.preprocess(crops, math_mode)
+        return self.run_preprocessed(tiles, grids, seqs, fixed_steps=fixed_steps)
