@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric: text-line-crops/sec (recognition), config 2.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE config 2 / SURVEY.md §8d): B = 256 synthetic 48x512 uint8 line crops per GPU -> 56x560,
+160 patches, 46-token prompt each; declared synthetic model SYN-REC (vision tower = reference defaults,
+decoder 12 x 1280, GQA 16/4, vocab 65 792), bf16, greedy decode max_tokens = 128 with early exit disabled
+(all 256 rows run 1 prefill + 127 decode steps).  A "step" is one pass of that hot path over one 256-crop batch.
+
+  value : crops/s, whole job, inputs (fp32 tiles + index plan) already resident in HBM when the clock starts
+  e2e   : crops/s through the public API (RecognitionRunner.run_preprocessed) from pinned HOST buffers,
+          host->device copies of tiles/plan and device->host reads of tokens/scores/boxes inside the timed region
+  roofline     : dominant kernel = the tcgen05 GEMM in the HBM-bound decode step
+  cpu_baseline : oracle port (fp32 PyTorch restatement of the reference modules) on this box's host cores,
+                 bounded sample, rank 0 only
+
+Multi-GPU (torchrun, one rank per GPU): replicas over independent crop batches (weak scaling); one NCCL
+broadcast of the packed weights at init, one all_gather of the result tensors per step.
+`--impl reference` times the reference algorithm's CPU path (the oracle port: /root/reference is not on the GPU
+box and the reference is Python, so there is nothing to compile) on all host threads, same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "text-line-crops/sec (recognition)"
+B_PER_GPU = 256
+MAX_TOKENS = 128
+CROP_H, CROP_W = 48, 512
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_oracle_sample(n_crops: int, steps: int, threads: int):
+    """Oracle port of the reference CPU path (fp32): prefill + (steps-1) decode steps over n_crops crops."""
+    from oracle import rec_oracle as O
+    from surya_b200.config import syn_rec
+    from surya_b200.synth import rec_state_dict, rec_synthetic_crops
+
+    torch.set_num_threads(threads)
+    cfg = syn_rec()
+    sd = rec_state_dict(cfg, seed=0)
+    crops = list(rec_synthetic_crops(n_crops, CROP_H, CROP_W, seed=1234))
+    batch = O.build_batch(crops, cfg)
+
+    def one():
+        t0 = time.perf_counter()
+        O.greedy_decode(sd, cfg, batch, steps, torch.float32)
+        return time.perf_counter() - t0
+
+    return one
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_crops = 16
+    one = cpu_oracle_sample(n_crops, MAX_TOKENS, threads)
+    for _ in range(max(1, min(args.warmup, 1))):
+        one()
+    times = [one() for _ in range(max(1, min(args.steps, 3)))]
+    t = float(np.mean(times))
+    v = n_crops / t
+    sample = f"{n_crops} crops x {MAX_TOKENS} tokens per step (fp32, SDPA-free eager math), {len(times)} timed steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "crops/s", "n_gpus": args.gpus, "steps": len(times),
+        "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": _config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": "crops/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def _config(n_gpus):
+    return {"workload": f"recognition: {B_PER_GPU} synthetic {CROP_H}x{CROP_W} line crops per GPU, greedy decode "
+                        f"max_tokens={MAX_TOKENS} (1 prefill + {MAX_TOKENS - 1} decode steps, early exit off), SYN-REC",
+            "model": "SYN-REC (declared synthetic: enc 8x1280/16h/I3420, dec 12x1280 GQA16/4 I3420, vocab 65792)",
+            "global_batch": B_PER_GPU * n_gpus, "crops_per_gpu": B_PER_GPU, "max_tokens": MAX_TOKENS,
+            "parallelism": f"replicas x{n_gpus} (independent crop batches)",
+            "l2": "no flush: per-step working set (0.96 GB weights + 0.5 GB KV + 1.2 GB activations) >> 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def decode_gemm_roofline(eng, peaks, reps=20):
+    """Live CUDA-event timing of the GEMM launches of ONE decode step (B=256), replayed as a CUDA graph over the
+    engine's real weight tensors.  achieved = algorithmic bytes per launch / average launch duration."""
+    from surya_b200 import ops
+    from surya_b200.config import align
+
+    cfg = eng.cfg
+    d = cfg.decoder
+    dev, dt = eng.device, eng.dtype
+    B, D = B_PER_GPU, d.hidden_size
+    Q = (d.num_attention_heads + 2 * d.num_key_value_heads) * d.head_dim
+    Ip = align(d.intermediate_size, 8)
+    base = 15 + 10 * cfg.vision_encoder.depth
+    x = torch.randn(B, D, device=dev).to(dt)
+    ao = torch.randn(B, d.num_attention_heads * d.head_dim, device=dev).to(dt)
+    qkv = torch.empty(B, Q, device=dev, dtype=dt)
+    act = torch.empty(B, Ip, device=dev, dtype=dt)
+    logits = torch.empty(B, cfg.vocab_size, device=dev, dtype=dt)
+    calls, nbytes, flops = [], 0, 0
+
+    def add(a, w, out, **kw):
+        nonlocal nbytes, flops
+        calls.append((a, w, out, kw))
+        nbytes += (a.numel() + w.numel() + out.numel()) * 2 + (out.numel() * 2 if kw.get("residual") is not None else 0)
+        flops += 2 * a.shape[0] * w.shape[0] * w.shape[1]
+
+    for l in range(d.num_hidden_layers):
+        w = eng.weights[base + 7 * l: base + 7 * (l + 1)]
+        add(x, w[1], qkv, bias=w[2])
+        add(ao, w[3], x, residual=x)
+        add(x, w[5], act, act="silu", swiglu=True)
+        add(act, w[6], x, residual=x)
+    add(x, eng.weights[8], logits, bias=eng.weights[9])
+
+    def run():
+        for a, w, out, kw in calls:
+            ops.gemm(a, w, out=out, **kw)
+
+    run()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        run()
+        with torch.cuda.graph(g, stream=s):
+            run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / reps
+    n = len(calls)
+    achieved = nbytes / n / (ms_step / n * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            "traffic": None, "kernel": "gemm_tn_kernel (tcgen05), decode-step launches", "launches_per_decode_step": n,
+            "alg_bytes_per_launch": nbytes / n, "avg_launch_us": ms_step / n * 1e3, "gemm_ms_per_decode_step": ms_step,
+            "gemm_tflops_in_decode": flops / (ms_step * 1e-3) / 1e12, "peak_src": peaks["src"]}, ms_step
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+
+    from surya_b200 import _lib
+    from surya_b200.config import syn_rec
+    from surya_b200.recognition import RecEngine, RecognitionRunner, build_prefill_plan, pack_rec_weights
+    from surya_b200.synth import rec_state_dict, rec_synthetic_crops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise _lib.SuryaB200Error("bench.py needs a B200 (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = _peaks()
+    cfg = syn_rec()
+    dtype = torch.bfloat16
+
+    # ---- weights: rank 0 packs, NCCL broadcast to the replicas
+    if rank == 0:
+        weights = pack_rec_weights(rec_state_dict(cfg, seed=0), cfg, dtype, dev)
+        meta = [(tuple(w.shape), str(w.dtype)) for w in weights]
+    else:
+        weights, meta = None, None
+    if world > 1:
+        box = [meta]
+        dist.broadcast_object_list(box, src=0)
+        meta = box[0]
+        if rank != 0:
+            weights = [torch.empty(s, dtype=getattr(torch, d.split(".")[-1]), device=dev) for s, d in meta]
+        for w in weights:
+            dist.broadcast(w, src=0)
+    eng = RecEngine(cfg, None, dtype=dtype, device=dev, max_slots=B_PER_GPU + 4, s_max=256, max_patches=B_PER_GPU * 160,
+                    max_tokens=B_PER_GPU * 46, packed_weights=weights)
+    runner = RecognitionRunner(eng, batch_size=B_PER_GPU, max_tokens=MAX_TOKENS)
+    crops = list(rec_synthetic_crops(B_PER_GPU, CROP_H, CROP_W, seed=1234 + rank))
+    tiles, grids, seqs = runner.preprocess(crops)
+    tiles_host = torch.from_numpy(np.concatenate(tiles, 0)).pin_memory()
+    h2d_bytes = tiles_host.numel() * 4
+    slots = eng.alloc_slots(B_PER_GPU)
+    plan = build_prefill_plan(cfg, np.array(grids), seqs, slots)
+    h2d_bytes += plan.ints.numel() * 4 + plan.ids.numel() * 8
+    d2h_bytes = B_PER_GPU * MAX_TOKENS * (8 + 4 + 48)
+
+    # ---- resident step: inputs in HBM, outputs stay on the device
+    tiles_dev = tiles_host.to(dev)
+    plan.ints = plan.ints.to(dev)
+    plan.ids = plan.ids.to(dev)
+    slot_t = torch.tensor(slots, dtype=torch.int32, device=dev)
+    lens = torch.tensor([len(s) for s in seqs], dtype=torch.int32, device=dev)
+    ids_io = torch.empty(B_PER_GPU, dtype=torch.int64, device=dev)
+    pos_io = torch.empty(B_PER_GPU, dtype=torch.int32, device=dev)
+    hist = {"tok": torch.empty((MAX_TOKENS - 1, B_PER_GPU), dtype=torch.int64, device=dev),
+            "score": torch.empty((MAX_TOKENS - 1, B_PER_GPU), dtype=torch.float32, device=dev),
+            "bbox": torch.empty((MAX_TOKENS - 1, B_PER_GPU, 6), dtype=torch.int64, device=dev),
+            "done": torch.empty((MAX_TOKENS - 1, B_PER_GPU), dtype=torch.uint8, device=dev)}
+    gather_buf = [torch.empty((MAX_TOKENS - 1, B_PER_GPU), dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
+
+    def resident_step():
+        out = eng.prefill(tiles_dev, plan)
+        ids_io.copy_(out["next_ids"])
+        pos_io.copy_(lens)
+        eng.decode_steps(ids_io, slot_t, pos_io, MAX_TOKENS - 1, hist=hist)
+        if world > 1:
+            dist.all_gather(gather_buf, hist["tok"])
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for _ in range(args.warmup):
+        resident_step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms_total = timed(resident_step, args.steps)
+    launches = _lib.launch_count() - l0
+    ms_step = ms_total / args.steps
+    value = B_PER_GPU * world * args.steps / (ms_total * 1e-3)
+
+    # ---- phase split (CUDA events, rank-local, outside the headline region)
+    def prefill_only():
+        eng.prefill(tiles_dev, plan)
+
+    def decode_only():
+        pos_io.copy_(lens)
+        eng.decode_steps(ids_io, slot_t, pos_io, MAX_TOKENS - 1, hist=hist)
+
+    ms_prefill = timed(prefill_only, 3) / 3
+    ms_decode = timed(decode_only, 3) / 3
+    eng.release_slots(slots)
+
+    # ---- e2e: public API from pinned host buffers, results read back to the host
+    def e2e_step():
+        runner.run_preprocessed(tiles, grids, seqs, fixed_steps=True)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    ms_e2e_total = timed(e2e_step, max(1, min(args.steps, 3)))
+    e2e_n = max(1, min(args.steps, 3))
+    e2e_value = B_PER_GPU * world * e2e_n / (ms_e2e_total * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        roof, gemm_ms = decode_gemm_roofline(eng, peaks)
+        roof["share_of_step"] = gemm_ms * (MAX_TOKENS - 1) / ms_step
+        # whole-step algorithmic bounds for context
+        alg = {"decode_bytes_per_step_gb": 1.02, "decode_hbm_ms_at_peak": 1.02e9 * (MAX_TOKENS - 1) / (peaks["hbm_gbs"] * 1e9) * 1e3,
+               "prefill_gflop_per_crop": 53.26 + 19.0, "prefill_tensor_ms_at_peak": (53.26 + 19.0) * B_PER_GPU / (peaks["tf_sustained"] * 1e3) * 1e3}
+        cpu = None
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n_c = 16
+            one = cpu_oracle_sample(n_c, MAX_TOKENS, threads)
+            one()
+            t = one()
+            cpu = {"value": n_c / t, "unit": "crops/s", "cores": threads, "kind": "port",
+                   "sample": f"{n_c} crops x {MAX_TOKENS} tokens, fp32 oracle port of the reference modules, 1 warm-up + 1 timed"}
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": _config(world),
+            "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "api": "surya_b200.recognition.RecognitionRunner.run_preprocessed (host tiles -> tokens/scores/boxes)"},
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "phases_ms": {"prefill(vision+decoder)": ms_prefill, f"decode x{MAX_TOKENS - 1}": ms_decode,
+                          "decode_step": ms_decode / (MAX_TOKENS - 1)},
+            "algorithmic": alg, "engine_workspace_gb": eng.workspace_bytes / 1e9,
+        }))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -97,3 +97,32 @@ def tiny_rec() -> RecConfig:
 
 def align(x: int, m: int) -> int:
     return (x + m - 1) // m * m
+
+
+# ------------------------------------------------------------------------------------------------ detection
+@dataclass
+class DetConfig:
+    """Mirror of EfficientViTConfig (surya/detection/model/config.py:12-31)."""
+    num_channels: int = 3
+    widths: Tuple[int, ...] = (32, 64, 128, 256, 512)
+    depths: Tuple[int, ...] = (1, 1, 1, 6, 6)
+    strides: Tuple[int, ...] = (2, 2, 2, 2, 2)
+    head_dim: int = 32
+    layer_norm_eps: float = 1e-6
+    decoder_layer_hidden_size: int = 128
+    decoder_hidden_size: int = 512
+    num_labels: int = 2
+    head_bn_eps: float = 1e-5   # nn.BatchNorm2d default in DecodeHead (encoderdecoder.py:691)
+    mla_eps: float = 1e-5       # LiteMLA eps (encoderdecoder.py:287)
+
+    def to_dict(self) -> dict:
+        return asdict(self)
+
+
+def det_default() -> DetConfig:
+    return DetConfig()
+
+
+def det_tiny() -> DetConfig:
+    """Reduced depth (same block types and channel widths) for fast CPU oracle tests."""
+    return DetConfig(depths=(1, 1, 1, 2, 2))

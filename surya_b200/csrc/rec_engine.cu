@@ -39,6 +39,9 @@ struct sb_rec_engine {
   cudaGraphExec_t graph_exec = nullptr;
   int graph_batch = 0;
   long long graph_nodes = 0;
+  // the legacy default stream cannot be captured: decode_steps hops onto an engine-owned stream, ordered by events
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   const void* graph_key[8] = {nullptr};
 
   const void* W(int idx) const { return w[idx]; }
@@ -282,6 +285,9 @@ int sb_rec_create(const sb_rec_config* cfg, const void* const* weights, int n_we
 void sb_rec_destroy(sb_rec_engine* e) {
   if (!e) return;
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_out) cudaEventDestroy(e->ev_out);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
   if (e->arena) cudaFree(e->arena);
   delete e;
 }
@@ -326,8 +332,28 @@ int sb_rec_decode_steps(sb_rec_engine* e, long long* ids_io, const int* slot, in
                         int use_graph, void* stream) {
   if (!e) { set_error("sb_rec_decode_steps: null engine"); return -1; }
   if (batch > e->c.max_slots || batch > e->c.max_tokens) { set_error("sb_rec_decode_steps: batch exceeds capacity"); return -2; }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (cudaMemsetAsync(e->st_step, 0, sizeof(int), st) != cudaSuccess) { set_error("memset failed"); return -3; }
+  cudaStream_t caller = static_cast<cudaStream_t>(stream);
+  cudaStream_t st = caller;
+  const bool hop = use_graph && (caller == nullptr || caller == cudaStreamLegacy || caller == cudaStreamPerThread);
+  if (hop) {
+    if (!e->own_stream) {
+      if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("sb_rec_decode_steps: could not create the engine stream");
+        return -8;
+      }
+    }
+    cudaEventRecord(e->ev_in, caller);
+    cudaStreamWaitEvent(e->own_stream, e->ev_in, 0);
+    st = e->own_stream;
+  }
+  struct Rejoin {  // whatever happens below, order the caller's stream after the engine stream
+    bool on; cudaStream_t own, caller; cudaEvent_t ev;
+    ~Rejoin() { if (on) { cudaEventRecord(ev, own); cudaStreamWaitEvent(caller, ev, 0); } }
+  } rejoin{hop, e->own_stream, caller, e->ev_out};
+  if (cudaMemsetAsync(e->st_step, 0, sizeof(int), st) != cudaSuccess) { cudaGetLastError(); set_error("memset failed"); return -3; }
   auto one_step = [&](cudaStream_t s) -> int {
     CK(run_decode_step(e, ids_io, slot, pos_io, batch, nullptr, e->st_tok, e->st_score, e->st_bbox, nullptr, e->st_done,
                        e->st_next, s));
@@ -348,21 +374,22 @@ int sb_rec_decode_steps(sb_rec_engine* e, long long* ids_io, const int* slot, in
     n_steps -= 1;
     if (n_steps <= 0) return 0;
     cudaGraph_t graph = nullptr;
-    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { set_error("graph capture begin failed"); return -4; }
+    cudaError_t cb = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (cb != cudaSuccess) { cudaGetLastError(); set_error("graph capture begin failed: %s", cudaGetErrorString(cb)); return -4; }
     const long long before = launch_count();
     int rc = one_step(st);
     e->graph_nodes = launch_count() - before;
     count_launches(-e->graph_nodes);  // captured, not executed
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    if (rc || ce != cudaSuccess) { set_error("graph capture failed: rc=%d %s", rc, cudaGetErrorString(ce)); return -5; }
+    if (rc || ce != cudaSuccess) { cudaGetLastError(); set_error("graph capture failed: rc=%d %s", rc, cudaGetErrorString(ce)); return -5; }
     ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (ce != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); e->graph_exec = nullptr; return -6; }
+    if (ce != cudaSuccess) { cudaGetLastError(); set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); e->graph_exec = nullptr; return -6; }
     e->graph_batch = batch;
     std::memcpy(e->graph_key, key, sizeof(key));
   }
   for (int i = 0; i < n_steps; ++i) {
-    if (cudaGraphLaunch(e->graph_exec, st) != cudaSuccess) { set_error("cudaGraphLaunch failed"); return -7; }
+    if (cudaGraphLaunch(e->graph_exec, st) != cudaSuccess) { cudaGetLastError(); set_error("cudaGraphLaunch failed"); return -7; }
     count_launches(e->graph_nodes);
   }
   return 0;

@@ -262,11 +262,12 @@ class RecEngine:
 
     def __init__(self, cfg: RecConfig, state_dict: Dict[str, torch.Tensor], dtype: torch.dtype = torch.bfloat16,
                  device: str | torch.device = "cuda", max_slots: int = 256, s_max: Optional[int] = None,
-                 max_patches: int = 65536, max_tokens: int = 32768, max_seqs: Optional[int] = None):
+                 max_patches: int = 65536, max_tokens: int = 32768, max_seqs: Optional[int] = None,
+                 packed_weights: Optional[List[torch.Tensor]] = None):
         self.lib = _lib.load()
         self.cfg, self.dtype, self.device = cfg, dtype, torch.device(device)
         e, d = cfg.vision_encoder, cfg.decoder
-        self.weights = pack_rec_weights(state_dict, cfg, dtype, self.device)
+        self.weights = packed_weights if packed_weights is not None else pack_rec_weights(state_dict, cfg, dtype, self.device)
         self.s_max = s_max or cfg.max_sequence_length
         self.max_slots = max_slots
         mask = 0
@@ -590,6 +591,12 @@ class RecognitionRunner:
         slot_host = torch.zeros(Bsz, dtype=torch.int32).pin_memory()
         pos_io = torch.zeros(Bsz, dtype=torch.int32, device=dev)
         slot_t = torch.zeros(Bsz, dtype=torch.int32, device=dev)
+        # persistent history buffers: same pointers every call -> the captured decode graph is reused
+        T = max(1, self.max_tokens)
+        hist = {"tok": torch.empty((T, Bsz), dtype=torch.int64, device=dev),
+                "score": torch.empty((T, Bsz), dtype=torch.float32, device=dev),
+                "bbox": torch.empty((T, Bsz, 6), dtype=torch.int64, device=dev),
+                "done": torch.empty((T, Bsz), dtype=torch.uint8, device=dev)}
 
         def finish(row):
             eng.release_slots([row_slot[row]])
@@ -626,8 +633,8 @@ class RecognitionRunner:
                         slot_host[r] = row_slot[r]
                     pos_io.copy_(pos_host, non_blocking=True)
                     slot_t.copy_(slot_host, non_blocking=True)
-                    hist = eng.decode_steps(ids_io, slot_t, pos_io, n)
-                    th, sh, bh = hist["tok"].cpu().numpy(), hist["score"].cpu().numpy(), hist["bbox"].cpu().numpy()
+                    eng.decode_steps(ids_io, slot_t, pos_io, n, hist=hist)
+                    th, sh, bh = hist["tok"][:n].cpu().numpy(), hist["score"][:n].cpu().numpy(), hist["bbox"][:n].cpu().numpy()
                     for r in active:
                         p = row_prompt[r]
                         for s in range(n):

@@ -89,3 +89,78 @@ def rec_synthetic_crops(n: int, height: int = 48, width: int = 512, seed: int = 
     import numpy as np
 
     return np.random.default_rng(seed).integers(0, 256, size=(n, height, width, 3), dtype=np.uint8)
+
+
+# ------------------------------------------------------------------------------------------------ detection
+def _bn_params(name: str, n: int, seed: int) -> Dict[str, torch.Tensor]:
+    """Randomised BatchNorm affine + running stats so that folding is actually exercised."""
+    g = _gen(name, seed)
+    return {
+        f"{name}.weight": 0.5 + torch.rand(n, generator=g),
+        f"{name}.bias": 0.1 * torch.randn(n, generator=g),
+        f"{name}.running_mean": 0.1 * torch.randn(n, generator=g),
+        f"{name}.running_var": 0.5 + torch.rand(n, generator=g),
+    }
+
+
+def det_state_dict(cfg, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """fp32 state dict for EfficientViTForSemanticSegmentation (names: SURVEY.md §9.8 / det_arch.py).
+
+    Conv weights use a fan-in scaled normal (std = 1/sqrt(fan_in)) instead of the reference's 0.02 so that
+    activations keep O(1) magnitude through ~40 layers and the fp16 parity test exercises real dynamic range."""
+    from .det_arch import det_blocks, det_head_specs
+
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(spec):
+        fan_in = (spec.cin // spec.groups) * spec.k * spec.k
+        sd[spec.wkey] = _normal(spec.wkey, (spec.cout, spec.cin // spec.groups, spec.k, spec.k), fan_in ** -0.5, seed)
+        if spec.bias:
+            sd[spec.bkey] = _normal(spec.bkey, (spec.cout,), 0.1, seed)
+        if spec.norm:
+            sd.update(_bn_params(f"{spec.name}.norm", spec.cout, seed))
+
+    for blk in det_blocks(cfg):
+        for c in blk.convs:
+            conv(c)
+        for c in blk.mla or []:
+            conv(c)
+    hs = det_head_specs(cfg)
+    for name, cin, cout in hs["linear_c"]:
+        sd[f"{name}.weight"] = _normal(f"{name}.weight", (cout, cin), cin ** -0.5, seed)
+        sd[f"{name}.bias"] = _normal(f"{name}.bias", (cout,), 0.1, seed)
+    name, cin, cout = hs["fuse"]
+    sd[f"{name}.weight"] = _normal(f"{name}.weight", (cout, cin, 1, 1), cin ** -0.5, seed)
+    sd.update(_bn_params(hs["bn"], cout, seed))
+    name, cin, cout = hs["cls"]
+    sd[f"{name}.weight"] = _normal(f"{name}.weight", (cout, cin, 1, 1), cin ** -0.5, seed)
+    sd[f"{name}.bias"] = _normal(f"{name}.bias", (cout,), 0.1, seed)
+    return sd
+
+
+def det_synthetic_pages(n: int, size: int = 1024, seed: int = 1234, text_like: bool = False):
+    """BASELINE config 3 input: uint8 [n, size, size, 3]; uniform noise, or white pages with random dark boxes."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    if not text_like:
+        return rng.integers(0, 256, size=(n, size, size, 3), dtype=np.uint8)
+    pages = np.full((n, size, size, 3), 255, dtype=np.uint8)
+    for p in pages:
+        for _ in range(40):
+            h = int(rng.integers(8, 25))
+            w = int(rng.integers(40, size // 2))
+            y = int(rng.integers(0, size - h))
+            x = int(rng.integers(0, size - w))
+            p[y:y + h, x:x + w] = rng.integers(0, 80)
+    return pages
+
+
+def det_normalize(pages) -> torch.Tensor:
+    """SegformerImageProcessor: rescale 1/255 + ImageNet mean/std, NCHW fp32 (surya/detection/processor.py:94-95, 140-146)."""
+    import numpy as np
+
+    mean = np.array((0.485, 0.456, 0.406), dtype=np.float32)
+    std = np.array((0.229, 0.224, 0.225), dtype=np.float32)
+    x = (pages.astype(np.float32) * (1 / 255.0) - mean) / std
+    return torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2)))
