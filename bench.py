@@ -43,6 +43,21 @@ MAX_TOKENS = 128
 CROP_H, CROP_W = 48, 512
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    print(f"[bench +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def host_threads() -> int:
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 64))
+
+
 def _peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -88,8 +103,12 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+CPU_CROPS, CPU_STEPS = 8, 17   # bounded sample: 8 crops, prefill + 16 decode steps actually executed
+
+
 def cpu_oracle_sample(n_crops: int, steps: int, threads: int):
-    """Oracle port of the reference CPU path (fp32): prefill + (steps-1) decode steps over n_crops crops."""
+    """Oracle port of the reference CPU path (fp32, all modules of the path): prefill + (steps-1) decode steps over
+    n_crops crops.  Returns a callable giving (seconds for prefill+steps, seconds extrapolated to MAX_TOKENS)."""
     from oracle import rec_oracle as O
     from surya_b200.config import syn_rec
     from surya_b200.synth import rec_state_dict, rec_synthetic_crops
@@ -102,25 +121,39 @@ def cpu_oracle_sample(n_crops: int, steps: int, threads: int):
 
     def one():
         t0 = time.perf_counter()
-        O.greedy_decode(sd, cfg, batch, steps, torch.float32)
-        return time.perf_counter() - t0
+        O.greedy_decode(sd, cfg, batch, 1, torch.float32)            # prefill only
+        t_pre = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        O.greedy_decode(sd, cfg, batch, steps, torch.float32)        # prefill + (steps - 1) decode steps
+        t_all = time.perf_counter() - t0
+        per_step = max(t_all - t_pre, 0.0) / max(1, steps - 1)
+        return t_all, t_pre + per_step * (MAX_TOKENS - 1)
 
     return one
+
+
+def cpu_sample_text(n_crops, steps):
+    return (f"{n_crops} crops: prefill + {steps - 1} decode steps executed (fp32 oracle port of the reference modules); "
+            f"crops/s = crops / (t_prefill + t_decode_step x {MAX_TOKENS - 1}), i.e. decode extrapolated to {MAX_TOKENS} tokens")
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    n_crops = 16
-    one = cpu_oracle_sample(n_crops, MAX_TOKENS, threads)
-    for _ in range(max(1, min(args.warmup, 1))):
-        one()
-    times = [one() for _ in range(max(1, min(args.steps, 3)))]
+    threads = host_threads()
+    n_crops = CPU_CROPS
+    one = cpu_oracle_sample(n_crops, CPU_STEPS, threads)
+    log(f"reference arm: {threads} threads, warm-up")
+    one()
+    times = []
+    for i in range(max(1, min(args.steps, 2))):
+        t_run, t_full = one()
+        log(f"reference arm step {i}: ran {t_run:.1f}s, full-length estimate {t_full:.1f}s")
+        times.append(t_full)
     t = float(np.mean(times))
     v = n_crops / t
-    sample = f"{n_crops} crops x {MAX_TOKENS} tokens per step (fp32, SDPA-free eager math), {len(times)} timed steps"
+    sample = cpu_sample_text(n_crops, CPU_STEPS) + f", {len(times)} timed steps"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "crops/s", "n_gpus": args.gpus, "steps": len(times),
         "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -233,6 +266,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = _peaks()
+    log(f"rank {rank}/{world} on cuda:{local}")
     cfg = syn_rec()
     dtype = torch.bfloat16
 
@@ -252,6 +286,7 @@ def main():
             dist.broadcast(w, src=0)
     eng = RecEngine(cfg, None, dtype=dtype, device=dev, max_slots=B_PER_GPU + 4, s_max=256, max_patches=B_PER_GPU * 160,
                     max_tokens=B_PER_GPU * 46, packed_weights=weights)
+    log(f"engine ready, workspace {eng.workspace_bytes / 1e9:.2f} GB")
     runner = RecognitionRunner(eng, batch_size=B_PER_GPU, max_tokens=MAX_TOKENS)
     crops = list(rec_synthetic_crops(B_PER_GPU, CROP_H, CROP_W, seed=1234 + rank))
     tiles, grids, seqs = runner.preprocess(crops)
@@ -305,8 +340,11 @@ def main():
             ms = t.item()
         return ms
 
+    log("inputs ready; warm-up")
     for _ in range(args.warmup):
         resident_step()
+    torch.cuda.synchronize()
+    log("timed region")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -324,6 +362,7 @@ def main():
         pos_io.copy_(lens)
         eng.decode_steps(ids_io, slot_t, pos_io, MAX_TOKENS - 1, hist=hist)
 
+    log(f"resident: {ms_step:.2f} ms/step -> {value:.1f} crops/s; phase split")
     ms_prefill = timed(prefill_only, 3) / 3
     ms_decode = timed(decode_only, 3) / 3
     eng.release_slots(slots)
@@ -332,6 +371,7 @@ def main():
     def e2e_step():
         runner.run_preprocessed(tiles, grids, seqs, fixed_steps=True)
 
+    log(f"prefill {ms_prefill:.2f} ms, decode {ms_decode:.2f} ms; e2e")
     e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -341,6 +381,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
+        log(f"e2e {e2e_value:.1f} crops/s; roofline replay")
         roof, gemm_ms = decode_gemm_roofline(eng, peaks)
         roof["share_of_step"] = gemm_ms * (MAX_TOKENS - 1) / ms_step
         # whole-step algorithmic bounds for context
@@ -348,13 +389,13 @@ def main():
                "prefill_gflop_per_crop": 53.26 + 19.0, "prefill_tensor_ms_at_peak": (53.26 + 19.0) * B_PER_GPU / (peaks["tf_sustained"] * 1e3) * 1e3}
         cpu = None
         if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            n_c = 16
-            one = cpu_oracle_sample(n_c, MAX_TOKENS, threads)
-            one()
-            t = one()
-            cpu = {"value": n_c / t, "unit": "crops/s", "cores": threads, "kind": "port",
-                   "sample": f"{n_c} crops x {MAX_TOKENS} tokens, fp32 oracle port of the reference modules, 1 warm-up + 1 timed"}
+            threads = host_threads()
+            log(f"cpu_baseline: oracle port on {threads} threads")
+            one = cpu_oracle_sample(CPU_CROPS, CPU_STEPS, threads)
+            t_run, t_full = one()
+            log(f"cpu_baseline: ran {t_run:.1f}s, full-length estimate {t_full:.1f}s")
+            cpu = {"value": CPU_CROPS / t_full, "unit": "crops/s", "cores": threads, "kind": "port",
+                   "sample": cpu_sample_text(CPU_CROPS, CPU_STEPS) + ", single timed run"}
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",

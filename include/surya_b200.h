@@ -176,6 +176,53 @@ int sb_rec_decode_steps(sb_rec_engine* eng, long long* ids_io, const int* slot, 
  * 2-D position embedding, "x", "xl", "logits", "qkv") into dst (device). */
 int sb_rec_debug_copy(sb_rec_engine* eng, const char* name, void* dst, size_t bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ detection engine
+ * Replaces EfficientViTForSemanticSegmentation.forward (surya/detection/model/encoderdecoder.py:725-753) as called by
+ * DetectionPredictor.batch_detection (surya/detection/__init__.py:111-120), plus the predictor's x4 bilinear upsample
+ * (:120-129).  The network is handed over as a flat op program (built by surya_b200/detection.py from the config the
+ * way the reference assembles its modules) over NHWC activations; BatchNorm is folded into weights at pack time. */
+typedef struct sb_det_engine sb_det_engine;
+
+enum { SB_DOP_STEM = 0, SB_DOP_CONV = 1, SB_DOP_PW = 2, SB_DOP_DW = 3, SB_DOP_GPW = 4, SB_DOP_MLA = 5, SB_DOP_UPCAT = 6,
+       SB_DOP_CLS = 7 };
+
+typedef struct {
+  int op;                 /* SB_DOP_* */
+  int src[4];             /* input buffer ids (src[0] = main input; -2 = external pixel_values) */
+  int n_src;
+  int src_off[4];         /* UPCAT: channel offset of each source in the concatenated output */
+  int dst;                /* output buffer id (-3 = external logits) */
+  int res;                /* residual buffer id or -1 */
+  int w, b;               /* weight-table indices (-1 = none) */
+  int cin, cout, k, stride, pad, act, groups;
+  int heads, dim;         /* MLA */
+  float eps;              /* MLA */
+} sb_det_op;
+
+/* weights: device pointers (see surya_b200/detection.py:pack_det_weights for the per-op layouts);
+ * buf_elems[i]: capacity of workspace buffer i in elements PER IMAGE at the maximum resolution. */
+int sb_det_create(int dtype, const sb_det_op* ops, int n_ops, const void* const* weights, int n_weights,
+                  const long long* buf_elems, int n_bufs, int max_batch, sb_det_engine** out);
+void sb_det_destroy(sb_det_engine* eng);
+size_t sb_det_workspace_bytes(const sb_det_engine* eng);
+/* pixel_values: NCHW [B,3,H,W] (engine dtype, or fp32 when in_f32); logits: NCHW [B, num_labels, H/4, W/4] engine dtype. */
+int sb_det_forward(sb_det_engine* eng, const void* pixel_values, int in_f32, int B, int H, int W, void* logits,
+                   void* stream);
+/* F.interpolate(logits, size=(HO, WO), mode="bilinear").float() : NCHW fp32 out (surya/detection/__init__.py:120-132). */
+int sb_det_upsample(int dtype, const void* logits, float* out, int planes, int hs, int ws, int HO, int WO, void* stream);
+/* parity tap: copy workspace buffer `buf` (NHWC) into dst. */
+int sb_det_debug_copy(sb_det_engine* eng, int buf, void* dst, size_t bytes, void* stream);
+
+/* k x k dense convolution, NHWC, implicit GEMM on tcgen05 (op-level entry point used by the kernel tests). */
+int sb_conv2d_nhwc(int dtype, const void* in, const void* weight, const float* bias, const void* residual, void* out,
+                   int n_img, int H, int W, int Cin, int Cout, int ksize, int stride, int pad, int act, void* stream);
+int sb_dwconv_nhwc(int dtype, const void* in, const void* w, const float* bias, void* out, int B, int H, int W, int C,
+                   int ks, int stride, int pad, int act, void* stream);
+int sb_gemm_grouped(int dtype, const void* A, int lda, int a_cols, const void* W, int ldw, void* C, int ldc, int M, int N,
+                    int Kpad, int group_k, int group_n, void* stream);
+int sb_lite_mla(int dtype, const void* qkv_a, const void* qkv_b, void* out, int B, int HW, int heads, int dim, float eps,
+                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

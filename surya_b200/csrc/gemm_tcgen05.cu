@@ -12,6 +12,7 @@
 // Rounding to the storage type happens exactly where eager PyTorch has an op boundary (after the
 // Linear, after the activation, after the residual add) so results track the reference path.
 #include "gemm.cuh"
+#include "gemm_epilogue.cuh"
 #include "sb_ptx.cuh"
 
 #include <cstdarg>
@@ -20,34 +21,6 @@
 #include <mutex>
 
 namespace sb {
-
-struct GemmKParams {
-  int M, N, K;
-  void* C;
-  int ldc;
-  const float* bias;
-  const void* residual;
-  int ldr;
-  int act;
-  int swiglu;
-  int out_f32;
-  int group_m;
-};
-
-__device__ __forceinline__ float apply_act(float x, int act) {
-  switch (act) {
-    case ACT_GELU_ERF: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-    case ACT_SILU: return x / (1.0f + expf(-x));
-    case ACT_HARDSWISH: return x * fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) / 6.0f;
-    case ACT_RELU: return fmaxf(x, 0.0f);
-    case ACT_GELU_TANH: {
-      const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-      float inner = k0 * (x + k1 * x * x * x);
-      return 0.5f * x * (1.0f + tanhf(inner));
-    }
-    default: return x;
-  }
-}
 
 __device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks, int gm, int& mb, int& nb) {
   int per_group = gm * n_blocks;
@@ -117,7 +90,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sbp = sa + A_BYTES;
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-          tma_load_2d(sa, &tma_a, &full_bar[s], kb * BK, mb * BM);
+          tma_load_2d(sa, &tma_a, &full_bar[s], kb * BK + nb * p.group_k, mb * BM);
           tma_load_2d(sbp, &tma_b, &full_bar[s], kb * BK, nb * BN);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -175,78 +148,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tmem_ld_wait();
         const int col0 = nb * BN + c * 32;
         if (col0 >= p.N) continue;
-        float x[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (col0 + j < p.N) x[j] += __ldg(p.bias + col0 + j);
-          }
-        }
-        if (!row_ok) continue;
-        if (p.swiglu) {
-          // columns (2i, 2i+1) = (gate_i, up_i)
-          const int oc0 = col0 >> 1;
-          const int n_out = p.N >> 1;
-          T* crow = reinterpret_cast<T*>(p.C) + static_cast<size_t>(row) * p.ldc;
-          T o[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float g = rnd<T>(x[2 * i]);
-            float u = rnd<T>(x[2 * i + 1]);
-            float sact = rnd<T>(apply_act(g, p.act));
-            o[i] = from_f<T>(sact * u);
-          }
-          if (vec_ok && oc0 + 16 <= n_out) {
-            uint4* dst = reinterpret_cast<uint4*>(crow + oc0);
-            const uint4* src = reinterpret_cast<const uint4*>(o);
-            dst[0] = src[0];
-            dst[1] = src[1];
-          } else {
-            for (int i = 0; i < 16; ++i)
-              if (oc0 + i < n_out) crow[oc0 + i] = o[i];
-          }
-        } else if (p.out_f32) {
-          float* crow = reinterpret_cast<float*>(p.C) + static_cast<size_t>(row) * p.ldc;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float y = apply_act(x[j], p.act);
-            if (col0 + j < p.N) crow[col0 + j] = y;
-          }
-        } else {
-          T* crow = reinterpret_cast<T*>(p.C) + static_cast<size_t>(row) * p.ldc;
-          const T* rrow = p.residual ? reinterpret_cast<const T*>(p.residual) + static_cast<size_t>(row) * p.ldr : nullptr;
-          const bool full = (col0 + 32 <= p.N) && vec_ok;
-          T r[32];
-          if (rrow) {
-            if (full) {
-              const uint4* src = reinterpret_cast<const uint4*>(rrow + col0);
-              uint4* dst = reinterpret_cast<uint4*>(r);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) dst[i] = src[i];
-            } else {
-              for (int j = 0; j < 32; ++j) r[j] = (col0 + j < p.N) ? rrow[col0 + j] : from_f<T>(0.f);
-            }
-          }
-          T o[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float y = rnd<T>(x[j]);
-            if (p.act != ACT_NONE) y = rnd<T>(apply_act(y, p.act));
-            if (rrow) y = y + to_f<T>(r[j]);
-            o[j] = from_f<T>(y);
-          }
-          if (full) {
-            uint4* dst = reinterpret_cast<uint4*>(crow + col0);
-            const uint4* src = reinterpret_cast<const uint4*>(o);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = src[i];
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) crow[col0 + j] = o[j];
-          }
-        }
+        epilogue_chunk<T>(v, p, row, row_ok, col0, vec_ok);
       }
       tc_fence_before();
       __syncwarp();
@@ -339,6 +241,52 @@ int make_tma_2d(CUtensorMap* map, int dtype, const void* base, int rows, int K, 
   return 0;
 }
 
+int make_tma_2d_sw(CUtensorMap* map, int dtype, const void* base, int rows, int K, int ld, int box_k, int box_rows,
+                   int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return -1; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (static_cast<size_t>(ld) * 2) % 16 != 0) {
+    set_error("TMA operand must be 16B aligned with a 16B-multiple row pitch (ptr=%p ld=%d)", base, ld);
+    return -2;
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_k), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(2d) failed: %d", (int)r); return -3; }
+  return 0;
+}
+
+// NHWC activation map for the implicit-GEMM convolution: dims {C, W, H, N}; box {box_c, box_w, box_h, 1} OUTPUT
+// pixels, traversed with `stride` in W and H (boxDim = pixels * stride, elementStrides = stride).
+int make_tma_nhwc(CUtensorMap* map, int dtype, const void* base, int N, int H, int W, int C, int box_c, int box_w,
+                  int box_h, int stride, int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return -1; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (static_cast<size_t>(C) * 2) % 16 != 0) {
+    set_error("NHWC TMA operand must be 16B aligned with C %% 8 == 0 (ptr=%p C=%d)", base, C);
+    return -2;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = fn(map, dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(nhwc) failed: %d (N=%d H=%d W=%d C=%d box=%d,%d,%d stride=%d)", (int)r, N, H, W, C,
+              box_c, box_w, box_h, stride);
+    return -3;
+  }
+  return 0;
+}
+
 template <typename T, int BN, int STAGES>
 static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   constexpr uint32_t STAGE_BYTES = 128 * 64 * 2 + BN * 64 * 2;
@@ -354,9 +302,9 @@ static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   CUtensorMap ma, mb;
-  int rc = make_tma_2d(&ma, a.dtype, a.A, a.M, a.K, a.lda, 128);
+  int rc = make_tma_2d(&ma, a.dtype, a.A, a.M, a.group_k ? a.a_cols : a.K, a.lda, 128);
   if (rc) return rc;
-  rc = make_tma_2d(&mb, a.dtype, a.W, a.N, a.K, a.ldw, BN);
+  rc = make_tma_2d(&mb, a.dtype, a.W, a.N, a.K, a.ldw, BN);  // grouped: W is [N, K] with K = padded per-group depth
   if (rc) return rc;
   GemmKParams p;
   p.M = a.M; p.N = a.N; p.K = a.K;
@@ -365,6 +313,7 @@ static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   p.residual = a.residual; p.ldr = a.ldr;
   p.act = a.act; p.swiglu = a.swiglu; p.out_f32 = a.out_f32;
   p.group_m = 8;
+  p.group_k = a.group_k;
   int m_blocks = (a.M + 127) / 128, n_blocks = (a.N + BN - 1) / BN;
   int tiles = m_blocks * n_blocks;
   int grid = tiles < num_sms() ? tiles : num_sms();
@@ -388,6 +337,7 @@ static int launch_typed(const GemmArgs& a, cudaStream_t stream) {
     }
     if (a.swiglu && bn < 32) bn = 32;
   }
+  if (a.group_k) bn = a.group_n;  // one n-block per channel group
   switch (bn) {
     case 256: return launch_cfg<T, 256, 4>(a, stream);
     case 128: return launch_cfg<T, 128, 6>(a, stream);

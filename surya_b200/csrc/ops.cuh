@@ -40,6 +40,31 @@ struct AttnArgs {
 };
 int attn_varlen(const AttnArgs& a, cudaStream_t st);
 
+// k x k dense convolution (NHWC, implicit GEMM on tcgen05); weight [Cout, k*k*Cin] with K ordered (r, s, c).
+struct ConvArgs {
+  int dtype = DT_F16;
+  const void* in = nullptr;      // [n_img, H, W, Cin]
+  const void* weight = nullptr;  // [Cout, ksize*ksize*Cin]
+  const float* bias = nullptr;   // [Cout] fp32 (folded BN shift) or null
+  const void* residual = nullptr;  // [n_img, Ho, Wo, Cout] or null
+  void* out = nullptr;           // [n_img, Ho, Wo, Cout]
+  int n_img = 0, H = 0, W = 0, Cin = 0, Cout = 0, ksize = 3, stride = 1, pad = 1, act = ACT_NONE;
+};
+int conv_igemm(const ConvArgs& a, cudaStream_t st);
+
+// Detection-path CUDA-core kernels (det_ops.cu).
+int det_stem_conv(int dtype, const void* in, int in_f32, const float* w, const float* bias, void* out, int B, int H,
+                  int W, int cout, cudaStream_t st);
+int det_dwconv(int dtype, const void* in, const void* w, const float* bias, void* out, int B, int H, int W, int C, int ks,
+               int stride, int pad, int act, cudaStream_t st);
+int det_lite_mla(int dtype, const void* qkv_a, const void* qkv_b, void* out, int B, int HW, int heads, int dim, float eps,
+                 cudaStream_t st);
+int det_upsample_cat(int dtype, const void* const* src, const int* hs, const int* ws, const int* ch_off, int n_src, int CS,
+                     void* dst, int B, int HO, int WO, cudaStream_t st);
+int det_classifier(int dtype, const void* x, const void* w, const void* b, void* out, long long P, int C, int HW, int n_out,
+                   cudaStream_t st);
+int det_upsample_nchw(int dtype, const void* in, float* out, int planes, int hs, int ws, int HO, int WO, cudaStream_t st);
+
 // Single-token decode attention over the slot KV cache, fused with RoPE(q,k) and the in-place cache append.
 //   qkv[b] = [q(nh*d) | k(nkv*d) | v(nkv*d)] for batch row b; slot[b], pos[b] (= number of cached tokens) on device.
 //   cache layout: [slot][kv_head][s_max][d]; writes rotated k / v at index pos[b], then attends over 0..pos[b].

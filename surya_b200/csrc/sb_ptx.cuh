@@ -134,6 +134,17 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
   return d;
 }
 
+// Same for 64-byte-swizzled tiles (rows of 32 x 16-bit elements; 8-row groups 512 B apart): SWIZZLE_64B = 4.
+__device__ __forceinline__ uint64_t umma_desc_k64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16, fp32 accumulate, both operands K-major.
 // fmt: 0 = f16, 1 = bf16.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t fmt, uint32_t M, uint32_t N) {

@@ -5,6 +5,8 @@ libsurya_b200.so on torch's current CUDA stream and raises if the library or a G
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -151,3 +153,47 @@ def small_head(x, w, b, sigmoid=True, box_scale=None):
                             c_int(n_out), c_int(1 if sigmoid else 0), ptr(out_f), ptr(out_box),
                             c_float(box_scale if box_scale is not None else 0.0), stream_ptr()), "sb_small_head")
     return out_f, out_box
+
+
+# ------------------------------------------------------------------------------------------------ detection ops (NHWC)
+def conv2d_nhwc(x, w, bias=None, residual=None, ksize=3, stride=1, pad=1, act="none"):
+    """x [N,H,W,Cin], w [Cout, k*k*Cin] (K ordered r,s,c), bias fp32 [Cout] -> [N,Ho,Wo,Cout]."""
+    lib = _lib.load()
+    N, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    Ho, Wo = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
+    out = torch.empty((N, Ho, Wo, Cout), device=x.device, dtype=x.dtype)
+    check(lib.sb_conv2d_nhwc(dt_code(x.dtype), ptr(x), ptr(w), ptr(bias), ptr(residual), ptr(out), c_int(N), c_int(H), c_int(W),
+                             c_int(Cin), c_int(Cout), c_int(ksize), c_int(stride), c_int(pad), c_int(ACT[act]), stream_ptr()),
+          "sb_conv2d_nhwc")
+    return out
+
+
+def dwconv_nhwc(x, w, bias=None, ksize=3, stride=1, pad=1, act="none"):
+    """x [N,H,W,C], w [k*k, C]."""
+    lib = _lib.load()
+    N, H, W, C = x.shape
+    Ho, Wo = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
+    out = torch.empty((N, Ho, Wo, C), device=x.device, dtype=x.dtype)
+    check(lib.sb_dwconv_nhwc(dt_code(x.dtype), ptr(x), ptr(w), ptr(bias), ptr(out), c_int(N), c_int(H), c_int(W), c_int(C),
+                             c_int(ksize), c_int(stride), c_int(pad), c_int(ACT[act]), stream_ptr()), "sb_dwconv_nhwc")
+    return out
+
+
+def gemm_grouped(a, w_pad, groups):
+    """Block-diagonal 1x1 conv: a [M, C], w_pad [C, 64] (row o of group g holds its C/groups inputs, zero padded)."""
+    lib = _lib.load()
+    M, C = a.shape
+    out = torch.empty((M, C), device=a.device, dtype=a.dtype)
+    check(lib.sb_gemm_grouped(dt_code(a.dtype), ptr(a), c_int(a.stride(0)), c_int(C), ptr(w_pad), c_int(64), ptr(out), c_int(C),
+                              c_int(M), c_int(C), c_int(64), c_int(C // groups), c_int(C // groups), stream_ptr()),
+          "sb_gemm_grouped")
+    return out
+
+
+def lite_mla(qkv_a, qkv_b, B, HW, heads, dim, eps):
+    lib = _lib.load()
+    out = torch.empty((B * HW, 2 * heads * dim), device=qkv_a.device, dtype=qkv_a.dtype)
+    check(lib.sb_lite_mla(dt_code(qkv_a.dtype), ptr(qkv_a), ptr(qkv_b), ptr(out), c_int(B), c_int(HW), c_int(heads), c_int(dim),
+                          ctypes.c_float(eps), stream_ptr()), "sb_lite_mla")
+    return out

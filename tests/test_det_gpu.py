@@ -1,0 +1,142 @@
+"""Detection path parity (GPU): kernels vs PyTorch fp32 restatements, engine vs the CPU oracle and the reference golden.
+North-star tolerance: sigmoid heatmaps within 1e-3 (fp16) of the reference path on identical inputs."""
+import json
+from pathlib import Path
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+OUT = ROOT / "gpurun_out"
+GOLDEN = ROOT / "tests" / "golden"
+
+
+def _report(name, payload):
+    OUT.mkdir(exist_ok=True)
+    path = OUT / "det_parity.json"
+    data = json.loads(path.read_text()) if path.exists() else {}
+    data[name] = payload
+    path.write_text(json.dumps(data, indent=1))
+
+
+@pytest.mark.parametrize("cin,cout,stride,hw,act,res", [
+    (32, 32, 1, (64, 48), "hardswish", False), (32, 512, 2, (64, 64), "hardswish", False), (64, 256, 1, (40, 56), "hardswish", False),
+    (64, 1024, 2, (32, 64), "none", False), (128, 512, 1, (24, 40), "hardswish", False), (32, 32, 1, (72, 80), "none", True),
+    (64, 96, 1, (17, 23), "relu", True),
+])
+def test_conv3x3_igemm(built_lib, cin, cout, stride, hw, act, res):
+    from surya_b200 import ops
+
+    dtype = torch.float16
+    g = torch.Generator(device="cuda").manual_seed(cin + cout + stride)
+    N, (H, W) = 3, hw
+    x = torch.randn(N, H, W, cin, device="cuda", generator=g).to(dtype)
+    w = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * (cin * 9) ** -0.5).to(dtype)
+    b = torch.randn(cout, device="cuda", generator=g) * 0.1
+    Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+    r = torch.randn(N, Ho, Wo, cout, device="cuda", generator=g).to(dtype) if res else None
+    out = ops.conv2d_nhwc(x, w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous(), b, r, 3, stride, 1, act)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), b, stride=stride, padding=1).to(dtype).float()
+    if act == "hardswish":
+        ref = F.hardswish(ref).to(dtype).float()
+    elif act == "relu":
+        ref = F.relu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    if res:
+        ref = (ref + r.float()).to(dtype).float()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 8e-3, f"conv3x3 cin={cin} cout={cout} s={stride}: max err {err}"
+
+
+@pytest.mark.parametrize("ks,stride,C", [(3, 1, 64), (3, 2, 2048), (5, 1, 1536)])
+def test_dwconv(built_lib, ks, stride, C):
+    from surya_b200 import ops
+
+    dtype = torch.float16
+    g = torch.Generator(device="cuda").manual_seed(ks + C)
+    x = torch.randn(2, 20, 28, C, device="cuda", generator=g).to(dtype)
+    w = (torch.randn(C, 1, ks, ks, device="cuda", generator=g) / ks).to(dtype)
+    b = torch.randn(C, device="cuda", generator=g) * 0.1
+    pad = ks // 2
+    out = ops.dwconv_nhwc(x, w.reshape(C, ks * ks).t().contiguous(), b, ks, stride, pad, "hardswish")
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), b, stride=stride, padding=pad, groups=C).to(dtype).float()
+    ref = F.hardswish(ref).permute(0, 2, 3, 1)
+    assert (out.float() - ref).abs().max().item() < 4e-3
+
+
+def test_grouped_pw_and_lite_mla(built_lib):
+    from surya_b200 import ops
+
+    dtype = torch.float16
+    g = torch.Generator(device="cuda").manual_seed(0)
+    B, HW, heads, dim = 2, 300, 16, 32
+    C = 3 * heads * dim
+    a = torch.randn(B * HW, C, device="cuda", generator=g).to(dtype)
+    w = (torch.randn(C, 32, device="cuda", generator=g) * 32 ** -0.5).to(dtype)
+    wp = torch.zeros(C, 64, device="cuda", dtype=dtype)
+    wp[:, :32] = w
+    out = ops.gemm_grouped(a, wp, groups=3 * heads)
+    ref = F.conv2d(a.float().t().reshape(1, C, B * HW, 1), w.float().reshape(C, 32, 1, 1), groups=3 * heads).reshape(C, -1).t()
+    assert (out.float() - ref).abs().max().item() < 4e-3
+    qa = torch.randn(B * HW, C, device="cuda", generator=g).to(dtype)
+    qb = torch.randn(B * HW, C, device="cuda", generator=g).to(dtype)
+    o = ops.lite_mla(qa, qb, B, HW, heads, dim, 1e-5)
+    ms = torch.cat([qa.reshape(B, HW, C), qb.reshape(B, HW, C)], -1).reshape(B, HW, 2 * heads, 3 * dim).permute(0, 2, 1, 3).float()
+    q, k, v = ms.chunk(3, -1)
+    q, k = F.relu(q), F.relu(k)
+    v = F.pad(v, (0, 1), value=1.0)
+    kv = k.transpose(-1, -2) @ v
+    r = q @ kv
+    r = (r[..., :-1] / (r[..., -1:] + 1e-5)).permute(0, 2, 1, 3).reshape(B * HW, 2 * heads * dim)
+    assert (o.float() - r).abs().max().item() < 2e-3 * max(1.0, r.abs().max().item())
+
+
+@pytest.mark.parametrize("kind,size", [("tiny", (256, 256)), ("tiny", (384, 512)), ("default", (1024, 1024))])
+def test_engine_vs_oracle(built_lib, kind, size):
+    from oracle import det_oracle as D
+    from surya_b200.config import det_default, det_tiny
+    from surya_b200.detection import DetEngine
+    from surya_b200.synth import det_normalize, det_state_dict, det_synthetic_pages
+
+    cfg = det_tiny() if kind == "tiny" else det_default()
+    sd = det_state_dict(cfg, seed=0)
+    B = 2
+    pages = det_synthetic_pages(B, max(size), seed=3, text_like=(kind == "default"))[:, : size[0], : size[1]]
+    x = det_normalize(pages)
+    eng = DetEngine(cfg, sd, torch.float16, max_batch=2, max_hw=size)
+    got = eng.forward(x.cuda())
+    up = eng.upsample(got, size)
+    torch.cuda.synchronize()
+    ref = D.forward(sd, cfg, x)
+    err = (got.float().cpu() - ref).abs().max().item()
+    ref_up = D.upsample_to_input(ref, size)
+    err_up = (up.cpu() - ref_up).abs().max().item()
+    _report(f"{kind}_{size[0]}x{size[1]}", {"max_abs_err_vs_fp32_oracle": err, "max_abs_err_upsampled": err_up,
+                                            "ref_min": ref.min().item(), "ref_max": ref.max().item(), "ref_std": ref.std().item()})
+    assert got.shape == ref.shape
+    assert err < 2e-3, f"heatmap max abs err {err}"
+    assert err_up < 2e-3
+    eng.close()
+
+
+def test_engine_vs_reference_golden(built_lib):
+    from surya_b200.config import det_default
+    from surya_b200.detection import B200EfficientViT, DetEngine
+    from surya_b200.synth import det_normalize, det_state_dict, det_synthetic_pages
+
+    g = torch.load(GOLDEN / "det_default.pt")
+    cfg = det_default()
+    sd = det_state_dict(cfg, seed=0)
+    x = det_normalize(det_synthetic_pages(1, 512, seed=11, text_like=True))
+    assert abs(x.double().sum().item() - g["input_checksum"].item()) < 1e-3
+    eng = DetEngine(cfg, sd, torch.float16, max_batch=1, max_hw=(512, 512))
+    model = B200EfficientViT(eng)
+    assert model.config.num_labels == 2
+    out = model(pixel_values=x.to("cuda", torch.float16)).logits
+    err = (out.float().cpu() - g["logits"]).abs().max().item()
+    _report("golden_512", {"max_abs_err_vs_reference": err})
+    assert err < 2e-3
+    eng.close()

@@ -1,0 +1,74 @@
+"""World-size-2 gloo test of the sharding host logic (deal, weight broadcast, result all-gather)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _fake_run(widths, max_tokens):
+    def run(indices):
+        toks, scs = [], []
+        boxes = np.zeros((len(indices), max_tokens, 6), np.int64)
+        for j, i in enumerate(indices):
+            L = 1 + (i * 7) % max_tokens
+            toks.append([(i * 31 + k) % 1000 for k in range(L)])
+            scs.append([0.5 + 0.001 * k for k in range(L)])
+            boxes[j, :L] = i
+        return toks, scs, boxes
+    return run
+
+
+def _worker(rank, world, port, widths, max_tokens, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from surya_b200.shard import broadcast_tensors, sharded_recognition
+
+    w = [torch.arange(12, dtype=torch.float32).reshape(3, 4), torch.ones(5, dtype=torch.bfloat16) * 3] if rank == 0 else None
+    w = broadcast_tensors(w)
+    ok_w = torch.equal(w[0], torch.arange(12, dtype=torch.float32).reshape(3, 4)) and w[1].dtype == torch.bfloat16 and float(w[1].sum()) == 15.0
+    out = sharded_recognition(_fake_run(widths, max_tokens), widths, max_tokens)
+    q.put((rank, ok_w, out[0], out[1], out[2].sum()))
+    dist.destroy_process_group()
+
+
+def test_deal_round_robin_balances_width_sorted_units():
+    from surya_b200.shard import deal_round_robin
+
+    widths = [100, 500, 300, 500, 50, 700, 20]
+    shares = deal_round_robin(widths, 2)
+    assert sorted(shares[0] + shares[1]) == list(range(7))
+    assert shares[0][0] == 5 and shares[1][0] == 1            # widest first, ties by index
+    assert abs(len(shares[0]) - len(shares[1])) <= 1
+
+
+def test_sharded_gather_world2_matches_single_process():
+    widths = [int(w) for w in np.random.default_rng(0).integers(20, 900, size=13)]
+    max_tokens = 16
+    from surya_b200.shard import sharded_recognition
+
+    ref = sharded_recognition(_fake_run(widths, max_tokens), widths, max_tokens)     # world size 1
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, widths, max_tokens, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok_w, toks, scs, boxsum in res:
+        assert ok_w, "weight broadcast mismatch"
+        assert toks == ref[0]
+        assert all(np.allclose(a, b) for a, b in zip(scs, ref[1]))
+        assert boxsum == ref[2].sum()
