@@ -43,6 +43,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = cp.tiles_x * cp.tiles_y;
@@ -126,6 +127,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     const int q = warp & 3;
     int as = 0; uint32_t aph = 0;
     const bool vec_ok = (p.ldc % 8 == 0) && (!p.residual || p.ldr % 8 == 0);
+    const bool v2 = epilogue_v2_ok(p);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int img, oy0, ox0, nb;
       coords(tile, img, oy0, ox0, nb);
@@ -135,15 +137,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const int oy = oy0 + m / TW, ox = ox0 + m % TW;
       const bool row_ok = oy < cp.Ho && ox < cp.Wo;
       const int row = (img * cp.Ho + oy) * cp.Wo + ox;
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      if (v2) {
+        epilogue_tile_v2<T, BN>(tacc, p, epi_smem + q * EPI_WARP_BYTES, lane,
+                                [&](int r) {
+                                  const int mm = q * 32 + r;
+                                  const int yy = oy0 + mm / TW, xx = ox0 + mm % TW;
+                                  return (yy < cp.Ho && xx < cp.Wo) ? (img * cp.Ho + yy) * cp.Wo + xx : -1;
+                                }, nb * BN);
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = nb * BN + c * 32;
-        if (col0 >= p.N) continue;
-        epilogue_chunk<T>(v, p, row, row_ok, col0, vec_ok);
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld_32x32(tacc + c * 32, v);
+          tmem_ld_wait();
+          const int col0 = nb * BN + c * 32;
+          if (col0 >= p.N) continue;
+          epilogue_chunk<T>(v, p, row, row_ok, col0, vec_ok);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -160,7 +172,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 template <typename T, int BN, int BKC, int STAGES>
 static int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   constexpr uint32_t STAGE_BYTES = 128 * BKC * 2 + BN * BKC * 2;
-  constexpr size_t SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  constexpr size_t SMEM = STAGES * STAGE_BYTES + 1024 + 256 + EPI_SMEM_BYTES;
   auto kern = conv_igemm_kernel<T, BN, BKC, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {

@@ -48,6 +48,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES + 256;   // 4 x EPI_WARP_BYTES staging for the epilogue warps
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -133,6 +134,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     int as = 0;
     uint32_t aph = 0;
     const bool vec_ok = (p.ldc % 8 == 0) && (!p.residual || p.ldr % 8 == 0);
+    const bool v2 = epilogue_v2_ok(p);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int mb, nb;
       tile_coords(tile, m_blocks, n_blocks, p.group_m, mb, nb);
@@ -140,15 +142,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       tc_fence_after();
       const int row = mb * BM + q * 32 + lane;
       const bool row_ok = row < p.M;
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      if (v2) {
+        const int row0 = mb * BM + q * 32;
+        epilogue_tile_v2<T, BN>(tacc, p, epi_smem + q * EPI_WARP_BYTES, lane,
+                                [&](int r) { return row0 + r < p.M ? row0 + r : -1; }, nb * BN);
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge lanes that skipped the previous chunk
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = nb * BN + c * 32;
-        if (col0 >= p.N) continue;
-        epilogue_chunk<T>(v, p, row, row_ok, col0, vec_ok);
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge lanes that skipped the previous chunk
+          tmem_ld_32x32(tacc + c * 32, v);
+          tmem_ld_wait();
+          const int col0 = nb * BN + c * 32;
+          if (col0 >= p.N) continue;
+          epilogue_chunk<T>(v, p, row, row_ok, col0, vec_ok);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -290,7 +299,7 @@ int make_tma_nhwc(CUtensorMap* map, int dtype, const void* base, int N, int H, i
 template <typename T, int BN, int STAGES>
 static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   constexpr uint32_t STAGE_BYTES = 128 * 64 * 2 + BN * 64 * 2;
-  constexpr size_t SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  constexpr size_t SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_SMEM_BYTES;
   static bool attr_set = false;
   auto kern = gemm_tn_kernel<T, BN, STAGES>;
   if (!attr_set) {

@@ -128,12 +128,19 @@ __global__ void rope_vision_kernel(T* __restrict__ qkv, int ld, const int2* __re
   const int half = d >> 1, quarter = d >> 2;
   int2 p = pos[tok];
   T* row = qkv + static_cast<size_t>(tok) * ld;
+  // cos/sin once per (token, frequency); shared by all q and k heads
+  __shared__ float s_cos[128], s_sin[128];
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    float f = (i < quarter) ? static_cast<float>(p.x) * inv_freq[i] : static_cast<float>(p.y) * inv_freq[i - quarter];
+    s_cos[i] = cosf(f);
+    s_sin[i] = sinf(f);
+  }
+  __syncthreads();
   const int total = 2 * nh * half;  // (q|k) x heads x pairs
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     int i = idx % half;
     int hh = idx / half;  // 0 .. 2*nh-1 (q heads then k heads; contiguous in memory)
-    float f = (i < quarter) ? static_cast<float>(p.x) * inv_freq[i] : static_cast<float>(p.y) * inv_freq[i - quarter];
-    float c = cosf(f), s = sinf(f);
+    float c = s_cos[i], s = s_sin[i];
     T* h = row + hh * d;
     float x1 = to_f<T>(h[i]), x2 = to_f<T>(h[i + half]);
     float o1 = __fadd_rn(__fmul_rn(x1, c), __fmul_rn(-x2, s));
@@ -177,12 +184,18 @@ __global__ void rope_kv_append_kernel(T* __restrict__ qkv, int ld, const int* __
   const int pos = tok_pos[tok];
   const int slot = tok_slot[tok];
   T* row = qkv + static_cast<size_t>(tok) * ld;
+  __shared__ float s_cos[128], s_sin[128];
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    float f = static_cast<float>(pos) * inv_freq[i];
+    s_cos[i] = rnd<T>(cosf(f));
+    s_sin[i] = rnd<T>(sinf(f));
+  }
+  __syncthreads();
   const int n_rot = (nh + nkv) * half;
   for (int idx = threadIdx.x; idx < n_rot; idx += blockDim.x) {
     int i = idx % half;
     int hh = idx / half;
-    float f = static_cast<float>(pos) * inv_freq[i];
-    float c = rnd<T>(cosf(f)), s = rnd<T>(sinf(f));
+    float c = s_cos[i], s = s_sin[i];
     T* h = row + hh * d;
     float x1 = to_f<T>(h[i]), x2 = to_f<T>(h[i + half]);
     float o1, o2;

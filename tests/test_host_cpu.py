@@ -181,3 +181,44 @@ def test_detect_repeat_token_matches_oracle():
         toks = rng.integers(0, k, size=n).tolist()
         assert got(toks) == ref(toks)
     assert got([7] * 40) and not got([7] * 39)
+
+
+def test_det_oracle_pinned_to_reference_golden():
+    from oracle import det_oracle as D
+    from surya_b200.config import det_default
+    from surya_b200.synth import det_normalize, det_state_dict, det_synthetic_pages
+
+    g = torch.load(GOLDEN / "det_default.pt")
+    cfg = det_default()
+    sd = det_state_dict(cfg, seed=0)
+    x = det_normalize(det_synthetic_pages(1, 512, seed=11, text_like=True))
+    assert abs(x.double().sum().item() - g["input_checksum"].item()) < 1e-3
+    got = D.forward(sd, cfg, x)
+    assert (got - g["logits"]).abs().max().item() < 1e-5
+
+
+def test_det_program_structure():
+    from surya_b200.config import det_default
+    from surya_b200.detection import OP_CLS, OP_CONV, OP_MLA, OP_STEM, pack_det_program, plan_buffers
+    from surya_b200.synth import det_state_dict
+
+    cfg = det_default()
+    prog = pack_det_program(det_state_dict(cfg, 0), cfg, torch.float16, "cpu")
+    kinds = [o["op"] for o in prog.ops]
+    assert kinds[0] == OP_STEM and kinds[-1] == OP_CLS
+    assert kinds.count(OP_MLA) == cfg.depths[-1] and kinds.count(OP_CONV) == 6
+    caps = plan_buffers(prog, 1024, 1024)
+    names = prog.buf_names
+    assert caps[names.index("feat0")] == 256 * 256 * 64 and caps[names.index("feat3")] == 32 * 32 * 512
+    assert caps[names.index("cat")] == 256 * 256 * 512
+    # BN folding is exact in fp32: folded 1x1 conv == conv + BN on random input
+    import torch.nn.functional as F
+    from surya_b200.detection import _fold
+    from surya_b200.det_arch import det_blocks
+    sd = det_state_dict(cfg, 0)
+    c = det_blocks(cfg)[3].convs[1]
+    w, b = _fold(sd, c)
+    x = torch.randn(2, c.cin, 5, 5)
+    n = f"{c.name}.norm"
+    ref = F.batch_norm(F.conv2d(x, sd[c.wkey]), sd[f"{n}.running_mean"], sd[f"{n}.running_var"], sd[f"{n}.weight"], sd[f"{n}.bias"], False, 0.0, c.eps)
+    assert torch.allclose(F.conv2d(x, w, b), ref, atol=1e-4)
