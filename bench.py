@@ -237,6 +237,67 @@ def decode_gemm_roofline(eng, peaks, reps=20):
             "gemm_tflops_in_decode": flops / (ms_step * 1e-3) / 1e12, "peak_src": peaks["src"]}, ms_step
 
 
+def detection_bench(dev, peaks, world, steps, warmup):
+    """BASELINE config 3 (secondary metric pages/sec): 32 synthetic 1024x1024 pages per GPU, EfficientViT-L seg
+    forward (default config, fp16, BN folded) + x4 bilinear upsample to fp32 on the device."""
+    import torch.distributed as dist
+
+    from surya_b200.config import det_default
+    from surya_b200.detection import DetEngine, detect_heatmaps
+    from surya_b200.synth import det_normalize, det_state_dict, det_synthetic_pages
+
+    B, S = 32, 1024
+    cfg = det_default()
+    eng = DetEngine(cfg, det_state_dict(cfg, 0), torch.float16, device=dev, max_batch=B, max_hw=(S, S))
+    x_host = det_normalize(det_synthetic_pages(B, S, seed=1234)).half().pin_memory()
+    x = x_host.to(dev)
+    out_host = torch.empty((B, 2, S, S), dtype=torch.float32).pin_memory()
+
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    def resident():
+        eng.forward(x)
+
+    def e2e():
+        up = detect_heatmaps(eng, x_host.to(dev, non_blocking=True))
+        out_host.copy_(up, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, warmup)):
+        resident()
+    ms = timed(resident, steps) / steps
+    e2e()
+    ms_e2e = timed(e2e, max(1, min(steps, 3))) / max(1, min(steps, 3))
+    gflop_page = 252.5
+    tf = gflop_page * B / (ms * 1e-3) / 1e3
+    res = {"metric": "pages/sec (detection)", "value": B * world / (ms * 1e-3), "unit": "pages/s", "ms_per_step": ms,
+           "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "pages/s", "h2d_bytes_per_step": x_host.numel() * 2,
+                   "d2h_bytes_per_step": out_host.numel() * 4,
+                   "api": "surya_b200.detection.detect_heatmaps (pinned fp16 NCHW pages -> fp32 full-res heatmaps on host)"},
+           "config": {"workload": f"detection: {B} synthetic {S}x{S} pages per GPU, EfficientViT-L seg forward (default config)",
+                      "dtype": "f16"},
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                        "frac": tf / peaks["tf_sustained"], "alg_gflop_per_page": gflop_page, "scope": "whole forward"},
+           "engine_workspace_gb": eng.workspace_bytes / 1e9}
+    eng.close()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -244,6 +305,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-detection", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -378,6 +440,12 @@ def main():
     ms_e2e_total = timed(e2e_step, max(1, min(args.steps, 3)))
     e2e_n = max(1, min(args.steps, 3))
     e2e_value = B_PER_GPU * world * e2e_n / (ms_e2e_total * 1e-3)
+    det = None
+    if not args.no_detection:
+        log("detection (secondary metric)")
+        eng_ws = eng.workspace_bytes
+        det = detection_bench(dev, peaks, world, args.steps, args.warmup)
+        log(f"detection: {det['value']:.1f} pages/s resident, {det['e2e']['value']:.1f} e2e")
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -405,7 +473,7 @@ def main():
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
             "phases_ms": {"prefill(vision+decoder)": ms_prefill, f"decode x{MAX_TOKENS - 1}": ms_decode,
                           "decode_step": ms_decode / (MAX_TOKENS - 1)},
-            "algorithmic": alg, "engine_workspace_gb": eng.workspace_bytes / 1e9,
+            "algorithmic": alg, "engine_workspace_gb": eng.workspace_bytes / 1e9, "detection": det,
         }))
     eng.close()
     if world > 1:
