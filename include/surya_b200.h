@@ -45,6 +45,11 @@ int sb_gemm(int dtype, const void* A, int lda, const void* W, int ldw, void* C, 
             const float* bias, const void* residual, int ldr, int act, int swiglu, int out_f32, int force_bn,
             void* stream);
 
+/* sb_gemm with an in-kernel timeline of CTA 0 (globaltimer ns into timeline_dev[0..42]); profiling aid. */
+int sb_gemm_timeline(int dtype, const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
+                     const float* bias, const void* residual, int ldr, int act, int swiglu, int force_bn,
+                     unsigned long long* timeline_dev, void* stream);
+
 /* Qwen2RMSNorm (decoder/__init__.py:241-258, encoder/__init__.py:90-104); src_rows optional gather. */
 int sb_rmsnorm(int dtype, const void* x, int ldx, const void* w, void* y, int ldy, int rows, int H, float eps,
                const int* src_rows, void* stream);

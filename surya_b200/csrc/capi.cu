@@ -20,6 +20,16 @@ int sb_gemm(int dtype, const void* A, int lda, const void* W, int ldw, void* C, 
   return gemm_launch(a, static_cast<cudaStream_t>(stream));
 }
 
+int sb_gemm_timeline(int dtype, const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
+                     const float* bias, const void* residual, int ldr, int act, int swiglu, int force_bn,
+                     unsigned long long* timeline_dev, void* stream) {
+  GemmArgs a;
+  a.dtype = dtype; a.A = A; a.lda = lda; a.W = W; a.ldw = ldw; a.C = C; a.ldc = ldc;
+  a.M = M; a.N = N; a.K = K; a.bias = bias; a.residual = residual; a.ldr = ldr;
+  a.act = act; a.swiglu = swiglu; a.force_bn = force_bn; a.dbg = timeline_dev;
+  return gemm_launch(a, static_cast<cudaStream_t>(stream));
+}
+
 int sb_rmsnorm(int dtype, const void* x, int ldx, const void* w, void* y, int ldy, int rows, int H, float eps,
                const int* src_rows, void* stream) {
   return rmsnorm(dtype, x, ldx, w, y, ldy, rows, H, eps, src_rows, static_cast<cudaStream_t>(stream));

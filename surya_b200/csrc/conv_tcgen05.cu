@@ -27,7 +27,7 @@ struct ConvKParams {
 };
 
 template <typename T, int BN, int BKC, int STAGES>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const ConvKParams cp) {
   constexpr int BM = 128, TW = 16, TH = 8;
@@ -56,7 +56,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tma_a); tma_prefetch_desc(&tma_b); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -125,27 +125,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int epi_tid = threadIdx.x - 128;
+    uint8_t* stage = epi_smem + (warp - 4) * EPI_STAGE_BYTES;
+    float* sbias = reinterpret_cast<float*>(epi_smem + EPI_WARPS * EPI_STAGE_BYTES);
     int as = 0; uint32_t aph = 0;
     const bool vec_ok = (p.ldc % 8 == 0) && (!p.residual || p.ldr % 8 == 0);
     const bool v2 = epilogue_v2_ok(p);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int img, oy0, ox0, nb;
       coords(tile, img, oy0, ox0, nb);
+      if (v2) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        epilogue_stage_bias<BN>(p, sbias, epi_tid, nb * BN);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      const int m = q * 32 + lane;
-      const int oy = oy0 + m / TW, ox = ox0 + m % TW;
-      const bool row_ok = oy < cp.Ho && ox < cp.Wo;
-      const int row = (img * cp.Ho + oy) * cp.Wo + ox;
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       if (v2) {
-        epilogue_tile_v2<T, BN>(tacc, p, epi_smem + q * EPI_WARP_BYTES, lane,
+        epilogue_tile_v2<T, BN>(tacc, p, stage, sbias, lane, half,
                                 [&](int r) {
                                   const int mm = q * 32 + r;
                                   const int yy = oy0 + mm / TW, xx = ox0 + mm % TW;
                                   return (yy < cp.Ho && xx < cp.Wo) ? (img * cp.Ho + yy) * cp.Wo + xx : -1;
                                 }, nb * BN);
-      } else {
+      } else if (half == 0) {
+        const int m = q * 32 + lane;
+        const int oy = oy0 + m / TW, ox = ox0 + m % TW;
+        const bool row_ok = oy < cp.Ho && ox < cp.Wo;
+        const int row = (img * cp.Ho + oy) * cp.Wo + ox;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t v[32];
@@ -172,7 +181,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 template <typename T, int BN, int BKC, int STAGES>
 static int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   constexpr uint32_t STAGE_BYTES = 128 * BKC * 2 + BN * BKC * 2;
-  constexpr size_t SMEM = STAGES * STAGE_BYTES + 1024 + 256 + EPI_SMEM_BYTES;
+  constexpr size_t SMEM = STAGES * STAGE_BYTES + 1024 + 256 + epi_smem_bytes<BN>();
   auto kern = conv_igemm_kernel<T, BN, BKC, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -193,12 +202,12 @@ static int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   ConvKParams cp;
   cp.g.M = a.n_img * Ho * Wo; cp.g.N = a.Cout; cp.g.K = a.ksize * a.ksize * a.Cin;
   cp.g.C = a.out; cp.g.ldc = a.Cout; cp.g.bias = a.bias; cp.g.residual = a.residual; cp.g.ldr = a.Cout;
-  cp.g.act = a.act; cp.g.swiglu = 0; cp.g.out_f32 = 0; cp.g.group_m = 8;
+  cp.g.act = a.act; cp.g.swiglu = 0; cp.g.out_f32 = 0; cp.g.group_m = 8; cp.g.group_k = 0; cp.g.dbg = nullptr;
   cp.n_img = a.n_img; cp.Ho = Ho; cp.Wo = Wo; cp.Cin = a.Cin; cp.ksize = a.ksize; cp.stride = a.stride; cp.pad = a.pad;
   cp.tiles_x = (Wo + 15) / 16; cp.tiles_y = (Ho + 7) / 8;
   const int tiles = a.n_img * cp.tiles_x * cp.tiles_y * ((a.Cout + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 256, SMEM, stream>>>(ma, mb, cp);
+  kern<<<grid, 384, SMEM, stream>>>(ma, mb, cp);
   return launch_ok();
 }
 

@@ -28,6 +28,7 @@ struct GemmArgs {
   // grouped 1x1 convolution (block-diagonal weights): n-block g reads A columns [g*group_k, g*group_k + K) and
   // W rows [g*group_n, (g+1)*group_n); W is [N, K] with K the zero-padded per-group depth; a_cols = A's width.
   int group_k = 0, group_n = 0, a_cols = 0;
+  unsigned long long* dbg = nullptr;      // optional in-kernel timeline (see GemmKParams::dbg)
 };
 
 // Returns cudaSuccess or an error; sets a message retrievable through sb_last_error().

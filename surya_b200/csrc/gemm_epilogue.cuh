@@ -18,6 +18,8 @@ struct GemmKParams {
   int out_f32;
   int group_m;
   int group_k;  // grouped 1x1 conv: A column offset per n-block (0 = dense)
+  unsigned long long* dbg;  // optional timeline buffer (globaltimer ns) written by CTA 0: [0]=start [1]=setup done
+                            // [2+kb]=k-block kb landed (first tile) [40]=accumulator ready [41]=epilogue done
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -39,7 +41,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 // x = acc (+bias) -> round -> act -> round (+residual) -> round -> store; `row` is the global output row
 // (already translated to an NHWC pixel index by the convolution kernel), `col0` the first of 32 columns.
 template <typename T>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const GemmKParams& p, int row, bool row_ok,
+__device__ __noinline__ void epilogue_chunk(const uint32_t (&v)[32], const GemmKParams& p, int row, bool row_ok,
                                                int col0, bool vec_ok) {
   float x[32];
 #pragma unroll
@@ -117,20 +119,21 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Epilogue v2: per-warp shared-memory staging so that every global access is a coalesced 128-byte row segment.
+// Tile epilogue (8 warps): TMEM -> registers -> packed 16-bit math -> swizzled per-warp staging -> coalesced global.
 //
-// A warp owns 32 accumulator rows.  For each group of GW (= min(BN, 64)) accumulator columns:
-//   1. bias slice and (optionally) the residual sub-tile [32 rows x GWo cols] are fetched with coalesced 16-byte
-//      loads into the warp's staging buffer;
-//   2. each lane pulls its row's accumulators from TMEM (tcgen05.ld 32x32b.x32 per 32 columns), applies
-//      bias -> round -> act -> round (+residual) -> round exactly like epilogue_chunk, and writes the packed
-//      row back into the staging buffer (row pitch padded by 16 B: conflict-free for 16-byte accesses);
-//   3. the warp streams the staging buffer to global memory, 8 lanes per 128-byte row segment.
-// Requires ldc % 8 == 0, ldr % 8 == 0, N % 8 == 0 (N % 16 == 0 with SwiGLU) and 16-bit output; callers fall back to
-// epilogue_chunk otherwise.
-constexpr int EPI_PITCH = 64 * 2 + 16;                       // bytes per staged row (64 columns + pad)
-constexpr int EPI_WARP_BYTES = 32 * EPI_PITCH + 64 * 4;      // staging tile + bias slice
-constexpr int EPI_SMEM_BYTES = 4 * EPI_WARP_BYTES;
+// History (profiles/r01_gemm_prefill_ncu.md, tools/gemm_timeline.py): the first epilogue (epilogue_chunk above, kept as
+// the generic fallback) was instruction-fetch bound and took 30-40 us per 128x256 tile; staging + compile-time
+// activation brought it to 12.6 us, still longer than the 8.4 us main loop.  This version
+//   * runs on 8 warps (two per TMEM lane quarter, alternating 64/32-column groups) so each SM sub-partition has two
+//     epilogue warps to interleave;
+//   * stages the tile's bias slice in shared memory once, before the accumulator is ready (overlaps the main loop);
+//   * keeps the per-element instruction count minimal: packed cvt (cvt.rn.bf16x2.f32 / f16x2), one rounding per eager
+//     op boundary, residual fetched with coalesced 16-byte loads issued before the TMEM load they overlap with;
+//   * moves every global byte as part of a 64/128-byte row segment (XOR-swizzled staging, conflict-free).
+// Requires ldc % 8 == 0, ldr % 8 == 0, N % 8 == 0 (N % 16 == 0 and act == silu with SwiGLU), 16-bit output.
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_STAGE_BYTES = 32 * 128;                       // per warp: 32 rows x 128 B (swizzled, no padding)
+template <int BN> constexpr int epi_smem_bytes() { return EPI_WARPS * EPI_STAGE_BYTES + BN * 4; }
 
 __device__ __forceinline__ bool epilogue_v2_ok(const GemmKParams& p) {
   if (p.out_f32 || (p.ldc & 7) || (p.residual && (p.ldr & 7))) return false;
@@ -138,9 +141,24 @@ __device__ __forceinline__ bool epilogue_v2_ok(const GemmKParams& p) {
   return p.N % 8 == 0;
 }
 
-// Compile-time activation (keeps the per-element code of the hot loop small: a runtime switch inside the unrolled
-// element loop replicated erff/tanhf/expf bodies 32x and made the epilogue instruction-fetch bound, see
-// profiles/r01_gemm_prefill_ncu.md).
+template <typename T> struct Pk;
+template <> struct Pk<__nv_bfloat16> {
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  static __device__ __forceinline__ float lo(uint32_t u) { return __uint_as_float(u << 16); }
+  static __device__ __forceinline__ float hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+};
+template <> struct Pk<__half> {
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  static __device__ __forceinline__ float lo(uint32_t u) { return __half2float(__ushort_as_half(static_cast<unsigned short>(u & 0xffffu))); }
+  static __device__ __forceinline__ float hi(uint32_t u) { return __half2float(__ushort_as_half(static_cast<unsigned short>(u >> 16))); }
+};
+
 template <int ACT>
 __device__ __forceinline__ float act_ct(float x) {
   if constexpr (ACT == ACT_GELU_ERF) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
@@ -153,120 +171,139 @@ __device__ __forceinline__ float act_ct(float x) {
   } else return x;
 }
 
-// taddr: TMEM address of (lane quarter, first column of this tile's accumulator); row_fn(r) = global output row of the
-// warp's r-th accumulator row (0..31) or -1 when that row is outside the problem; n_col0 = first weight row of the tile.
+// byte offset of 16-byte chunk `ch` of staged row `row` for rows of CPR chunks (XOR swizzle, bank-conflict free)
+template <int CPR>
+__device__ __forceinline__ int stage_off(int row, int ch) {
+  if constexpr (CPR == 8) return row * 128 + ((ch ^ (row & 7)) << 4);
+  else if constexpr (CPR == 4) return row * 64 + ((ch ^ ((row >> 1) & 3)) << 4);
+  else if constexpr (CPR == 2) return row * 32 + ((ch ^ ((row >> 2) & 1)) << 4);
+  else return row * 16;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const int n = valid ? 16 : 0;   // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// One warp, one tile.  taddr: TMEM address (lane quarter, first accumulator column of the tile); row_fn(r): global output
+// row of the warp's r-th row or -1; n_col0: first weight row (accumulator column) of the tile; half: 0/1 = which of the two
+// warps sharing this lane quarter; sbias: the tile's bias slice (BN floats, already staged, zeros when absent).
+// stage: 4 KB per warp = residual sub-tile (cp.async, prefetched one group ahead) + output sub-tile, both swizzled.
 template <typename T, int BN, int ACT, bool SWIGLU, typename RowFn>
-__device__ __noinline__ void epilogue_tile_ct(uint32_t taddr, const GemmKParams& p, uint8_t* warp_smem, int lane,
-                                              RowFn row_fn, int n_col0) {
-  constexpr int GW = BN < 64 ? BN : 64;            // accumulator columns per group
-  constexpr int GWO = SWIGLU ? GW / 2 : GW;        // output columns per group
-  constexpr int CPR = GWO / 8;                     // 16-byte chunks per staged row
-  uint8_t* stage = warp_smem;
-  float* sbias = reinterpret_cast<float*>(warp_smem + 32 * EPI_PITCH);
+__device__ __forceinline__ void epilogue_tile_ct(uint32_t taddr, const GemmKParams& p, uint8_t* stage, const float* sbias,
+                                                 int lane, int half, RowFn row_fn, int n_col0) {
+  constexpr int GW = 32;                            // accumulator columns per group (one tcgen05.ld .x32)
+  constexpr int NG = BN / GW;
+  constexpr int GWO = SWIGLU ? GW / 2 : GW;         // output columns per group
+  constexpr int CPR = GWO / 8;                      // 16-byte chunks per staged row
+  constexpr int ITERS = CPR;                        // 32 rows x CPR chunks / 32 lanes
+  uint8_t* rstage = stage;                          // residual sub-tile
+  uint8_t* ostage = stage + 2048;                   // output sub-tile
   const int n_out = SWIGLU ? (p.N >> 1) : p.N;
   T* cbase = reinterpret_cast<T*>(p.C);
   const T* rbase = SWIGLU ? nullptr : reinterpret_cast<const T*>(p.residual);
-  const bool has_bias = p.bias != nullptr;
+  int grow[ITERS];
+  const int pch = lane % CPR;                       // idx = it*32 + lane -> the chunk is the same for every `it`
+  const int prow0 = lane / CPR;                     // row = it * (32 / CPR) + lane / CPR
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) grow[it] = row_fn(it * (32 / CPR) + prow0);
+
+  auto prefetch_residual = [&](int g) {
+    const int ocol0 = n_col0 + g * GW;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const bool ok = grow[it] >= 0 && ocol0 + pch * 8 < n_out;
+      const T* src = ok ? rbase + static_cast<size_t>(grow[it]) * p.ldr + ocol0 + pch * 8 : rbase;
+      cp_async16(rstage + stage_off<CPR>(it * (32 / CPR) + prow0, pch), src, ok);
+    }
+  };
+  if (rbase && n_col0 + half * GW < p.N) prefetch_residual(half);
+
 #pragma unroll 1
-  for (int g = 0; g < BN / GW; ++g) {
-    const int acol0 = n_col0 + g * GW;             // accumulator (weight-row) column
+  for (int g = half; g < NG; g += 2) {
+    const int acol0 = n_col0 + g * GW;
     if (acol0 >= p.N) break;
     const int ocol0 = SWIGLU ? (acol0 >> 1) : acol0;
-    __syncwarp();
-    if (has_bias) {
+    uint32_t o[GWO / 2];                            // this lane's packed output row segment
+    {
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + g * GW, v);
+      tmem_ld_wait();
+      const float* bs = sbias + g * GW;
 #pragma unroll
-      for (int j = lane; j < GW; j += 32) sbias[j] = (acol0 + j < p.N) ? __ldg(p.bias + acol0 + j) : 0.f;
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bs + j);
+        const float x0 = __uint_as_float(v[j]) + b4.x, x1 = __uint_as_float(v[j + 1]) + b4.y;
+        const float x2 = __uint_as_float(v[j + 2]) + b4.z, x3 = __uint_as_float(v[j + 3]) + b4.w;
+        if constexpr (SWIGLU) {
+          // (x0,x1) = (gate_i, up_i), (x2,x3) = (gate_i+1, up_i+1); every eager op boundary rounds once
+          const uint32_t t0 = Pk<T>::pack(x0, x1), t1 = Pk<T>::pack(x2, x3);
+          const uint32_t s = Pk<T>::pack(act_ct<ACT>(Pk<T>::lo(t0)), act_ct<ACT>(Pk<T>::lo(t1)));
+          o[j / 4] = Pk<T>::pack(Pk<T>::lo(s) * Pk<T>::hi(t0), Pk<T>::hi(s) * Pk<T>::hi(t1));
+        } else {
+          uint32_t t0 = Pk<T>::pack(x0, x1), t1 = Pk<T>::pack(x2, x3);
+          if constexpr (ACT != ACT_NONE) {
+            t0 = Pk<T>::pack(act_ct<ACT>(Pk<T>::lo(t0)), act_ct<ACT>(Pk<T>::hi(t0)));
+            t1 = Pk<T>::pack(act_ct<ACT>(Pk<T>::lo(t1)), act_ct<ACT>(Pk<T>::hi(t1)));
+          }
+          o[j / 2] = t0;
+          o[j / 2 + 1] = t1;
+        }
+      }
     }
     if (rbase) {
+      cp_async_wait_all();
+      __syncwarp();                                 // every lane's residual pieces have landed
 #pragma unroll
-      for (int it = 0; it < CPR; ++it) {
-        const int idx = it * 32 + lane;
-        const int r = idx / CPR, ch = idx % CPR;
-        const int grow = row_fn(r);
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (grow >= 0 && ocol0 + ch * 8 < n_out)
-          v = *reinterpret_cast<const uint4*>(rbase + static_cast<size_t>(grow) * p.ldr + ocol0 + ch * 8);
-        *reinterpret_cast<uint4*>(stage + r * EPI_PITCH + ch * 16) = v;
+      for (int ch = 0; ch < CPR; ++ch) {
+        const uint4 r4 = *reinterpret_cast<const uint4*>(rstage + stage_off<CPR>(lane, ch));
+        const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t t = o[ch * 4 + k];
+          o[ch * 4 + k] = Pk<T>::pack(Pk<T>::lo(t) + Pk<T>::lo(rr[k]), Pk<T>::hi(t) + Pk<T>::hi(rr[k]));
+        }
       }
+      __syncwarp();                                 // residual buffer free again
+      if (g + 2 < NG && n_col0 + (g + 2) * GW < p.N) prefetch_residual(g + 2);
     }
-    __syncwarp();
-#pragma unroll 1
-    for (int c = 0; c < GW / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(taddr + g * GW + c * 32, v);
-      tmem_ld_wait();
-      float x[32];
+    __syncwarp();                                   // previous group's output rows have been stored
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-      if (has_bias) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(sbias + c * 32 + j);
-          x[j] += b4.x; x[j + 1] += b4.y; x[j + 2] += b4.z; x[j + 3] += b4.w;
-        }
-      }
-      if constexpr (SWIGLU) {
-        T o[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float gt = rnd<T>(x[2 * i]);
-          const float up = rnd<T>(x[2 * i + 1]);
-          o[i] = from_f<T>(rnd<T>(act_ct<ACT>(gt)) * up);
-        }
-        uint4* dst = reinterpret_cast<uint4*>(stage + lane * EPI_PITCH + c * 32);
-        dst[0] = reinterpret_cast<const uint4*>(o)[0];
-        dst[1] = reinterpret_cast<const uint4*>(o)[1];
-      } else {
-        T o[32];
-        uint4* srow = reinterpret_cast<uint4*>(stage + lane * EPI_PITCH + c * 64);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float y = rnd<T>(x[j]);
-          if constexpr (ACT != ACT_NONE) y = rnd<T>(act_ct<ACT>(y));
-          x[j] = y;
-        }
-        if (rbase) {
-          uint4 rv[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) rv[i] = srow[i];
-          const T* r = reinterpret_cast<const T*>(rv);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] += to_f<T>(r[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) o[j] = from_f<T>(x[j]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) srow[i] = reinterpret_cast<const uint4*>(o)[i];
-      }
-    }
+    for (int ch = 0; ch < CPR; ++ch)
+      *reinterpret_cast<uint4*>(ostage + stage_off<CPR>(lane, ch)) = make_uint4(o[ch * 4], o[ch * 4 + 1], o[ch * 4 + 2], o[ch * 4 + 3]);
     __syncwarp();
 #pragma unroll
-    for (int it = 0; it < CPR; ++it) {
-      const int idx = it * 32 + lane;
-      const int r = idx / CPR, ch = idx % CPR;
-      const int grow = row_fn(r);
-      if (grow >= 0 && ocol0 + ch * 8 < n_out)
-        *reinterpret_cast<uint4*>(cbase + static_cast<size_t>(grow) * p.ldc + ocol0 + ch * 8) =
-            *reinterpret_cast<const uint4*>(stage + r * EPI_PITCH + ch * 16);
+    for (int it = 0; it < ITERS; ++it) {
+      if (grow[it] >= 0 && ocol0 + pch * 8 < n_out)
+        *reinterpret_cast<uint4*>(cbase + static_cast<size_t>(grow[it]) * p.ldc + ocol0 + pch * 8) =
+            *reinterpret_cast<const uint4*>(ostage + stage_off<CPR>(it * (32 / CPR) + prow0, pch));
     }
   }
 }
 
-// Runtime -> compile-time dispatch on (act, swiglu); done once per tile, outside every loop.
+// Stage the tile's bias slice (zeros when the GEMM has none); called by all epilogue threads before the accumulator wait.
+template <int BN>
+__device__ __forceinline__ void epilogue_stage_bias(const GemmKParams& p, float* sbias, int epi_tid, int n_col0) {
+  for (int j = epi_tid; j < BN; j += EPI_WARPS * 32)
+    sbias[j] = (p.bias && n_col0 + j < p.N) ? __ldg(p.bias + n_col0 + j) : 0.f;
+}
+
+// Runtime -> compile-time dispatch on (act, swiglu); once per tile, outside every loop.
 template <typename T, int BN, typename RowFn>
-__device__ __forceinline__ void epilogue_tile_v2(uint32_t taddr, const GemmKParams& p, uint8_t* warp_smem, int lane,
-                                                 RowFn row_fn, int n_col0) {
+__device__ __forceinline__ void epilogue_tile_v2(uint32_t taddr, const GemmKParams& p, uint8_t* stage, const float* sbias,
+                                                 int lane, int half, RowFn row_fn, int n_col0) {
   if (p.swiglu) {
-    epilogue_tile_ct<T, BN, ACT_SILU, true>(taddr, p, warp_smem, lane, row_fn, n_col0);
+    epilogue_tile_ct<T, BN, ACT_SILU, true>(taddr, p, stage, sbias, lane, half, row_fn, n_col0);
     return;
   }
   switch (p.act) {
-    case ACT_NONE: epilogue_tile_ct<T, BN, ACT_NONE, false>(taddr, p, warp_smem, lane, row_fn, n_col0); break;
-    case ACT_GELU_ERF: epilogue_tile_ct<T, BN, ACT_GELU_ERF, false>(taddr, p, warp_smem, lane, row_fn, n_col0); break;
-    case ACT_HARDSWISH: epilogue_tile_ct<T, BN, ACT_HARDSWISH, false>(taddr, p, warp_smem, lane, row_fn, n_col0); break;
-    case ACT_RELU: epilogue_tile_ct<T, BN, ACT_RELU, false>(taddr, p, warp_smem, lane, row_fn, n_col0); break;
-    case ACT_SILU: epilogue_tile_ct<T, BN, ACT_SILU, false>(taddr, p, warp_smem, lane, row_fn, n_col0); break;
-    default: epilogue_tile_ct<T, BN, ACT_GELU_TANH, false>(taddr, p, warp_smem, lane, row_fn, n_col0); break;
+    case ACT_NONE: epilogue_tile_ct<T, BN, ACT_NONE, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0); break;
+    case ACT_GELU_ERF: epilogue_tile_ct<T, BN, ACT_GELU_ERF, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0); break;
+    case ACT_HARDSWISH: epilogue_tile_ct<T, BN, ACT_HARDSWISH, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0); break;
+    case ACT_RELU: epilogue_tile_ct<T, BN, ACT_RELU, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0); break;
+    case ACT_SILU: epilogue_tile_ct<T, BN, ACT_SILU, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0); break;
+    default: epilogue_tile_ct<T, BN, ACT_GELU_TANH, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0); break;
   }
 }
 

@@ -33,7 +33,7 @@ __device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks
 }
 
 template <typename T, int BN, int STAGES>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const GemmKParams p) {
   constexpr int BM = 128, BK = 64;
@@ -52,6 +52,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  auto stamp = [&](int slot) {
+    if (p.dbg && blockIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.dbg[slot] = t;
+    }
+  };
+  if (threadIdx.x == 0) stamp(0);
   const int m_blocks = (p.M + BM - 1) / BM;
   const int n_blocks = (p.N + BN - 1) / BN;
   const int k_blocks = (p.K + BK - 1) / BK;
@@ -68,7 +76,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -77,6 +85,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) stamp(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -112,6 +121,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (tile == static_cast<int>(blockIdx.x) && kb < 38) stamp(2 + kb);
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint64_t da = umma_desc_k128(sa);
           const uint64_t db = umma_desc_k128(sa + A_BYTES);
@@ -130,7 +140,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;   // two warps share a quarter and alternate column groups
+    const int epi_tid = threadIdx.x - 128;
+    uint8_t* stage = epi_smem + (warp - 4) * EPI_STAGE_BYTES;
+    float* sbias = reinterpret_cast<float*>(epi_smem + EPI_WARPS * EPI_STAGE_BYTES);
     int as = 0;
     uint32_t aph = 0;
     const bool vec_ok = (p.ldc % 8 == 0) && (!p.residual || p.ldr % 8 == 0);
@@ -138,16 +152,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int mb, nb;
       tile_coords(tile, m_blocks, n_blocks, p.group_m, mb, nb);
+      if (v2) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // all epilogue warps are done with the previous tile's bias
+        epilogue_stage_bias<BN>(p, sbias, epi_tid, nb * BN);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      const int row = mb * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      if (warp == 4 && lane == 0 && tile == static_cast<int>(blockIdx.x)) stamp(40);
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       if (v2) {
         const int row0 = mb * BM + q * 32;
-        epilogue_tile_v2<T, BN>(tacc, p, epi_smem + q * EPI_WARP_BYTES, lane,
+        epilogue_tile_v2<T, BN>(tacc, p, stage, sbias, lane, half,
                                 [&](int r) { return row0 + r < p.M ? row0 + r : -1; }, nb * BN);
-      } else {
+      } else if (half == 0) {
+        const int row = mb * BM + q * 32 + lane;
+        const bool row_ok = row < p.M;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t v[32];
@@ -162,6 +182,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (warp == 4 && lane == 0 && tile == static_cast<int>(blockIdx.x)) stamp(41);
       as ^= 1;
       if (as == 0) aph ^= 1;
     }
@@ -173,6 +194,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (threadIdx.x == 0) stamp(42);
 }
 
 // ----------------------------------------------------------------------------------- host side
@@ -299,7 +321,7 @@ int make_tma_nhwc(CUtensorMap* map, int dtype, const void* base, int N, int H, i
 template <typename T, int BN, int STAGES>
 static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   constexpr uint32_t STAGE_BYTES = 128 * 64 * 2 + BN * 64 * 2;
-  constexpr size_t SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_SMEM_BYTES;
+  constexpr size_t SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + epi_smem_bytes<BN>();
   static bool attr_set = false;
   auto kern = gemm_tn_kernel<T, BN, STAGES>;
   if (!attr_set) {
@@ -323,10 +345,11 @@ static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   p.act = a.act; p.swiglu = a.swiglu; p.out_f32 = a.out_f32;
   p.group_m = 8;
   p.group_k = a.group_k;
+  p.dbg = a.dbg;
   int m_blocks = (a.M + 127) / 128, n_blocks = (a.N + BN - 1) / BN;
   int tiles = m_blocks * n_blocks;
   int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 256, SMEM, stream>>>(ma, mb, p);
+  kern<<<grid, 384, SMEM, stream>>>(ma, mb, p);
   return launch_ok();
 }
 

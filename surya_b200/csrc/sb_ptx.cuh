@@ -151,6 +151,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t fmt, uint32_t M, 
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// Register re-partitioning between warpgroups (all 4 warps of an aligned warpgroup must execute it).
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ----------------------------------------------------------------------------- numeric helpers
 template <typename T> struct TypeInfo;
 template <> struct TypeInfo<__nv_bfloat16> {
