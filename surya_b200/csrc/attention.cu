@@ -277,6 +277,8 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const DecodeKParams p)
   __shared__ float s_red[4][G];
   __shared__ float s_max_g[G], s_sum_g[G];
 
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, kvh = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slot = p.slot[b];
@@ -419,7 +421,7 @@ static int launch_decode(const DecodeAttnArgs& a, cudaStream_t st) {
   p.inv_freq = a.inv_freq; p.out = a.out; p.ldo = a.ldo;
   p.n_heads = a.n_heads; p.n_kv_heads = a.n_kv_heads; p.s_max = a.s_max; p.scale = a.scale;
   dim3 grid(a.batch, a.n_kv_heads), block(128);
-  kern<<<grid, block, smem, st>>>(p);
+  launch_pdl(kern, grid, block, smem, st, p);
   return launch_ok();
 }
 

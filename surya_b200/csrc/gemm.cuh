@@ -28,6 +28,8 @@ struct GemmArgs {
   // grouped 1x1 convolution (block-diagonal weights): n-block g reads A columns [g*group_k, g*group_k + K) and
   // W rows [g*group_n, (g+1)*group_n); W is [N, K] with K the zero-padded per-group depth; a_cols = A's width.
   int group_k = 0, group_n = 0, a_cols = 0;
+  int w_constant = 0;                     // W is never written by a preceding kernel: its tiles may be prefetched
+                                          // before the programmatic-dependency wait (engine weights)
   unsigned long long* dbg = nullptr;      // optional in-kernel timeline (see GemmKParams::dbg)
 };
 
@@ -41,5 +43,19 @@ int launch_ok();
 long long launch_count();
 void count_launches(long long n);  // kernels replayed through a CUDA graph
 int num_sms();
+
+// Launch with the programmatic-stream-serialization attribute (PDL) unless SB_PDL=0.
+bool pdl_enabled();
+template <typename... P, typename... A>
+inline cudaError_t launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
 
 }  // namespace sb

@@ -18,6 +18,7 @@ struct GemmKParams {
   int out_f32;
   int group_m;
   int group_k;  // grouped 1x1 conv: A column offset per n-block (0 = dense)
+  int w_constant;  // W tiles may be fetched before the programmatic-dependency wait
   unsigned long long* dbg;  // optional timeline buffer (globaltimer ns) written by CTA 0: [0]=start [1]=setup done
                             // [2+kb]=k-block kb landed (first tile) [40]=accumulator ready [41]=epilogue done
 };

@@ -16,6 +16,7 @@
 #include "sb_ptx.cuh"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <atomic>
 #include <mutex>
@@ -38,8 +39,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                const GemmKParams p) {
   constexpr int BM = 128, BK = 64;
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
+  constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  static_assert(2 * BN <= 512, "two accumulator buffers must fit the 512 TMEM columns");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -60,6 +61,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   };
   if (threadIdx.x == 0) stamp(0);
+  pdl_trigger();
   const int m_blocks = (p.M + BM - 1) / BM;
   const int n_blocks = (p.N + BN - 1) / BN;
   const int k_blocks = (p.K + BK - 1) / BK;
@@ -92,16 +94,34 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      // Weight tiles of the first pipeline fill do not depend on the previous kernel: request them before the
+      // programmatic-dependency wait so that the DRAM latency overlaps the predecessor's tail.
+      int early = 0;
+      if (p.w_constant && static_cast<int>(blockIdx.x) < num_tiles) {
+        int mb, nb;
+        tile_coords(blockIdx.x, m_blocks, n_blocks, p.group_m, mb, nb);
+        early = k_blocks < STAGES ? k_blocks : STAGES;
+        for (int kb = 0; kb < early; ++kb) {
+          uint8_t* sa = smem + kb * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[kb], STAGE_BYTES);
+          tma_load_2d(sa + A_BYTES, &tma_b, &full_bar[kb], kb * BK, nb * BN);
+        }
+      }
+      pdl_wait();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int mb, nb;
         tile_coords(tile, m_blocks, n_blocks, p.group_m, mb, nb);
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sbp = sa + A_BYTES;
-          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-          tma_load_2d(sa, &tma_a, &full_bar[s], kb * BK + nb * p.group_k, mb * BM);
-          tma_load_2d(sbp, &tma_b, &full_bar[s], kb * BK, nb * BN);
+          if (tile == static_cast<int>(blockIdx.x) && kb < early) {
+            tma_load_2d(sa, &tma_a, &full_bar[s], kb * BK + nb * p.group_k, mb * BM);   // B already in flight
+          } else {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+            tma_load_2d(sa, &tma_a, &full_bar[s], kb * BK + nb * p.group_k, mb * BM);
+            tma_load_2d(sbp, &tma_b, &full_bar[s], kb * BK, nb * BN);
+          }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -140,6 +160,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue warps
+    pdl_wait();
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;   // two warps share a quarter and alternate column groups
     const int epi_tid = threadIdx.x - 128;
@@ -209,6 +230,11 @@ const char* last_error() { return g_err; }
 
 static std::atomic<long long> g_launches{0};
 long long launch_count() { return g_launches.load(); }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SB_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 void count_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int launch_ok() {
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -346,10 +372,11 @@ static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   p.group_m = 8;
   p.group_k = a.group_k;
   p.dbg = a.dbg;
+  p.w_constant = a.w_constant;
   int m_blocks = (a.M + 127) / 128, n_blocks = (a.N + BN - 1) / BN;
   int tiles = m_blocks * n_blocks;
   int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 384, SMEM, stream>>>(ma, mb, p);
+  if (launch_pdl(kern, dim3(grid), dim3(384), SMEM, stream, ma, mb, p) != cudaSuccess) { /* reported by launch_ok */ }
   return launch_ok();
 }
 
@@ -357,22 +384,33 @@ template <typename T>
 static int launch_typed(const GemmArgs& a, cudaStream_t stream) {
   int bn = a.force_bn;
   if (bn == 0) {
-    // Largest tile that still yields about one wave of CTAs; small problems fall to narrower tiles so
-    // that more SMs stream the weight matrix.
+    // Big problems: 128x256 tiles (highest flop per byte of smem fill).  Otherwise the main loop is bound by DRAM latency x
+    // bytes in flight per SM, so prefer a single wave of many small tiles: cost = waves * bytes per k-block, with a penalty
+    // when fewer than ~60 % of the SMs would be streaming the weight matrix.
     const int sms = num_sms();
     const int m_blocks = (a.M + 127) / 128;
-    bn = 32;
-    const int cands[4] = {256, 128, 64, 32};
-    for (int i = 0; i < 4; ++i) {
-      int nb = (a.N + cands[i] - 1) / cands[i];
-      if (m_blocks * nb >= (sms * 3) / 4 || i == 3) { bn = cands[i]; break; }
+    if (m_blocks * ((a.N + 255) / 256) >= (sms * 3) / 4) {
+      bn = 256;
+    } else {
+      const int cands[5] = {256, 128, 96, 64, 32};
+      double best = 1e30;
+      for (int i = 0; i < 5; ++i) {
+        const int c = cands[i];
+        if (a.swiglu && (c % 32)) continue;
+        const int tiles = m_blocks * ((a.N + c - 1) / c);
+        const int waves = (tiles + sms - 1) / sms;
+        double cost = static_cast<double>(waves) * (128 + c);
+        const double occ = 0.6 * sms / tiles;
+        if (occ > 1.0) cost *= occ;
+        if (cost < best) { best = cost; bn = c; }
+      }
     }
-    if (a.swiglu && bn < 32) bn = 32;
   }
   if (a.group_k) bn = a.group_n;  // one n-block per channel group
   switch (bn) {
     case 256: return launch_cfg<T, 256, 4>(a, stream);
     case 128: return launch_cfg<T, 128, 6>(a, stream);
+    case 96: return launch_cfg<T, 96, 6>(a, stream);
     case 64: return launch_cfg<T, 64, 8>(a, stream);
     case 32: return launch_cfg<T, 32, 8>(a, stream);
     default: set_error("unsupported BN %d", bn); return -12;

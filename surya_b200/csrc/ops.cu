@@ -17,6 +17,8 @@ namespace sb {
 template <typename T>
 __global__ void rmsnorm_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ w, T* __restrict__ y, int ldy,
                                int rows, int H, float eps, const int* __restrict__ src_rows) {
+  pdl_trigger();
+  pdl_wait();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -67,11 +69,11 @@ int rmsnorm(int dtype, const void* x, int ldx, const void* w, void* y, int ldy, 
   int wpb = 4;
   dim3 grid((rows + wpb - 1) / wpb), block(32 * wpb);
   if (dtype == DT_BF16)
-    rmsnorm_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w,
-                                                         (__nv_bfloat16*)y, ldy, rows, H, eps, src_rows);
+    launch_pdl(rmsnorm_kernel<__nv_bfloat16>, grid, block, 0, st, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w,
+               (__nv_bfloat16*)y, ldy, rows, H, eps, src_rows);
   else
-    rmsnorm_kernel<__half><<<grid, block, 0, st>>>((const __half*)x, ldx, (const __half*)w, (__half*)y, ldy, rows, H,
-                                                  eps, src_rows);
+    launch_pdl(rmsnorm_kernel<__half>, grid, block, 0, st, (const __half*)x, ldx, (const __half*)w, (__half*)y, ldy, rows, H,
+               eps, src_rows);
   return launch_ok();
 }
 
@@ -279,6 +281,8 @@ template <typename T>
 __global__ void argmax_score_kernel(const T* __restrict__ logits, int ld, int V, long long* __restrict__ tok,
                                     float* __restrict__ score, unsigned char* __restrict__ done,
                                     long long* __restrict__ next_ids, int eos, int pad) {
+  pdl_trigger();
+  pdl_wait();
   int row = blockIdx.x;
   const T* l = logits + static_cast<size_t>(row) * ld;
   float m = -INFINITY;
@@ -363,11 +367,11 @@ int argmax_score(int dtype, const void* logits, int ld, int rows, int V, long lo
   if (ld % 8) { set_error("argmax_score: logits pitch must be a multiple of 8"); return -1; }
   dim3 grid(rows), block(512);
   if (dtype == DT_BF16)
-    argmax_score_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)logits, ld, V, tok, score, done,
-                                                              next_ids, eos, pad);
+    launch_pdl(argmax_score_kernel<__nv_bfloat16>, grid, block, 0, st, (const __nv_bfloat16*)logits, ld, V, tok, score, done,
+               next_ids, eos, pad);
   else
-    argmax_score_kernel<__half><<<grid, block, 0, st>>>((const __half*)logits, ld, V, tok, score, done, next_ids, eos,
-                                                       pad);
+    launch_pdl(argmax_score_kernel<__half>, grid, block, 0, st, (const __half*)logits, ld, V, tok, score, done, next_ids, eos,
+               pad);
   return launch_ok();
 }
 
@@ -378,6 +382,8 @@ template <typename T>
 __global__ void small_head_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ w, const T* __restrict__ b,
                                   int rows, int H, int n_out, int sigmoid, float* __restrict__ out_f,
                                   long long* __restrict__ out_box, float box_scale) {
+  pdl_trigger();
+  pdl_wait();
   int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (gw >= rows * n_out) return;
@@ -401,12 +407,11 @@ int small_head(int dtype, const void* x, int ldx, const void* w, const void* b, 
   int warps = rows * n_out;
   dim3 grid((warps + 3) / 4), block(128);
   if (dtype == DT_BF16)
-    small_head_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w,
-                                                            (const __nv_bfloat16*)b, rows, H, n_out, sigmoid, out_f,
-                                                            out_box, box_scale);
+    launch_pdl(small_head_kernel<__nv_bfloat16>, grid, block, 0, st, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w,
+               (const __nv_bfloat16*)b, rows, H, n_out, sigmoid, out_f, out_box, box_scale);
   else
-    small_head_kernel<__half><<<grid, block, 0, st>>>((const __half*)x, ldx, (const __half*)w, (const __half*)b, rows,
-                                                     H, n_out, sigmoid, out_f, out_box, box_scale);
+    launch_pdl(small_head_kernel<__half>, grid, block, 0, st, (const __half*)x, ldx, (const __half*)w, (const __half*)b, rows,
+               H, n_out, sigmoid, out_f, out_box, box_scale);
   return launch_ok();
 }
 
@@ -414,6 +419,8 @@ int small_head(int dtype, const void* x, int ldx, const void* w, const void* b, 
 template <typename T>
 __global__ void embed_rows_kernel(const long long* __restrict__ ids, const T* __restrict__ embed, T* __restrict__ out,
                                   int ldo, int n, int H) {
+  pdl_trigger();
+  pdl_wait();
   int t = blockIdx.x;
   if (t >= n) return;
   const uint4* e = reinterpret_cast<const uint4*>(embed + static_cast<size_t>(ids[t]) * H);
@@ -426,10 +433,10 @@ int embed_rows(int dtype, const long long* ids, const void* embed, void* out, in
   if (H % 8 || ldo % 8) { set_error("embed_rows: H and pitch must be multiples of 8"); return -1; }
   dim3 grid(n), block(128);
   if (dtype == DT_BF16)
-    embed_rows_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(ids, (const __nv_bfloat16*)embed, (__nv_bfloat16*)out, ldo,
-                                                            n, H);
+    launch_pdl(embed_rows_kernel<__nv_bfloat16>, grid, block, 0, st, ids, (const __nv_bfloat16*)embed, (__nv_bfloat16*)out, ldo,
+               n, H);
   else
-    embed_rows_kernel<__half><<<grid, block, 0, st>>>(ids, (const __half*)embed, (__half*)out, ldo, n, H);
+    launch_pdl(embed_rows_kernel<__half>, grid, block, 0, st, ids, (const __half*)embed, (__half*)out, ldo, n, H);
   return launch_ok();
 }
 

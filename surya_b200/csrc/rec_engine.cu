@@ -67,6 +67,7 @@ static int linear(const sb_rec_engine* e, const void* A, int lda, const void* Wt
   a.M = M; a.N = N; a.K = K;
   a.bias = static_cast<const float*>(bias_f32);
   a.residual = residual; a.ldr = ldr; a.act = act; a.swiglu = swiglu;
+  a.w_constant = 1;   // engine weights are never written after packing
   return gemm_launch(a, st);
 }
 
@@ -211,6 +212,8 @@ __global__ void record_step_kernel(int* step, int B, const long long* tok, const
                                    const unsigned char* done, const long long* next, long long* tok_hist,
                                    float* score_hist, long long* bbox_hist, unsigned char* done_hist,
                                    long long* ids_io, int* pos_io) {
+  pdl_trigger();
+  pdl_wait();
   const int s = *step;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     size_t o = static_cast<size_t>(s) * B + b;
@@ -357,8 +360,9 @@ int sb_rec_decode_steps(sb_rec_engine* e, long long* ids_io, const int* slot, in
   auto one_step = [&](cudaStream_t s) -> int {
     CK(run_decode_step(e, ids_io, slot, pos_io, batch, nullptr, e->st_tok, e->st_score, e->st_bbox, nullptr, e->st_done,
                        e->st_next, s));
-    record_step_kernel<<<1, 256, 0, s>>>(e->st_step, batch, e->st_tok, e->st_score, e->st_bbox, e->st_done, e->st_next,
-                                         tok_hist, score_hist, bbox_hist, done_hist, ids_io, pos_io);
+    launch_pdl(record_step_kernel, dim3(1), dim3(256), 0, s, e->st_step, batch, (const long long*)e->st_tok,
+               (const float*)e->st_score, (const long long*)e->st_bbox, (const unsigned char*)e->st_done,
+               (const long long*)e->st_next, tok_hist, score_hist, bbox_hist, done_hist, ids_io, pos_io);
     return launch_ok();
   };
   if (!use_graph) {

@@ -151,6 +151,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t fmt, uint32_t M, 
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// Programmatic dependent launch: `pdl_trigger` lets the next kernel in the stream start its prologue early,
+// `pdl_wait` blocks until every prerequisite grid has completed and its memory is visible (no-ops without PDL).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Register re-partitioning between warpgroups (all 4 warps of an aligned warpgroup must execute it).
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
