@@ -228,6 +228,33 @@ int sb_gemm_grouped(int dtype, const void* A, int lda, int a_cols, const void* W
 int sb_lite_mla(int dtype, const void* qkv_a, const void* qkv_b, void* out, int B, int HW, int heads, int dim, float eps,
                 void* stream);
 
+/* ------------------------------------------------------------------------------------------------ layout / table_rec ops
+ * Donut-Swin encoder (surya/common/donut/encoder.py) and ADETR decoder (surya/common/adetr/decoder.py) pieces that the
+ * recognition / detection entry points above do not already cover; the layer loops are driven from
+ * surya_b200/layout.py (round 1: correctness first, C++ engine-isation is the next step). */
+/* SuryaADETRDecoderRMSNorm (adetr/decoder.py:29-47): T(clamp(x * rsqrt(max(mean(x^2), eps)) * (1 + w))). */
+int sb_rmsnorm_adetr(int dtype, const void* x, int ldx, const void* w, void* y, int ldy, int rows, int H, float eps,
+                     void* stream);
+/* nn.LayerNorm (donut/encoder.py:117,163,544-548; layout/model/decoder.py:73). */
+int sb_layernorm(int dtype, const void* x, const void* w, const void* b, void* y, int rows, int C, float eps, void* stream);
+/* im2col of the patch-embedding Conv2d(k = stride = P) (donut/encoder.py:228-230): NCHW -> [B*gh*gw, Kp], col = c*P*P+ky*P+kx. */
+int sb_patch_gather(int dtype, const void* in, int in_f32, void* out, int B, int Cin, int H, int W, int P, int Kp, void* stream);
+/* x[b, t, :] += tab[t, :] (stage sin-cos table donut/encoder.py:773-776; position_embeddings layout/model/encoder.py:76-77). */
+int sb_add_bcast_rows(int dtype, void* x, const void* tab, long long rows, int rows_per_batch, int C, void* stream);
+/* DonutSwinPatchMerging's 2x2 gather (donut/encoder.py:301-312): [B,H,W,C] -> [B,H/2,W/2,4C]. */
+int sb_patch_merge_gather(int dtype, const void* x, void* y, int B, int H, int W, int C, void* stream);
+/* DonutSwinLayer attention core (donut/encoder.py:383-442, 562-590, 598-664): 8x8 windows, cyclic shift, relative-position
+ * bias table [225, nh], -100 shift mask; qkv [B*H*W, 3C] and out [B*H*W, C] in natural token order. */
+int sb_swin_window_attn(int dtype, const void* qkv, const void* bias_table, void* out, int B, int H, int W, int C, int nh,
+                        int shift, void* stream);
+/* BboxEmbedding (layout/model/decoder.py:36-57): tables = 15 device pointers (w,h,cx,cy,xskew,yskew,x1,y1,...,y4,label). */
+int sb_bbox_embed_sum(int dtype, const long long* boxes, const void* const* tables, void* out, int n, int Hd, int bbox_size,
+                      void* stream);
+/* q_len = 1 attention over a fixed K/V set with explicit strides (ADETR cross-attention, adetr/decoder.py:150-194). */
+int sb_attn_single_query(int dtype, const void* q, int ldq, const void* K, const void* V, long long batch_stride,
+                         long long head_stride, long long token_stride, void* out, int ldo, int B, int nh, int nkv, int head_dim,
+                         int n_keys, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,9 +85,70 @@ def summarise(lm: torch.Tensor, bb: torch.Tensor, cfg, full_logits: bool):
     return g
 
 
+def make_layout_golden():
+    """Reference Swin encoder + ADETR decoder driven like LayoutPredictor.batch_layout_detection
+    (surya/layout/__init__.py:83-137): encoder once, prefill call, greedy box steps."""
+    from surya_b200.config import layout_tiny
+    from surya_b200.synth import adetr_layout_state_dict, layout_synthetic_pages, swin_state_dict
+
+    cfg = layout_tiny()
+    e, d = cfg.encoder, cfg.decoder
+    sde, sdd = swin_state_dict(e, 0), adetr_layout_state_dict(d, 0)
+    enc, dec = ref_shim.build_reference_layout_models(cfg, sde, sdd)
+    x = layout_synthetic_pages(2, e.image_size, seed=7)
+    steps = 8
+    with torch.inference_mode():
+        ref_enc = enc(pixel_values=x)[0]
+        dec.model._setup_cache(dec.config, 2, "cpu", torch.float32)
+        boxes = torch.full((2, 1, 7), d.bos_token_id, dtype=torch.long)
+        pos = torch.arange(1)
+        toks, bbs, cls = [], [], []
+        for s in range(steps):
+            out = dec(input_boxes=boxes, encoder_hidden_states=ref_enc, cache_position=pos, use_cache=True, prefill=(s == 0))
+            pos = pos[-1:] + 1
+            b, c = out["bbox_logits"][:, -1, :], out["class_logits"][:, -1, :]
+            boxes = torch.cat([(b * d.bbox_size).unsqueeze(1), c.argmax(-1).unsqueeze(1).unsqueeze(1)], dim=-1).to(torch.long)
+            toks.append(boxes[:, 0].clone())
+            bbs.append(b.float().clone())
+            cls.append(c.float().clone())
+    g = {"encoder": ref_enc.float().clone(), "tokens": torch.stack(toks, 1), "bbox": torch.stack(bbs, 1),
+         "class_logits": torch.stack(cls, 1), "input_checksum": x.double().sum(),
+         "meta": {"kind": "layout_tiny", "steps": steps, "seed": 0, "page_seed": 7, "torch": str(torch.__version__),
+                  "reference": "VikParuchuri/surya@80e9a7e (v0.14.6), fp32 CPU, eager attention"}}
+    torch.save(g, GOLDEN / "layout_tiny.pt")
+    top2 = g["class_logits"].topk(2, -1).values
+    print(f"[golden] layout_tiny: tokens[0,:2]={g['tokens'][0, :2].tolist()} min class margin={(top2[..., 0] - top2[..., 1]).min():.4f}")
+
+
+def make_det_golden():
+    """Reference EfficientViT segmentation logits for one seeded 512x512 page (surya/detection/__init__.py:94-104)."""
+    from surya_b200.config import det_default
+    from surya_b200.synth import det_normalize, det_state_dict, det_synthetic_pages
+
+    cfg = det_default()
+    sd = det_state_dict(cfg, seed=0)
+    m = ref_shim.build_reference_det_model(cfg, sd)
+    x = det_normalize(det_synthetic_pages(1, 512, seed=11, text_like=True))
+    with torch.inference_mode():
+        logits = m(pixel_values=x).logits.float()
+        logits16 = m.half()(pixel_values=x.half()).logits.float()    # the reference's own fp16 path (settings MODEL_DTYPE on GPU)
+    g = {"logits": logits, "logits_fp16_path": logits16, "input_checksum": x.double().sum(),
+         "meta": {"reference": "VikParuchuri/surya@80e9a7e EfficientViTForSemanticSegmentation, CPU; fp32 and model.half() runs",
+                  "size": 512, "seed": 11}}
+    torch.save(g, GOLDEN / "det_default.pt")
+    print(f"[golden] det_default: logits {tuple(logits.shape)} max={logits.max():.4f}")
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
+    which = set(sys.argv[1:]) or {"rec", "det", "layout"}
+    if "layout" in which:
+        make_layout_golden()
+    if "det" in which:
+        make_det_golden()
+    if "rec" not in which:
+        return
     for kind, cfg, steps in (("tiny", tiny_rec(), 12), ("synrec", syn_rec(), 3)):
         t0 = time.time()
         sd = rec_state_dict(cfg, seed=0)

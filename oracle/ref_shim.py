@@ -83,3 +83,40 @@ def build_reference_rec_model(cfg, state_dict, attn: str = "sdpa"):
     missing = [m for m in missing if "rotary" not in m and "inv_freq" not in m]
     assert not missing and not unexpected, (missing, unexpected)
     return model.eval()
+
+
+def build_reference_layout_models(cfg, sd_enc, sd_dec):
+    """Instantiate the reference DonutSwinLayoutModel + SuryaLayoutDecoder (surya/layout/model/{encoder,decoder}.py) for
+    our LayoutConfig with the synthetic weights (fp32, eval).  Two transformers-5 incompatibilities are neutralised on the
+    reference's base classes (no behaviour on the forward path): weight tying hooks and get_head_mask."""
+    install()
+    from surya.common.adetr.decoder import SuryaADETRDecoderPreTrainedModel
+    from surya.common.donut.encoder import DonutSwinPreTrainedModel
+    from surya.layout.model.config import DonutSwinLayoutConfig, SuryaLayoutDecoderConfig
+    from surya.layout.model.decoder import SuryaLayoutDecoder
+    from surya.layout.model.encoder import DonutSwinLayoutModel
+
+    SuryaADETRDecoderPreTrainedModel.tie_weights = lambda self, **k: None
+    SuryaADETRDecoderPreTrainedModel._tie_weights = lambda self, **k: None
+    DonutSwinPreTrainedModel.get_head_mask = lambda self, head_mask, n, *a, **k: [None] * n
+    e, d = cfg.encoder, cfg.decoder
+    enc = DonutSwinLayoutModel(DonutSwinLayoutConfig(image_size=e.image_size, depths=list(e.depths),
+                                                     encoder_length=e.encoder_length)).eval()
+    miss, unexp = enc.load_state_dict(sd_enc, strict=False)
+    assert not [m for m in miss if "relative_position_index" not in m] and not unexp, (miss, unexp)
+    dec = SuryaLayoutDecoder(SuryaLayoutDecoderConfig(num_hidden_layers=d.num_hidden_layers)).eval()
+    miss, unexp = dec.load_state_dict(sd_dec, strict=False)
+    assert not miss and not unexp, (miss, unexp)
+    return enc, dec
+
+
+def build_reference_det_model(cfg, state_dict):
+    """Reference EfficientViTForSemanticSegmentation (surya/detection/model/encoderdecoder.py) with the synthetic weights."""
+    install()
+    from surya.detection.model.config import EfficientViTConfig
+    from surya.detection.model.encoderdecoder import EfficientViTForSemanticSegmentation
+
+    m = EfficientViTForSemanticSegmentation(EfficientViTConfig()).eval()
+    missing, unexpected = m.load_state_dict(state_dict, strict=False)
+    assert not [k for k in missing if "num_batches_tracked" not in k] and not unexpected, (missing, unexpected)
+    return m

@@ -126,3 +126,78 @@ def det_default() -> DetConfig:
 def det_tiny() -> DetConfig:
     """Reduced depth (same block types and channel widths) for fast CPU oracle tests."""
     return DetConfig(depths=(1, 1, 1, 2, 2))
+
+
+# ------------------------------------------------------------------------------------------------ layout (Donut-Swin + ADETR)
+@dataclass
+class SwinConfig:
+    """Mirror of DonutSwinLayoutConfig / DonutSwinTableRecConfig (surya/layout/model/config.py:85-106,
+    surya/table_rec/model/config.py:89-111)."""
+    image_size: Tuple[int, int] = (768, 768)
+    patch_size: int = 4
+    num_channels: int = 3
+    embed_dim: int = 128
+    depths: Tuple[int, ...] = (2, 2, 16, 2)
+    num_heads: Tuple[int, ...] = (4, 8, 16, 32)
+    window_size: int = 8
+    mlp_ratio: float = 4.0
+    layer_norm_eps: float = 1e-5
+    encoder_length: int = 768
+
+    @property
+    def hidden_size(self) -> int:
+        return self.embed_dim * 2 ** (len(self.depths) - 1)
+
+    @property
+    def grid(self) -> Tuple[int, int]:
+        return (self.image_size[0] // self.patch_size, self.image_size[1] // self.patch_size)
+
+
+@dataclass
+class AdetrConfig:
+    """Mirror of SuryaLayoutDecoderConfig (surya/layout/model/config.py:138-179)."""
+    num_hidden_layers: int = 8
+    vocab_size: int = 1025
+    bbox_size: int = 1024
+    label_count: int = 20
+    skew_scaler: int = 512
+    special_token_count: int = 3
+    hidden_size: int = 1024
+    intermediate_size: int = 4096
+    encoder_hidden_size: int = 1024
+    num_attention_heads: int = 16
+    num_key_value_heads: int = 4
+    rms_norm_eps: float = 1e-6
+    layer_norm_eps: float = 1e-5
+    rope_theta: float = 10000.0
+    pad_token_id: int = 0
+    eos_token_id: int = 1
+    bos_token_id: int = 1
+    pause_token_id: int = 2
+    pause_token_count: int = 0
+    double_residual_flow: bool = True
+    max_boxes: int = 100
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_attention_heads
+
+
+@dataclass
+class LayoutConfig:
+    encoder: SwinConfig = field(default_factory=SwinConfig)
+    decoder: AdetrConfig = field(default_factory=AdetrConfig)
+
+    def to_dict(self) -> dict:
+        return asdict(self)
+
+
+def layout_default() -> LayoutConfig:
+    return LayoutConfig()
+
+
+def layout_tiny() -> LayoutConfig:
+    """Shallow variant (same widths, windows and head dims) for fast CPU oracle tests; 256x256 input."""
+    enc = SwinConfig(image_size=(256, 256), depths=(2, 2, 2, 2), encoder_length=64)
+    dec = AdetrConfig(num_hidden_layers=2)
+    return LayoutConfig(encoder=enc, decoder=dec)

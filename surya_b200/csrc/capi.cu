@@ -94,4 +94,35 @@ int sb_small_head(int dtype, const void* x, int ldx, const void* w, const void* 
                     static_cast<cudaStream_t>(stream));
 }
 
+int sb_rmsnorm_adetr(int dtype, const void* x, int ldx, const void* w, void* y, int ldy, int rows, int H, float eps,
+                     void* stream) {
+  return rmsnorm(dtype, x, ldx, w, y, ldy, rows, H, eps, nullptr, static_cast<cudaStream_t>(stream), 1);
+}
+int sb_layernorm(int dtype, const void* x, const void* w, const void* b, void* y, int rows, int C, float eps, void* stream) {
+  return layernorm(dtype, x, w, b, y, rows, C, eps, static_cast<cudaStream_t>(stream));
+}
+int sb_patch_gather(int dtype, const void* in, int in_f32, void* out, int B, int Cin, int H, int W, int P, int Kp, void* stream) {
+  return patch_gather(dtype, in, in_f32, out, B, Cin, H, W, P, Kp, static_cast<cudaStream_t>(stream));
+}
+int sb_add_bcast_rows(int dtype, void* x, const void* tab, long long rows, int rows_per_batch, int C, void* stream) {
+  return add_bcast_rows(dtype, x, tab, rows, rows_per_batch, C, static_cast<cudaStream_t>(stream));
+}
+int sb_patch_merge_gather(int dtype, const void* x, void* y, int B, int H, int W, int C, void* stream) {
+  return patch_merge_gather(dtype, x, y, B, H, W, C, static_cast<cudaStream_t>(stream));
+}
+int sb_swin_window_attn(int dtype, const void* qkv, const void* bias_table, void* out, int B, int H, int W, int C, int nh,
+                        int shift, void* stream) {
+  return swin_window_attn(dtype, qkv, bias_table, out, B, H, W, C, nh, shift, static_cast<cudaStream_t>(stream));
+}
+int sb_bbox_embed_sum(int dtype, const long long* boxes, const void* const* tables, void* out, int n, int Hd, int bbox_size,
+                      void* stream) {
+  return bbox_embed_sum(dtype, boxes, tables, out, n, Hd, bbox_size, static_cast<cudaStream_t>(stream));
+}
+int sb_attn_single_query(int dtype, const void* q, int ldq, const void* K, const void* V, long long batch_stride,
+                         long long head_stride, long long token_stride, void* out, int ldo, int B, int nh, int nkv, int head_dim,
+                         int n_keys, float scale, void* stream) {
+  return attn_single_query(dtype, q, ldq, K, V, batch_stride, head_stride, token_stride, out, ldo, B, nh, nkv, head_dim, n_keys,
+                           scale, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

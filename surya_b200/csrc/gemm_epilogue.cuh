@@ -138,7 +138,7 @@ template <int BN> constexpr int epi_smem_bytes() { return EPI_WARPS * EPI_STAGE_
 
 __device__ __forceinline__ bool epilogue_v2_ok(const GemmKParams& p) {
   if (p.out_f32 || (p.ldc & 7) || (p.residual && (p.ldr & 7))) return false;
-  if (p.swiglu) return p.act == ACT_SILU && p.N % 16 == 0;
+  if (p.swiglu) return (p.act == ACT_SILU || p.act == ACT_GELU_TANH) && p.N % 16 == 0;
   return p.N % 8 == 0;
 }
 
@@ -294,8 +294,9 @@ __device__ __forceinline__ void epilogue_stage_bias(const GemmKParams& p, float*
 template <typename T, int BN, typename RowFn>
 __device__ __forceinline__ void epilogue_tile_v2(uint32_t taddr, const GemmKParams& p, uint8_t* stage, const float* sbias,
                                                  int lane, int half, RowFn row_fn, int n_col0) {
-  if (p.swiglu) {
-    epilogue_tile_ct<T, BN, ACT_SILU, true>(taddr, p, stage, sbias, lane, half, row_fn, n_col0);
+  if (p.swiglu) {   // SwiGLU (Qwen2 MLPs) or GeGLU (ADETR MLP, gelu_pytorch_tanh)
+    if (p.act == ACT_SILU) epilogue_tile_ct<T, BN, ACT_SILU, true>(taddr, p, stage, sbias, lane, half, row_fn, n_col0);
+    else epilogue_tile_ct<T, BN, ACT_GELU_TANH, true>(taddr, p, stage, sbias, lane, half, row_fn, n_col0);
     return;
   }
   switch (p.act) {

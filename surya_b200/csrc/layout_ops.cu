@@ -1,0 +1,511 @@
+// surya_b200 — kernels of the layout / table_rec path (Donut-Swin encoder + ADETR decoder) that the recognition and
+// detection paths do not already provide.
+//
+//   layernorm          nn.LayerNorm (surya/common/donut/encoder.py:117,163,544-548; layout/model/decoder.py:73)
+//   patch4_gather      im2col of the 4x4 stride-4 patch-embedding conv (encoder.py:228-230) -> GEMM operand
+//   add_bcast_rows     + 2-D sin-cos stage table / learned position_embeddings (encoder.py:773-776; layout encoder.py:76-77)
+//   swin_window_attn   shifted-window attention with relative-position bias and -100 shift mask
+//                      (encoder.py:383-442, 562-590, 598-664): windows, cyclic shift and un-shift are pure index maps,
+//                      so tokens stay in natural (b, y, x) order for every GEMM / LayerNorm around it
+//   patch_merge_gather 2x2 neighbourhood concat in the reference's channel order (encoder.py:301-312)
+//   bbox_embed_sum     BboxEmbedding: 15 table gathers with integer corner arithmetic (layout/model/decoder.py:36-57)
+//   attn_single_query  q_len = 1 attention over a fixed K/V set with arbitrary strides (ADETR cross-attention,
+//                      surya/common/adetr/decoder.py:150-194)
+#include "ops.cuh"
+#include "sb_ptx.cuh"
+
+namespace sb {
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+template <typename T>
+__global__ void layernorm_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ b,
+                                 T* __restrict__ y, int rows, int C, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const T* xr = x + static_cast<size_t>(row) * C;
+  T* yr = y + static_cast<size_t>(row) * C;
+  float s = 0.f;
+  for (int i = lane * 8; i < C; i += 256) {
+    uint4 u = *reinterpret_cast<const uint4*>(xr + i);
+    const T* e = reinterpret_cast<const T*>(&u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += to_f<T>(e[j]);
+  }
+  const float mean = warp_sum(s) / C;
+  float v = 0.f;
+  for (int i = lane * 8; i < C; i += 256) {
+    uint4 u = *reinterpret_cast<const uint4*>(xr + i);
+    const T* e = reinterpret_cast<const T*>(&u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { float d = to_f<T>(e[j]) - mean; v += d * d; }
+  }
+  const float rstd = rsqrtf(warp_sum(v) / C + eps);
+  for (int i = lane * 8; i < C; i += 256) {
+    uint4 u = *reinterpret_cast<const uint4*>(xr + i);
+    uint4 wu = *reinterpret_cast<const uint4*>(w + i);
+    uint4 bu = *reinterpret_cast<const uint4*>(b + i);
+    const T *e = reinterpret_cast<const T*>(&u), *we = reinterpret_cast<const T*>(&wu), *be = reinterpret_cast<const T*>(&bu);
+    uint4 o;
+    T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) oe[j] = from_f<T>((to_f<T>(e[j]) - mean) * rstd * to_f<T>(we[j]) + to_f<T>(be[j]));
+    *reinterpret_cast<uint4*>(yr + i) = o;
+  }
+}
+
+int layernorm(int dtype, const void* x, const void* w, const void* b, void* y, int rows, int C, float eps, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  if (C % 8) { set_error("layernorm: C must be a multiple of 8"); return -1; }
+  dim3 grid((rows + 3) / 4), block(128);
+  if (dtype == DT_F16) layernorm_kernel<__half><<<grid, block, 0, st>>>((const __half*)x, (const __half*)w, (const __half*)b, (__half*)y, rows, C, eps);
+  else layernorm_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, rows, C, eps);
+  return launch_ok();
+}
+
+// ------------------------------------------------------------------------------------------------ patch-embed im2col
+// in NCHW [B, Cin, H, W]; out [B*gh*gw, Kp]: column = c*P*P + ky*P + kx (Conv2d weight flatten order), zero padded to Kp.
+template <typename T, typename InT>
+__global__ void patch_gather_kernel(const InT* __restrict__ in, T* __restrict__ out, int B, int Cin, int H, int W, int P, int Kp) {
+  const int gh = H / P, gw = W / P;
+  const long long total = static_cast<long long>(B) * gh * gw * Kp;
+  const int K = Cin * P * P;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int col = idx % Kp;
+    const long long tok = idx / Kp;
+    float v = 0.f;
+    if (col < K) {
+      const int c = col / (P * P), ky = (col / P) % P, kx = col % P;
+      const int gx = tok % gw, gy = (tok / gw) % gh;
+      const int b = tok / (static_cast<long long>(gw) * gh);
+      const InT* p = in + ((static_cast<size_t>(b) * Cin + c) * H + gy * P + ky) * W + gx * P + kx;
+      if constexpr (sizeof(InT) == 4) v = static_cast<float>(*p); else v = to_f<InT>(*p);
+    }
+    out[idx] = from_f<T>(v);
+  }
+}
+
+int patch_gather(int dtype, const void* in, int in_f32, void* out, int B, int Cin, int H, int W, int P, int Kp, cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * (H / P) * (W / P) * Kp;
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > num_sms() * 32) grid = num_sms() * 32;
+  if (dtype == DT_F16) {
+    if (in_f32) patch_gather_kernel<__half, float><<<grid, 256, 0, st>>>((const float*)in, (__half*)out, B, Cin, H, W, P, Kp);
+    else patch_gather_kernel<__half, __half><<<grid, 256, 0, st>>>((const __half*)in, (__half*)out, B, Cin, H, W, P, Kp);
+  } else {
+    if (in_f32) patch_gather_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const float*)in, (__nv_bfloat16*)out, B, Cin, H, W, P, Kp);
+    else patch_gather_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, Cin, H, W, P, Kp);
+  }
+  return launch_ok();
+}
+
+// ------------------------------------------------------------------------------------------------ x[b, t, :] += tab[t, :]
+template <typename T>
+__global__ void add_bcast_rows_kernel(T* __restrict__ x, const T* __restrict__ tab, long long rows, int rows_per_batch, int C) {
+  const int cv = C >> 3;
+  const long long total = rows * cv;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = (idx % cv) * 8;
+    const long long r = idx / cv;
+    uint4 xv = *reinterpret_cast<const uint4*>(x + r * C + c8);
+    const uint4 tv = *reinterpret_cast<const uint4*>(tab + static_cast<size_t>(r % rows_per_batch) * C + c8);
+    T* xe = reinterpret_cast<T*>(&xv);
+    const T* te = reinterpret_cast<const T*>(&tv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xe[j] = from_f<T>(to_f<T>(xe[j]) + to_f<T>(te[j]));
+    *reinterpret_cast<uint4*>(x + r * C + c8) = xv;
+  }
+}
+
+int add_bcast_rows(int dtype, void* x, const void* tab, long long rows, int rows_per_batch, int C, cudaStream_t st) {
+  if (C % 8) { set_error("add_bcast_rows: C must be a multiple of 8"); return -1; }
+  const long long total = rows * (C / 8);
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > num_sms() * 32) grid = num_sms() * 32;
+  if (dtype == DT_F16) add_bcast_rows_kernel<__half><<<grid, 256, 0, st>>>((__half*)x, (const __half*)tab, rows, rows_per_batch, C);
+  else add_bcast_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)x, (const __nv_bfloat16*)tab, rows, rows_per_batch, C);
+  return launch_ok();
+}
+
+// ------------------------------------------------------------------------------------------------ 2x2 patch-merging gather
+// x [B, H, W, C] -> y [B, H/2, W/2, 4C], channel blocks (dy,dx) = (0,0), (1,0), (0,1), (1,1)
+template <typename T>
+__global__ void patch_merge_gather_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C) {
+  const int cv = C >> 3, Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(B) * Ho * Wo * 4 * cv;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = (idx % cv) * 8;
+    long long r = idx / cv;
+    const int blk = r % 4;
+    r /= 4;
+    const int ox = r % Wo, oy = (r / Wo) % Ho;
+    const int b = r / (static_cast<long long>(Wo) * Ho);
+    const int dy = blk & 1, dx = blk >> 1;
+    const uint4 v = *reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + 2 * oy + dy) * W + 2 * ox + dx) * C + c8);
+    *reinterpret_cast<uint4*>(y + (((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * 4 + blk) * C + c8) = v;
+  }
+}
+
+int patch_merge_gather(int dtype, const void* x, void* y, int B, int H, int W, int C, cudaStream_t st) {
+  if (C % 8 || H % 2 || W % 2) { set_error("patch_merge_gather: C %% 8, even H and W"); return -1; }
+  const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * 4 * (C / 8);
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > num_sms() * 32) grid = num_sms() * 32;
+  if (dtype == DT_F16) patch_merge_gather_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, (__half*)y, B, H, W, C);
+  else patch_merge_gather_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, H, W, C);
+  return launch_ok();
+}
+
+// ------------------------------------------------------------------------------------------------ Swin window attention
+template <typename T> struct MmaS;
+template <> struct MmaS<__nv_bfloat16> {
+  static __device__ __forceinline__ void run(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) { __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&v); }
+};
+template <> struct MmaS<__half> {
+  static __device__ __forceinline__ void run(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) { __half2 v = __floats2half2_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&v); }
+};
+
+// qkv [B*H*W, 3C] natural token order (q | k | v, head h at h*32); bias_table T [225, nh]; out [B*H*W, C].
+// One CTA = one 8x8 window x 4 heads (128 contiguous channels per token); warp w owns query rows 16w..16w+15.
+template <typename T>
+__global__ void __launch_bounds__(128) swin_window_attn_kernel(const T* __restrict__ qkv, const T* __restrict__ bias_table,
+                                                               T* __restrict__ out, int H, int W, int C, int nh, int shift,
+                                                               float scale) {
+  constexpr int WS = 8, NT = 64, HD = 32, HG = 4, LDS = HG * HD + 8;
+  extern __shared__ __align__(16) uint8_t smem_sw[];
+  T* sQ = reinterpret_cast<T*>(smem_sw);
+  T* sK = sQ + NT * LDS;
+  T* sV = sK + NT * LDS;
+  float* sBias = reinterpret_cast<float*>(sV + NT * LDS);   // [225][HG]
+  __shared__ int s_tok[NT];
+  __shared__ int s_reg[NT];
+
+  const int nwx = W / WS, nwy = H / WS;
+  const int win = blockIdx.x % (nwx * nwy);
+  const int b = blockIdx.x / (nwx * nwy);
+  const int hg = blockIdx.y;                 // head group
+  const int wy = win / nwx, wx = win % nwx;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+
+  if (tid < NT) {
+    const int py = tid / WS, px = tid % WS;
+    const int ys = wy * WS + py, xs = wx * WS + px;                 // coordinates in the shifted image
+    const int y = (ys + shift) % H, x = (xs + shift) % W;           // torch.roll(-shift) source
+    s_tok[tid] = (b * H + y) * W + x;
+    int ry = 0, rx = 0;
+    if (shift > 0) {
+      ry = ys < H - WS ? 0 : (ys < H - shift ? 1 : 2);
+      rx = xs < W - WS ? 0 : (xs < W - shift ? 1 : 2);
+    }
+    s_reg[tid] = ry * 3 + rx;
+  }
+  for (int i = tid; i < 225 * HG; i += 128) {
+    const int e = i / HG, hh = i % HG;
+    sBias[i] = to_f<T>(bias_table[static_cast<size_t>(e) * nh + hg * HG + hh]);
+  }
+  __syncthreads();
+  // gather Q, K, V rows of this window for the 4 heads (256 contiguous bytes per token and tensor)
+  constexpr int VPR = HG * HD / 8;  // 16
+  for (int i = tid; i < NT * VPR; i += 128) {
+    const int r = i / VPR, c = i % VPR;
+    const T* base = qkv + static_cast<size_t>(s_tok[r]) * (3 * C) + hg * HG * HD + c * 8;
+    *reinterpret_cast<uint4*>(sQ + r * LDS + c * 8) = *reinterpret_cast<const uint4*>(base);
+    *reinterpret_cast<uint4*>(sK + r * LDS + c * 8) = *reinterpret_cast<const uint4*>(base + C);
+    *reinterpret_cast<uint4*>(sV + r * LDS + c * 8) = *reinterpret_cast<const uint4*>(base + 2 * C);
+  }
+  __syncthreads();
+
+  const int rbase = warp * 16;
+  const int q0 = rbase + g, q1 = q0 + 8;
+  const int q0y = q0 / WS, q0x = q0 % WS, q1y = q1 / WS, q1x = q1 % WS;
+  const int reg0 = s_reg[q0], reg1 = s_reg[q1];
+  for (int hh = 0; hh < HG; ++hh) {
+    const int co = hh * HD;
+    uint32_t aQ[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      aQ[ks][0] = *reinterpret_cast<const uint32_t*>(sQ + q0 * LDS + co + ks * 16 + 2 * t);
+      aQ[ks][1] = *reinterpret_cast<const uint32_t*>(sQ + q1 * LDS + co + ks * 16 + 2 * t);
+      aQ[ks][2] = *reinterpret_cast<const uint32_t*>(sQ + q0 * LDS + co + ks * 16 + 8 + 2 * t);
+      aQ[ks][3] = *reinterpret_cast<const uint32_t*>(sQ + q1 * LDS + co + ks * 16 + 8 + 2 * t);
+    }
+    float S[8][4];
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      S[nt][0] = S[nt][1] = S[nt][2] = S[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sK + (nt * 8 + g) * LDS + co + ks * 16 + 2 * t);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sK + (nt * 8 + g) * LDS + co + ks * 16 + 8 + 2 * t);
+        MmaS<T>::run(S[nt], aQ[ks], b0, b1);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = nt * 8 + 2 * t + (e & 1);
+        const int ky = key / WS, kx = key % WS;
+        const int qy = e < 2 ? q0y : q1y, qx = e < 2 ? q0x : q1x;
+        float add = sBias[((qy - ky + WS - 1) * (2 * WS - 1) + (qx - kx + WS - 1)) * HG + hh];
+        if (shift > 0 && s_reg[key] != (e < 2 ? reg0 : reg1)) add = rnd<T>(add - 100.0f);   // mask + bias summed in T
+        const float sv = S[nt][e] * scale + add;
+        S[nt][e] = sv;
+        if (e < 2) mx0 = fmaxf(mx0, sv); else mx1 = fmaxf(mx1, sv);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      S[nt][0] = __expf(S[nt][0] - mx0); S[nt][1] = __expf(S[nt][1] - mx0);
+      S[nt][2] = __expf(S[nt][2] - mx1); S[nt][3] = __expf(S[nt][3] - mx1);
+      l0 += S[nt][0] + S[nt][1];
+      l1 += S[nt][2] + S[nt][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    float O[4][4];
+#pragma unroll
+    for (int dn = 0; dn < 4; ++dn) O[dn][0] = O[dn][1] = O[dn][2] = O[dn][3] = 0.f;
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+      uint32_t aP[4];
+      aP[0] = MmaS<T>::pack(S[2 * kc][0] * i0, S[2 * kc][1] * i0);
+      aP[1] = MmaS<T>::pack(S[2 * kc][2] * i1, S[2 * kc][3] * i1);
+      aP[2] = MmaS<T>::pack(S[2 * kc + 1][0] * i0, S[2 * kc + 1][1] * i0);
+      aP[3] = MmaS<T>::pack(S[2 * kc + 1][2] * i1, S[2 * kc + 1][3] * i1);
+      const int mid = lane >> 3, r = lane & 7;
+#pragma unroll
+      for (int dn = 0; dn < 4; dn += 2) {
+        uint32_t bv[4];
+        const T* addr = sV + (kc * 16 + (mid & 1) * 8 + r) * LDS + co + (dn + (mid >> 1)) * 8;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                     : "=r"(bv[0]), "=r"(bv[1]), "=r"(bv[2]), "=r"(bv[3]) : "r"(smem_u32(addr)));
+        MmaS<T>::run(O[dn], aP, bv[0], bv[1]);
+        MmaS<T>::run(O[dn + 1], aP, bv[2], bv[3]);
+      }
+    }
+    T* o0 = out + static_cast<size_t>(s_tok[q0]) * C + (hg * HG + hh) * HD;
+    T* o1 = out + static_cast<size_t>(s_tok[q1]) * C + (hg * HG + hh) * HD;
+#pragma unroll
+    for (int dn = 0; dn < 4; ++dn) {
+      *reinterpret_cast<uint32_t*>(o0 + dn * 8 + 2 * t) = MmaS<T>::pack(O[dn][0], O[dn][1]);
+      *reinterpret_cast<uint32_t*>(o1 + dn * 8 + 2 * t) = MmaS<T>::pack(O[dn][2], O[dn][3]);
+    }
+  }
+}
+
+int swin_window_attn(int dtype, const void* qkv, const void* bias_table, void* out, int B, int H, int W, int C, int nh, int shift,
+                     cudaStream_t st) {
+  if (H % 8 || W % 8 || nh % 4 || C != nh * 32) {
+    set_error("swin_window_attn: needs H, W multiples of the 8x8 window, head_dim 32 and heads in groups of 4 (H=%d W=%d C=%d nh=%d)", H, W, C, nh);
+    return -1;
+  }
+  constexpr size_t SMEM = 3 * 64 * (128 + 8) * 2 + 225 * 4 * 4;
+  dim3 grid(B * (H / 8) * (W / 8), nh / 4), block(128);
+  const float scale = 0.17677669529663687f;  // 32^-0.5
+  if (dtype == DT_F16) {
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(swin_window_attn_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM); set = true; }
+    swin_window_attn_kernel<__half><<<grid, block, SMEM, st>>>((const __half*)qkv, (const __half*)bias_table, (__half*)out, H, W, C, nh, shift, scale);
+  } else {
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(swin_window_attn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM); set = true; }
+    swin_window_attn_kernel<__nv_bfloat16><<<grid, block, SMEM, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)bias_table, (__nv_bfloat16*)out, H, W, C, nh, shift, scale);
+  }
+  return launch_ok();
+}
+
+// ------------------------------------------------------------------------------------------------ BboxEmbedding
+// boxes i64 [n, 7] = (cx, cy, w, h, xskew, yskew, label); tables T [15][...]: w,h,cx,cy,xskew,yskew,x1,y1,..,y4 each
+// [vocab, Hd], label [label_count, Hd].  Sums follow the reference's association order, one rounding per add.
+struct BboxTables { const void* t[15]; };
+
+template <typename T>
+__global__ void bbox_embed_sum_kernel(const long long* __restrict__ boxes, BboxTables tabs, T* __restrict__ out, int n, int Hd,
+                                      int bbox_size) {
+  const int r = blockIdx.x;
+  if (r >= n) return;
+  const long long* bx = boxes + static_cast<size_t>(r) * 7;
+  const long long cx = bx[0], cy = bx[1], w = bx[2], h = bx[3], xs = bx[4], ys = bx[5], label = bx[6];
+  auto trunc_div2 = [](long long v) { return static_cast<long long>(static_cast<double>(v) / 2.0); };  // (x / 2).to(long)
+  const long long xa = trunc_div2(xs - bbox_size / 2), ya = trunc_div2(ys - bbox_size / 2);
+  auto fdiv2 = [](long long v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); };                            // python floor //
+  auto cl = [&](long long v) { return v < 0 ? 0LL : (v > bbox_size ? static_cast<long long>(bbox_size) : v); };
+  const long long hw = fdiv2(w), hh = fdiv2(h);
+  const long long idx[15] = {w, h, cx, cy, xs, ys,
+                             cl(cx - hw - xa), cl(cy - hh - ya), cl(cx + hw - xa), cl(cy + hh + ya),
+                             cl(cx + hw + xa), cl(cy + hh + ya), cl(cx - hw + xa), cl(cy - hh - ya), label};
+  const T* rows[15];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) rows[i] = reinterpret_cast<const T*>(tabs.t[i]) + static_cast<size_t>(idx[i]) * Hd;
+  T* o = out + static_cast<size_t>(r) * Hd;
+  for (int c = threadIdx.x; c < Hd; c += blockDim.x) {
+    auto f = [&](int i) { return to_f<T>(rows[i][c]); };
+    const float size = rnd<T>(rnd<T>(rnd<T>(f(0) + f(1)) + f(2)) + f(3));
+    const float skew = rnd<T>(f(4) + f(5));
+    float corner = rnd<T>(f(6) + f(7));
+#pragma unroll
+    for (int i = 8; i < 14; ++i) corner = rnd<T>(corner + f(i));
+    const float e = rnd<T>(rnd<T>(rnd<T>(f(14) + size) + skew) + corner);
+    o[c] = from_f<T>(e);
+  }
+}
+
+int bbox_embed_sum(int dtype, const long long* boxes, const void* const* tables, void* out, int n, int Hd, int bbox_size,
+                   cudaStream_t st) {
+  if (n <= 0) return 0;
+  BboxTables tb;
+  for (int i = 0; i < 15; ++i) tb.t[i] = tables[i];
+  if (dtype == DT_F16) bbox_embed_sum_kernel<__half><<<n, 128, 0, st>>>(boxes, tb, (__half*)out, n, Hd, bbox_size);
+  else bbox_embed_sum_kernel<__nv_bfloat16><<<n, 128, 0, st>>>(boxes, tb, (__nv_bfloat16*)out, n, Hd, bbox_size);
+  return launch_ok();
+}
+
+// ------------------------------------------------------------------------------------------------ single-query attention
+// q [B, nh*HD]; K/V element (b, kvh, j, c) at base + b*bs + kvh*hs + j*ts + c; out [B, nh*HD]. One CTA per (b, kv head).
+template <typename T, int HD, int G>
+__global__ void __launch_bounds__(128) attn_single_query_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ K,
+                                                                const T* __restrict__ V, long long bs, long long hs,
+                                                                long long ts, T* __restrict__ out, int ldo, int n_keys,
+                                                                float scale) {
+  constexpr int VPR = HD / 8, NKG = 128 / VPR;
+  extern __shared__ __align__(16) uint8_t smem_sq[];
+  float* q_s = reinterpret_cast<float*>(smem_sq);   // [G][HD]
+  float* red = q_s + G * HD;                         // [NKG][G][HD]
+  float* sc = red + NKG * G * HD;                    // [G][n_keys]
+  __shared__ float s_red[4][G];
+  __shared__ float s_m[G], s_l[G];
+  const int b = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const T* qr = q + static_cast<size_t>(b) * ldq + kvh * G * HD;
+  for (int i = tid; i < G * HD; i += 128) q_s[i] = to_f<T>(qr[i]);
+  const T* kb = K + b * bs + kvh * hs;
+  const T* vb = V + b * bs + kvh * hs;
+  __syncthreads();
+  float tmax[G];
+#pragma unroll
+  for (int gq = 0; gq < G; ++gq) tmax[gq] = -INFINITY;
+  for (int j = tid; j < n_keys; j += 128) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kb + j * ts);
+    float acc[G];
+#pragma unroll
+    for (int gq = 0; gq < G; ++gq) acc[gq] = 0.f;
+#pragma unroll
+    for (int c = 0; c < VPR; ++c) {
+      const uint4 u = kr[c];
+      const T* e = reinterpret_cast<const T*>(&u);
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        const float kf = to_f<T>(e[x]);
+#pragma unroll
+        for (int gq = 0; gq < G; ++gq) acc[gq] += q_s[gq * HD + c * 8 + x] * kf;
+      }
+    }
+#pragma unroll
+    for (int gq = 0; gq < G; ++gq) {
+      const float sv = acc[gq] * scale;
+      sc[gq * n_keys + j] = sv;
+      tmax[gq] = fmaxf(tmax[gq], sv);
+    }
+  }
+#pragma unroll
+  for (int gq = 0; gq < G; ++gq) { const float m = warp_max(tmax[gq]); if (lane == 0) s_red[warp][gq] = m; }
+  __syncthreads();
+  if (tid < G) s_m[tid] = fmaxf(fmaxf(s_red[0][tid], s_red[1][tid]), fmaxf(s_red[2][tid], s_red[3][tid]));
+  __syncthreads();
+  float tsum[G];
+#pragma unroll
+  for (int gq = 0; gq < G; ++gq) tsum[gq] = 0.f;
+  for (int j = tid; j < n_keys; j += 128) {
+#pragma unroll
+    for (int gq = 0; gq < G; ++gq) {
+      const float pv = __expf(sc[gq * n_keys + j] - s_m[gq]);
+      tsum[gq] += pv;
+      sc[gq * n_keys + j] = pv;
+    }
+  }
+#pragma unroll
+  for (int gq = 0; gq < G; ++gq) { const float s = warp_sum(tsum[gq]); if (lane == 0) s_red[warp][gq] = s; }
+  __syncthreads();
+  if (tid < G) s_l[tid] = s_red[0][tid] + s_red[1][tid] + s_red[2][tid] + s_red[3][tid];
+  __syncthreads();
+  const int chunk = tid % VPR, kg = tid / VPR;
+  if (kg < NKG) {
+    float acc[G][8];
+#pragma unroll
+    for (int gq = 0; gq < G; ++gq)
+#pragma unroll
+      for (int x = 0; x < 8; ++x) acc[gq][x] = 0.f;
+    for (int j = kg; j < n_keys; j += NKG) {
+      const uint4 u = *reinterpret_cast<const uint4*>(vb + j * ts + chunk * 8);
+      const T* e = reinterpret_cast<const T*>(&u);
+#pragma unroll
+      for (int gq = 0; gq < G; ++gq) {
+        const float pj = rnd<T>(sc[gq * n_keys + j] / s_l[gq]);
+#pragma unroll
+        for (int x = 0; x < 8; ++x) acc[gq][x] += pj * to_f<T>(e[x]);
+      }
+    }
+#pragma unroll
+    for (int gq = 0; gq < G; ++gq)
+#pragma unroll
+      for (int x = 0; x < 8; ++x) red[(kg * G + gq) * HD + chunk * 8 + x] = acc[gq][x];
+  }
+  __syncthreads();
+  T* orow = out + static_cast<size_t>(b) * ldo + kvh * G * HD;
+  for (int i = tid; i < G * HD; i += 128) {
+    float s = 0.f;
+#pragma unroll
+    for (int k2 = 0; k2 < NKG; ++k2) s += red[k2 * G * HD + i];
+    orow[i] = from_f<T>(s);
+  }
+}
+
+template <typename T, int G>
+static int launch_sq(const void* q, int ldq, const void* K, const void* V, long long bs, long long hs, long long ts, void* out,
+                     int ldo, int B, int nkv, int n_keys, float scale, cudaStream_t st) {
+  constexpr int HD = 64, NKG = 128 / (HD / 8);
+  const size_t smem = (static_cast<size_t>(G) * HD + static_cast<size_t>(NKG) * G * HD + static_cast<size_t>(G) * n_keys) * sizeof(float);
+  auto kern = attn_single_query_kernel<T, HD, G>;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("attn_single_query: %zu bytes of shared memory exceed the device limit", smem);
+      return -3;
+    }
+    attr = smem;
+  }
+  kern<<<dim3(B, nkv), 128, smem, st>>>((const T*)q, ldq, (const T*)K, (const T*)V, bs, hs, ts, (T*)out, ldo, n_keys, scale);
+  return launch_ok();
+}
+
+int attn_single_query(int dtype, const void* q, int ldq, const void* K, const void* V, long long bs, long long hs, long long ts,
+                      void* out, int ldo, int B, int nh, int nkv, int head_dim, int n_keys, float scale, cudaStream_t st) {
+  if (head_dim != 64) { set_error("attn_single_query: head_dim 64 is instantiated (got %d)", head_dim); return -1; }
+  const int G = nh / nkv;
+#define SQ(T_) \
+  (G == 1 ? launch_sq<T_, 1>(q, ldq, K, V, bs, hs, ts, out, ldo, B, nkv, n_keys, scale, st) : \
+   G == 2 ? launch_sq<T_, 2>(q, ldq, K, V, bs, hs, ts, out, ldo, B, nkv, n_keys, scale, st) : \
+   G == 4 ? launch_sq<T_, 4>(q, ldq, K, V, bs, hs, ts, out, ldo, B, nkv, n_keys, scale, st) : -9)
+  int rc = dtype == DT_F16 ? SQ(__half) : SQ(__nv_bfloat16);
+#undef SQ
+  if (rc == -9) set_error("attn_single_query: GQA group %d not instantiated (1/2/4)", G);
+  return rc;
+}
+
+}  // namespace sb

@@ -16,7 +16,7 @@ namespace sb {
 // One warp per row. y = weight * T(x * rsqrt(mean(x^2) + eps)); optional row gather (src_rows).
 template <typename T>
 __global__ void rmsnorm_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ w, T* __restrict__ y, int ldy,
-                               int rows, int H, float eps, const int* __restrict__ src_rows) {
+                               int rows, int H, float eps, const int* __restrict__ src_rows, int mode) {
   pdl_trigger();
   pdl_wait();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -41,7 +41,10 @@ __global__ void rmsnorm_kernel(const T* __restrict__ x, int ldx, const T* __rest
     ss += f * f;
   }
   ss = warp_sum(ss);
-  float inv = rsqrtf(ss / static_cast<float>(H) + eps);
+  // mode 0: Qwen2RMSNorm  y = w * T(x * rsqrt(mean + eps))
+  // mode 1: SuryaADETRDecoderRMSNorm (adetr/decoder.py:29-47)  y = T(clamp(x * rsqrt(max(mean, eps)) * (1 + w)))
+  float inv = mode ? rsqrtf(fmaxf(ss / static_cast<float>(H), eps)) : rsqrtf(ss / static_cast<float>(H) + eps);
+  const float tmax = sizeof(T) == 2 && TypeInfo<T>::umma_fmt == 0 ? 65504.f : 3.3895313892515355e38f;
   for (int i = lane; i < nv; i += 32) {
     uint4 u = *reinterpret_cast<const uint4*>(xr + i * 8);
     uint4 wv = *reinterpret_cast<const uint4*>(w + i * 8);
@@ -51,29 +54,41 @@ __global__ void rmsnorm_kernel(const T* __restrict__ x, int ldx, const T* __rest
     T* oe = reinterpret_cast<T*>(&o);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float n = rnd<T>(to_f<T>(e[j]) * inv);
-      oe[j] = from_f<T>(to_f<T>(we[j]) * n);
+      if (mode) {
+        float v = to_f<T>(e[j]) * inv * (1.0f + to_f<T>(we[j]));
+        v = fminf(fmaxf(v, -tmax), tmax);
+        oe[j] = from_f<T>(v != v ? 0.f : v);
+      } else {
+        float n = rnd<T>(to_f<T>(e[j]) * inv);
+        oe[j] = from_f<T>(to_f<T>(we[j]) * n);
+      }
     }
     *reinterpret_cast<uint4*>(yr + i * 8) = o;
   }
   for (int i = (nv << 3) + lane; i < H; i += 32) {
-    float n = rnd<T>(to_f<T>(xr[i]) * inv);
-    yr[i] = from_f<T>(to_f<T>(w[i]) * n);
+    if (mode) {
+      float v = to_f<T>(xr[i]) * inv * (1.0f + to_f<T>(w[i]));
+      v = fminf(fmaxf(v, -tmax), tmax);
+      yr[i] = from_f<T>(v != v ? 0.f : v);
+    } else {
+      float n = rnd<T>(to_f<T>(xr[i]) * inv);
+      yr[i] = from_f<T>(to_f<T>(w[i]) * n);
+    }
   }
 }
 
 int rmsnorm(int dtype, const void* x, int ldx, const void* w, void* y, int ldy, int rows, int H, float eps,
-            const int* src_rows, cudaStream_t st) {
+            const int* src_rows, cudaStream_t st, int mode) {
   if (rows <= 0) return 0;
   if (ldx % 8 || ldy % 8) { set_error("rmsnorm: row pitch must be a multiple of 8 elements"); return -1; }
   int wpb = 4;
   dim3 grid((rows + wpb - 1) / wpb), block(32 * wpb);
   if (dtype == DT_BF16)
     launch_pdl(rmsnorm_kernel<__nv_bfloat16>, grid, block, 0, st, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w,
-               (__nv_bfloat16*)y, ldy, rows, H, eps, src_rows);
+               (__nv_bfloat16*)y, ldy, rows, H, eps, src_rows, mode);
   else
     launch_pdl(rmsnorm_kernel<__half>, grid, block, 0, st, (const __half*)x, ldx, (const __half*)w, (__half*)y, ldy, rows, H,
-               eps, src_rows);
+               eps, src_rows, mode);
   return launch_ok();
 }
 

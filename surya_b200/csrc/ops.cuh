@@ -5,7 +5,7 @@
 namespace sb {
 
 int rmsnorm(int dtype, const void* x, int ldx, const void* w, void* y, int ldy, int rows, int H, float eps,
-            const int* src_rows, cudaStream_t st);
+            const int* src_rows, cudaStream_t st, int mode = 0);
 int gather_pad_rows(int dtype, const void* src, int src_is_f32, int lds, const int* perm, void* dst, int ldd, int rows,
                     int K, int Kp, cudaStream_t st);
 int rope_vision(int dtype, void* qkv, int ld, const int* pos_rc, const float* inv_freq, int n_tok, int nh, int d,
@@ -64,6 +64,18 @@ int det_upsample_cat(int dtype, const void* const* src, const int* hs, const int
 int det_classifier(int dtype, const void* x, const void* w, const void* b, void* out, long long P, int C, int HW, int n_out,
                    cudaStream_t st);
 int det_upsample_nchw(int dtype, const void* in, float* out, int planes, int hs, int ws, int HO, int WO, cudaStream_t st);
+
+// Layout / table_rec kernels (layout_ops.cu).
+int layernorm(int dtype, const void* x, const void* w, const void* b, void* y, int rows, int C, float eps, cudaStream_t st);
+int patch_gather(int dtype, const void* in, int in_f32, void* out, int B, int Cin, int H, int W, int P, int Kp, cudaStream_t st);
+int add_bcast_rows(int dtype, void* x, const void* tab, long long rows, int rows_per_batch, int C, cudaStream_t st);
+int patch_merge_gather(int dtype, const void* x, void* y, int B, int H, int W, int C, cudaStream_t st);
+int swin_window_attn(int dtype, const void* qkv, const void* bias_table, void* out, int B, int H, int W, int C, int nh, int shift,
+                     cudaStream_t st);
+int bbox_embed_sum(int dtype, const long long* boxes, const void* const* tables, void* out, int n, int Hd, int bbox_size,
+                   cudaStream_t st);
+int attn_single_query(int dtype, const void* q, int ldq, const void* K, const void* V, long long bs, long long hs, long long ts,
+                      void* out, int ldo, int B, int nh, int nkv, int head_dim, int n_keys, float scale, cudaStream_t st);
 
 // Single-token decode attention over the slot KV cache, fused with RoPE(q,k) and the in-place cache append.
 //   qkv[b] = [q(nh*d) | k(nkv*d) | v(nkv*d)] for batch row b; slot[b], pos[b] (= number of cached tokens) on device.

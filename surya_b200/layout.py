@@ -1,0 +1,265 @@
+"""Layout path: Donut-Swin encoder + ADETR box decoder on the CUDA kernels, behind the call surface LayoutPredictor uses.
+
+  * LayoutEngine        packed weights + forward passes built from libsurya_b200.so ops (tcgen05 GEMMs for every Linear,
+                        swin_window_attn, layernorm, decode_attn / attn_single_query, ...); round 1 drives the layer loops
+                        from Python (correctness first), the kernels are the same ones the C++ engines use
+  * B200LayoutModel     quacks like the model LayoutPredictor touches (surya/layout/__init__.py:83-123, 222):
+                        model.encoder(pixel_values=...)[0], model.decoder(input_boxes=..., encoder_hidden_states=...,
+                        cache_position=..., use_cache=True, prefill=...) -> {"bbox_logits", "class_logits"},
+                        model.decoder.model._setup_cache / _clear_cache, config fields
+  * layout_greedy       the predictor's device-side loop: encoder once, greedy box decoding (surya/layout/__init__.py:106-183)
+
+No PyTorch math on the forward path (torch = memory + streams), no import of oracle/.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib, ops
+from .config import LayoutConfig
+from .synth import LAYOUT_EMBED_TABLES
+
+
+def _sincos_table(width: int, height: int, dim: int) -> torch.Tensor:
+    """DonutSwinStage.build_2d_sincos_position_embedding (surya/common/donut/encoder.py:736-761), fp32 on the host."""
+    gw = torch.arange(int(width), dtype=torch.float32)
+    gh = torch.arange(int(height), dtype=torch.float32)
+    gw, gh = torch.meshgrid(gw, gh, indexing="ij")
+    pos_dim = dim // 4
+    omega = 1.0 / (10000.0 ** (torch.arange(pos_dim, dtype=torch.float32) / pos_dim))
+    ow = gw.flatten()[..., None] @ omega[None]
+    oh = gh.flatten()[..., None] @ omega[None]
+    return torch.concat([ow.sin(), ow.cos(), oh.sin(), oh.cos()], dim=1)
+
+
+class LayoutEngine:
+    def __init__(self, cfg: LayoutConfig, sd_enc: Dict[str, torch.Tensor], sd_dec: Dict[str, torch.Tensor],
+                 dtype: torch.dtype = torch.float16, device: str | torch.device = "cuda", max_batch: int = 16):
+        _lib.load()
+        self.cfg, self.dtype, self.device, self.max_batch = cfg, dtype, torch.device(device), max_batch
+        e, d = cfg.encoder, cfg.decoder
+        dev = self.device
+
+        def T(x):
+            return x.to(dtype).contiguous().to(dev)
+
+        def B32(x):
+            return x.to(dtype).float().contiguous().to(dev)
+
+        # ---- Swin encoder
+        K = e.num_channels * e.patch_size ** 2
+        self.pe_kp = (K + 63) // 64 * 64
+        pw = torch.zeros((e.embed_dim, self.pe_kp))
+        pw[:, :K] = sd_enc["embeddings.patch_embeddings.projection.weight"].reshape(e.embed_dim, K)
+        self.pe_w, self.pe_b = T(pw), B32(sd_enc["embeddings.patch_embeddings.projection.bias"])
+        self.pe_ln = (T(sd_enc["embeddings.norm.weight"]), T(sd_enc["embeddings.norm.bias"]))
+        gh, gw = e.grid
+        self.stages = []
+        for s, (depth, nh) in enumerate(zip(e.depths, e.num_heads)):
+            C = e.embed_dim * 2 ** s
+            st = {"C": C, "nh": nh, "pos": T(_sincos_table(gw // 2 ** s, gh // 2 ** s, C)), "layers": []}
+            for b in range(depth):
+                p = f"encoder.layers.{s}.blocks.{b}."
+                a = p + "attention.self."
+                st["layers"].append({
+                    "ln1": (T(sd_enc[p + "layernorm_before.weight"]), T(sd_enc[p + "layernorm_before.bias"])),
+                    "qkv_w": T(torch.cat([sd_enc[a + "query.weight"], sd_enc[a + "key.weight"], sd_enc[a + "value.weight"]], 0)),
+                    "qkv_b": B32(torch.cat([sd_enc[a + "query.bias"], sd_enc[a + "key.bias"], sd_enc[a + "value.bias"]], 0)),
+                    "rpb": T(sd_enc[a + "relative_position_bias_table"]),
+                    "o_w": T(sd_enc[p + "attention.output.dense.weight"]), "o_b": B32(sd_enc[p + "attention.output.dense.bias"]),
+                    "ln2": (T(sd_enc[p + "layernorm_after.weight"]), T(sd_enc[p + "layernorm_after.bias"])),
+                    "fc1_w": T(sd_enc[p + "intermediate.dense.weight"]), "fc1_b": B32(sd_enc[p + "intermediate.dense.bias"]),
+                    "fc2_w": T(sd_enc[p + "output.dense.weight"]), "fc2_b": B32(sd_enc[p + "output.dense.bias"]),
+                    "shift": 0 if b % 2 == 0 else e.window_size // 2,
+                })
+            if s < len(e.depths) - 1:
+                p = f"encoder.layers.{s}.downsample."
+                st["merge"] = {"ln": (T(sd_enc[p + "norm.weight"]), T(sd_enc[p + "norm.bias"])), "w": T(sd_enc[p + "reduction.weight"])}
+            self.stages.append(st)
+        self.enc_pos = T(sd_enc["position_embeddings"][0])
+
+        # ---- ADETR decoder
+        nh, nkv, hd, H = d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.hidden_size
+        order = list(LAYOUT_EMBED_TABLES) + ["label"]
+        self.tables = [T(sd_dec[f"model.embed_tokens.{t}_embed.weight"]) for t in order]
+        self.layers = []
+        for l in range(d.num_hidden_layers):
+            p = f"model.layers.{l}."
+            gate, up = sd_dec[p + "mlp_block.gate_proj.weight"], sd_dec[p + "mlp_block.up_proj.weight"]
+            self.layers.append({
+                "cross_norm": T(sd_dec[p + "cross_pre_norm.weight"]), "self_norm": T(sd_dec[p + "temporal_pre_norm.weight"]),
+                "mlp_norm": T(sd_dec[p + "channel_pre_norm.weight"]),
+                "cq_w": T(sd_dec[p + "cross_attn_block.q_proj.weight"]),
+                "ckv_w": T(torch.cat([sd_dec[p + "cross_attn_block.k_proj.weight"], sd_dec[p + "cross_attn_block.v_proj.weight"]], 0)),
+                "co_w": T(sd_dec[p + "cross_attn_block.o_proj.weight"]), "co_b": B32(sd_dec[p + "cross_attn_block.o_proj.bias"]),
+                "sqkv_w": T(torch.cat([sd_dec[p + "temporal_block.q_proj.weight"], sd_dec[p + "temporal_block.k_proj.weight"],
+                                       sd_dec[p + "temporal_block.v_proj.weight"]], 0)),
+                "so_w": T(sd_dec[p + "temporal_block.o_proj.weight"]), "so_b": B32(sd_dec[p + "temporal_block.o_proj.bias"]),
+                "gu_w": T(torch.stack([gate, up], 1).reshape(2 * gate.shape[0], gate.shape[1])),
+                "down_w": T(sd_dec[p + "mlp_block.down_proj.weight"]),
+            })
+        self.final_norm = T(sd_dec["model.final_norm.weight"])
+        self.out_ln = (T(sd_dec["pre_output_norm.weight"]), T(sd_dec["pre_output_norm.bias"]))
+        self.cls_w = T(sd_dec["lm_head.weight"])
+        self.bbox_w, self.bbox_b = T(sd_dec["bbox_head.weight"]), T(sd_dec["bbox_head.bias"])
+        self.inv_freq = (1.0 / (d.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).to(dev)
+        self.s_max = d.max_boxes + 8
+        self._cache_batch = 0
+        self.cross_kv: List[Optional[torch.Tensor]] = [None] * d.num_hidden_layers
+        self.kcache: List[torch.Tensor] = []
+        self.vcache: List[torch.Tensor] = []
+        self.n_enc = 0
+
+    # ---------------------------------------------------------------------------------------------- encoder
+    def encode(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        """DonutSwinLayoutModel.forward (surya/layout/model/encoder.py:33-81): NCHW pixels -> [B, L, hidden]."""
+        e = self.cfg.encoder
+        B, _, Hi, Wi = pixel_values.shape
+        if (Hi, Wi) != tuple(e.image_size):
+            raise _lib.SuryaB200Error(f"layout encoder expects {e.image_size} inputs, got {(Hi, Wi)}")
+        if not pixel_values.is_cuda:
+            pixel_values = pixel_values.to(self.device, non_blocking=True)
+        if pixel_values.dtype not in (torch.float32, self.dtype):
+            raise _lib.SuryaB200Error("pixel_values must be float32 or the engine dtype")
+        x = ops.patch_gather(pixel_values, e.patch_size, self.pe_kp, self.dtype)
+        x = ops.gemm(x, self.pe_w, bias=self.pe_b)
+        x = ops.layernorm(x, *self.pe_ln, eps=1e-5)
+        H, W = e.grid
+        for st in self.stages:
+            C, nh = st["C"], st["nh"]
+            ops.add_bcast_rows_(x, st["pos"])
+            for L in st["layers"]:
+                h = ops.layernorm(x, *L["ln1"], eps=e.layer_norm_eps)
+                qkv = ops.gemm(h, L["qkv_w"], bias=L["qkv_b"])
+                a = ops.swin_window_attn(qkv, L["rpb"], B, H, W, nh, L["shift"] if min(H, W) > e.window_size else 0)
+                x = ops.gemm(a, L["o_w"], bias=L["o_b"], residual=x)
+                h = ops.layernorm(x, *L["ln2"], eps=e.layer_norm_eps)
+                h = ops.gemm(h, L["fc1_w"], bias=L["fc1_b"], act="gelu")
+                x = ops.gemm(h, L["fc2_w"], bias=L["fc2_b"], residual=x)
+            if "merge" in st:
+                m = ops.patch_merge_gather(x, B, H, W)
+                m = ops.layernorm(m, *st["merge"]["ln"], eps=1e-5)
+                x = ops.gemm(m, st["merge"]["w"])
+                H, W = H // 2, W // 2
+        ops.add_bcast_rows_(x, self.enc_pos[: H * W])
+        return x.view(B, H * W, -1)
+
+    # ---------------------------------------------------------------------------------------------- decoder
+    def setup_cache(self, batch: int):
+        """SuryaADETRDecoderModel._setup_cache (surya/common/adetr/decoder.py): fresh self / cross caches."""
+        d = self.cfg.decoder
+        self.cross_kv = [None] * d.num_hidden_layers
+        if batch != self._cache_batch:
+            shape = (batch, d.num_key_value_heads, self.s_max, d.head_dim)
+            self.kcache = [torch.zeros(shape, dtype=self.dtype, device=self.device) for _ in range(d.num_hidden_layers)]
+            self.vcache = [torch.zeros(shape, dtype=self.dtype, device=self.device) for _ in range(d.num_hidden_layers)]
+            self._cache_batch = batch
+        self._slot = torch.arange(batch, dtype=torch.int32, device=self.device)
+
+    def clear_cache(self):
+        self.cross_kv = [None] * self.cfg.decoder.num_hidden_layers
+
+    def decode_step(self, boxes: torch.Tensor, enc: torch.Tensor, position: int):
+        """One q_len = 1 decoder call (SuryaLayoutDecoder.forward, surya/layout/model/decoder.py:95-126).
+        boxes int64 [B, 7]; enc [B, L, Henc]; position = cache position of this token.  Returns (bbox sigmoid [B,6] fp32,
+        class logits [B, label_count] fp32 holding the dtype-rounded values)."""
+        d = self.cfg.decoder
+        nh, nkv, hd, H = d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.hidden_size
+        B, Lk = enc.shape[0], enc.shape[1]
+        if position >= self.s_max:
+            raise _lib.SuryaB200Error("decoder position exceeds the allocated self-attention cache")
+        scale = hd ** -0.5
+        x = ops.bbox_embed_sum(boxes, self.tables, H, d.bbox_size, self.dtype)
+        pos = torch.full((B,), position, dtype=torch.int32, device=self.device)
+        enc2d = enc.reshape(B * Lk, -1)
+        for l, L in enumerate(self.layers):
+            raw = x
+            n = ops.rmsnorm_adetr(x, L["cross_norm"], d.rms_norm_eps)
+            q = ops.gemm(n, L["cq_w"])
+            if self.cross_kv[l] is None:      # K/V of the encoder states, computed at the first call and cached
+                self.cross_kv[l] = ops.gemm(enc2d, L["ckv_w"])
+            a = ops.attn_single_query(q, self.cross_kv[l], Lk, nh, nkv, hd, scale)
+            cross = ops.gemm(a, L["co_w"], bias=L["co_b"], residual=raw)
+            n = ops.rmsnorm_adetr(cross, L["self_norm"], d.rms_norm_eps)
+            qkv = ops.gemm(n, L["sqkv_w"])
+            a = ops.decode_attn(qkv, self.kcache[l], self.vcache[l], self._slot, pos, self.inv_freq, nh, nkv, hd, scale)
+            res = ops.gemm(a, L["so_w"], bias=L["so_b"], residual=raw if d.double_residual_flow else cross)
+            n = ops.rmsnorm_adetr(res, L["mlp_norm"], d.rms_norm_eps)
+            m = ops.gemm(n, L["gu_w"], act="gelu_tanh", swiglu=True)
+            x = ops.gemm(m, L["down_w"], residual=res)
+        x = ops.rmsnorm_adetr(x, self.final_norm, d.rms_norm_eps)
+        h = ops.layernorm(x, *self.out_ln, eps=d.layer_norm_eps)
+        bbox, _ = ops.small_head(h, self.bbox_w, self.bbox_b, sigmoid=True)
+        cls, _ = ops.small_head(h, self.cls_w, None, sigmoid=False)
+        return bbox, cls
+
+
+class _Ns:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class B200LayoutModel:
+    """Attribute-compatible with what LayoutPredictor uses on `self.model` (surya/layout/__init__.py:83-123, 154-157, 222)."""
+
+    def __init__(self, engine: LayoutEngine):
+        self.engine = engine
+        self.device, self.dtype = engine.device, engine.dtype
+        d = engine.cfg.decoder
+        dec_cfg = _Ns(**engine.cfg.decoder.__dict__)
+        self.config = _Ns(decoder=dec_cfg, encoder=_Ns(**engine.cfg.encoder.__dict__))
+        outer = self
+
+        class _Inner:
+            def _setup_cache(self, config, batch, device, dtype):
+                outer.engine.setup_cache(batch)
+
+            def _clear_cache(self):
+                outer.engine.clear_cache()
+
+        class _Decoder:
+            config = dec_cfg
+            model = _Inner()
+
+            def __call__(self, input_boxes=None, encoder_hidden_states=None, cache_position=None, use_cache=True, prefill=False, **kw):
+                if input_boxes.shape[1] != 1:
+                    raise NotImplementedError("pause tokens (q_len > 1) are not used by the shipped config (pause_token_count = 0)")
+                if prefill:
+                    outer.engine.setup_cache(input_boxes.shape[0])
+                bbox, cls = outer.engine.decode_step(input_boxes[:, 0].to(torch.int64), encoder_hidden_states,
+                                                     int(cache_position[-1]))
+                return {"bbox_logits": bbox.to(outer.dtype).unsqueeze(1), "class_logits": cls.to(outer.dtype).unsqueeze(1)}
+
+        self.decoder = _Decoder()
+
+    def encoder(self, pixel_values=None, **kw):
+        return (self.engine.encode(pixel_values),)
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+
+def layout_greedy(engine: LayoutEngine, pixel_values: torch.Tensor, steps: int):
+    """Device part of LayoutPredictor.batch_layout_detection (surya/layout/__init__.py:106-137, 183): encoder once, then
+    `steps` greedy decoder calls; next input = [trunc(bbox * bbox_size) x 6, argmax class].  Returns tokens [B, steps, 7],
+    bbox [B, steps, 6] and class logits [B, steps, label_count] (fp32 tensors on the device)."""
+    d = engine.cfg.decoder
+    enc = engine.encode(pixel_values)
+    B = enc.shape[0]
+    engine.setup_cache(B)
+    boxes = torch.full((B, 7), d.bos_token_id, dtype=torch.int64, device=engine.device)
+    toks, bbs, cls_all = [], [], []
+    for s in range(steps):
+        bbox, cls = engine.decode_step(boxes, enc, s)
+        pred = cls.argmax(-1)
+        boxes = torch.cat([(bbox * d.bbox_size).to(torch.int64), pred.unsqueeze(1)], dim=1)
+        toks.append(boxes.clone())
+        bbs.append(bbox)
+        cls_all.append(cls)
+    return torch.stack(toks, 1), torch.stack(bbs, 1), torch.stack(cls_all, 1), enc

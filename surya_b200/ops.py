@@ -197,3 +197,83 @@ def lite_mla(qkv_a, qkv_b, B, HW, heads, dim, eps):
     check(lib.sb_lite_mla(dt_code(qkv_a.dtype), ptr(qkv_a), ptr(qkv_b), ptr(out), c_int(B), c_int(HW), c_int(heads), c_int(dim),
                           ctypes.c_float(eps), stream_ptr()), "sb_lite_mla")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ layout / table_rec ops
+def rmsnorm_adetr(x, w, eps=1e-6):
+    lib = _lib.load()
+    out = torch.empty_like(x)
+    check(lib.sb_rmsnorm_adetr(dt_code(x.dtype), ptr(x), c_int(_rowmajor(x)), ptr(w), ptr(out), c_int(_rowmajor(out)),
+                               c_int(x.shape[0]), c_int(x.shape[1]), c_float(eps), stream_ptr()), "sb_rmsnorm_adetr")
+    return out
+
+
+def layernorm(x, w, b, eps=1e-5):
+    lib = _lib.load()
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    check(lib.sb_layernorm(dt_code(x.dtype), ptr(x), ptr(w), ptr(b), ptr(out), c_int(x.shape[0]), c_int(x.shape[1]),
+                           c_float(eps), stream_ptr()), "sb_layernorm")
+    return out
+
+
+def patch_gather(pixels, P, Kp, dtype):
+    lib = _lib.load()
+    B, C, H, W = pixels.shape
+    pixels = pixels.contiguous()
+    out = torch.empty((B * (H // P) * (W // P), Kp), device=pixels.device, dtype=dtype)
+    check(lib.sb_patch_gather(dt_code(dtype), ptr(pixels), c_int(1 if pixels.dtype == torch.float32 else 0), ptr(out), c_int(B),
+                              c_int(C), c_int(H), c_int(W), c_int(P), c_int(Kp), stream_ptr()), "sb_patch_gather")
+    return out
+
+
+def add_bcast_rows_(x, tab):
+    lib = _lib.load()
+    check(lib.sb_add_bcast_rows(dt_code(x.dtype), ptr(x), ptr(tab), ctypes.c_longlong(x.shape[0]), c_int(tab.shape[0]),
+                                c_int(x.shape[1]), stream_ptr()), "sb_add_bcast_rows")
+    return x
+
+
+def patch_merge_gather(x, B, H, W):
+    lib = _lib.load()
+    C = x.shape[1]
+    out = torch.empty((B * (H // 2) * (W // 2), 4 * C), device=x.device, dtype=x.dtype)
+    check(lib.sb_patch_merge_gather(dt_code(x.dtype), ptr(x), ptr(out), c_int(B), c_int(H), c_int(W), c_int(C), stream_ptr()),
+          "sb_patch_merge_gather")
+    return out
+
+
+def swin_window_attn(qkv, bias_table, B, H, W, nh, shift):
+    lib = _lib.load()
+    C = qkv.shape[1] // 3
+    out = torch.empty((qkv.shape[0], C), device=qkv.device, dtype=qkv.dtype)
+    check(lib.sb_swin_window_attn(dt_code(qkv.dtype), ptr(qkv), ptr(bias_table), ptr(out), c_int(B), c_int(H), c_int(W), c_int(C),
+                                  c_int(nh), c_int(shift), stream_ptr()), "sb_swin_window_attn")
+    return out
+
+
+def bbox_embed_sum(boxes, tables, hidden, bbox_size, dtype):
+    """boxes int64 [n, 7]; tables: list of 15 device tensors (w,h,cx,cy,xskew,yskew,x1,y1,x2,y2,x3,y3,x4,y4,label)."""
+    lib = _lib.load()
+    n = boxes.shape[0]
+    out = torch.empty((n, hidden), device=boxes.device, dtype=dtype)
+    arr = (_lib.c_void_p * 15)(*[t.data_ptr() for t in tables])
+    check(lib.sb_bbox_embed_sum(dt_code(dtype), ptr(boxes.contiguous()), arr, ptr(out), c_int(n), c_int(hidden), c_int(bbox_size),
+                                stream_ptr()), "sb_bbox_embed_sum")
+    return out
+
+
+def attn_single_query(q, kv, n_keys, nh, nkv, hd, scale):
+    """q [B, nh*hd]; kv [B*n_keys, 2*nkv*hd] = per token (K heads | V heads), i.e. the fused cross K/V projection output."""
+    lib = _lib.load()
+    B = q.shape[0]
+    out = torch.empty_like(q)
+    row = 2 * nkv * hd
+    esz = kv.element_size()
+    kptr = kv.data_ptr()
+    vptr = kptr + nkv * hd * esz
+    check(lib.sb_attn_single_query(dt_code(q.dtype), ptr(q), c_int(_rowmajor(q)), _lib.c_void_p(kptr), _lib.c_void_p(vptr),
+                                   ctypes.c_longlong(n_keys * row), ctypes.c_longlong(hd), ctypes.c_longlong(row), ptr(out),
+                                   c_int(_rowmajor(out)), c_int(B), c_int(nh), c_int(nkv), c_int(hd), c_int(n_keys), c_float(scale),
+                                   stream_ptr()), "sb_attn_single_query")
+    return out

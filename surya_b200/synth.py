@@ -164,3 +164,87 @@ def det_normalize(pages) -> torch.Tensor:
     std = np.array((0.229, 0.224, 0.225), dtype=np.float32)
     x = (pages.astype(np.float32) * (1 / 255.0) - mean) / std
     return torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2)))
+
+
+# ------------------------------------------------------------------------------------------------ layout (Swin + ADETR)
+def _ln(name, n, seed):
+    g = _gen(name, seed)
+    return {f"{name}.weight": 1.0 + 0.1 * torch.randn(n, generator=g), f"{name}.bias": 0.05 * torch.randn(n, generator=g)}
+
+
+def swin_state_dict(cfg, seed: int = 0, prefix: str = "") -> Dict[str, torch.Tensor]:
+    """fp32 state dict for DonutSwinLayoutModel / DonutSwinModel (names: SURVEY.md §9.8)."""
+    sd: Dict[str, torch.Tensor] = {}
+    p = prefix
+    C0 = cfg.embed_dim
+    sd[p + "embeddings.patch_embeddings.projection.weight"] = _normal(p + "pe.w", (C0, cfg.num_channels, cfg.patch_size, cfg.patch_size), (cfg.num_channels * cfg.patch_size ** 2) ** -0.5, seed)
+    sd[p + "embeddings.patch_embeddings.projection.bias"] = _normal(p + "pe.b", (C0,), 0.05, seed)
+    sd.update(_ln(p + "embeddings.norm", C0, seed))
+    ws = cfg.window_size
+    for s, (depth, nh) in enumerate(zip(cfg.depths, cfg.num_heads)):
+        C = C0 * 2 ** s
+        for b in range(depth):
+            q = f"{p}encoder.layers.{s}.blocks.{b}."
+            sd.update(_ln(q + "layernorm_before", C, seed))
+            sd.update(_ln(q + "layernorm_after", C, seed))
+            sd[q + "attention.self.relative_position_bias_table"] = _normal(q + "rpb", ((2 * ws - 1) ** 2, nh), 0.5, seed)
+            for nm in ("query", "key", "value"):
+                sd[q + f"attention.self.{nm}.weight"] = _normal(q + nm + ".w", (C, C), C ** -0.5, seed)
+                sd[q + f"attention.self.{nm}.bias"] = _normal(q + nm + ".b", (C,), 0.05, seed)
+            sd[q + "attention.output.dense.weight"] = _normal(q + "ao.w", (C, C), 0.5 * C ** -0.5, seed)
+            sd[q + "attention.output.dense.bias"] = _normal(q + "ao.b", (C,), 0.02, seed)
+            I = int(cfg.mlp_ratio * C)
+            sd[q + "intermediate.dense.weight"] = _normal(q + "fc1.w", (I, C), C ** -0.5, seed)
+            sd[q + "intermediate.dense.bias"] = _normal(q + "fc1.b", (I,), 0.05, seed)
+            sd[q + "output.dense.weight"] = _normal(q + "fc2.w", (C, I), 0.5 * I ** -0.5, seed)
+            sd[q + "output.dense.bias"] = _normal(q + "fc2.b", (C,), 0.02, seed)
+        if s < len(cfg.depths) - 1:
+            q = f"{p}encoder.layers.{s}.downsample."
+            sd[q + "reduction.weight"] = _normal(q + "red.w", (2 * C, 4 * C), (4 * C) ** -0.5, seed)
+            sd.update(_ln(q + "norm", 4 * C, seed))
+    sd[p + "position_embeddings"] = _normal(p + "pos", (1, cfg.encoder_length, cfg.hidden_size), 0.1, seed)
+    return sd
+
+
+LAYOUT_EMBED_TABLES = ("w", "h", "cx", "cy", "xskew", "yskew", "x1", "y1", "x2", "y2", "x3", "y3", "x4", "y4")
+
+
+def adetr_layout_state_dict(cfg, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """fp32 state dict for SuryaLayoutDecoder (surya/layout/model/decoder.py + surya/common/adetr/decoder.py)."""
+    sd: Dict[str, torch.Tensor] = {}
+    H, I = cfg.hidden_size, cfg.intermediate_size
+    nh, nkv, hd = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+    for t in LAYOUT_EMBED_TABLES:
+        sd[f"model.embed_tokens.{t}_embed.weight"] = _normal(f"emb.{t}", (cfg.vocab_size, H), 0.25, seed)
+    sd["model.embed_tokens.label_embed.weight"] = _normal("emb.label", (cfg.label_count, H), 0.25, seed)
+    for l in range(cfg.num_hidden_layers):
+        q = f"model.layers.{l}."
+        for nm in ("cross_pre_norm", "temporal_pre_norm", "channel_pre_norm"):
+            sd[q + nm + ".weight"] = 0.1 * torch.randn(H, generator=_gen(q + nm, seed))
+        for blk, kin in (("temporal_block", H), ("cross_attn_block", cfg.encoder_hidden_size)):
+            sd[q + f"{blk}.q_proj.weight"] = _normal(q + blk + ".q", (nh * hd, H), H ** -0.5, seed)
+            sd[q + f"{blk}.k_proj.weight"] = _normal(q + blk + ".k", (nkv * hd, kin), kin ** -0.5, seed)
+            sd[q + f"{blk}.v_proj.weight"] = _normal(q + blk + ".v", (nkv * hd, kin), kin ** -0.5, seed)
+            sd[q + f"{blk}.o_proj.weight"] = _normal(q + blk + ".o", (H, nh * hd), 0.5 * H ** -0.5, seed)
+            sd[q + f"{blk}.o_proj.bias"] = _normal(q + blk + ".ob", (H,), 0.02, seed)
+        sd[q + "mlp_block.gate_proj.weight"] = _normal(q + "gate", (I, H), H ** -0.5, seed)
+        sd[q + "mlp_block.up_proj.weight"] = _normal(q + "up", (I, H), H ** -0.5, seed)
+        sd[q + "mlp_block.down_proj.weight"] = _normal(q + "down", (H, I), 0.5 * I ** -0.5, seed)
+    sd["model.final_norm.weight"] = 0.1 * torch.randn(H, generator=_gen("final_norm", seed))
+    sd["lm_head.weight"] = _normal("lm_head", (cfg.label_count, H), H ** -0.5, seed)
+    sd["bbox_head.weight"] = _normal("bbox_head.w", (6, H), H ** -0.5, seed)
+    sd["bbox_head.bias"] = _normal("bbox_head.b", (6,), 0.1, seed)
+    sd.update(_ln("pre_output_norm", H, seed))
+    return sd
+
+
+def layout_synthetic_pages(n: int, size=(768, 768), seed: int = 1234) -> torch.Tensor:
+    """BASELINE config 4 input: uint8 noise pages through the Donut processor's rescale + normalise
+    (surya/common/donut/processor.py:61-116: resize is a no-op at the native size); NCHW fp32."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    x = rng.integers(0, 256, size=(n, size[0], size[1], 3), dtype=np.uint8).astype(np.float32) * (1 / 255.0)
+    mean = np.array((0.485, 0.456, 0.406), dtype=np.float32)
+    std = np.array((0.229, 0.224, 0.225), dtype=np.float32)
+    return torch.from_numpy(np.ascontiguousarray(((x - mean) / std).transpose(0, 3, 1, 2)))

@@ -222,3 +222,31 @@ def test_det_program_structure():
     n = f"{c.name}.norm"
     ref = F.batch_norm(F.conv2d(x, sd[c.wkey]), sd[f"{n}.running_mean"], sd[f"{n}.running_var"], sd[f"{n}.weight"], sd[f"{n}.bias"], False, 0.0, c.eps)
     assert torch.allclose(F.conv2d(x, w, b), ref, atol=1e-4)
+
+
+def test_layout_oracle_pinned_to_reference_golden():
+    """oracle/layout_oracle.py (fp32) reproduces the reference Swin encoder + ADETR decoder bit-for-bit on the seeded case."""
+    from oracle import layout_oracle as L
+    from surya_b200.config import layout_tiny
+    from surya_b200.synth import adetr_layout_state_dict, layout_synthetic_pages, swin_state_dict
+
+    g = torch.load(GOLDEN / "layout_tiny.pt")
+    cfg = layout_tiny()
+    sde, sdd = swin_state_dict(cfg.encoder, 0), adetr_layout_state_dict(cfg.decoder, 0)
+    x = layout_synthetic_pages(2, cfg.encoder.image_size, seed=g["meta"]["page_seed"])
+    assert abs(x.double().sum().item() - g["input_checksum"].item()) < 1e-3
+    tok, enc, bl, cl = L.layout_greedy(sde, sdd, cfg, x, g["meta"]["steps"], return_logits=True)
+    assert (enc - g["encoder"]).abs().max().item() < 1e-5
+    assert (bl - g["bbox"]).abs().max().item() < 1e-5
+    assert (cl - g["class_logits"]).abs().max().item() < 1e-4
+    assert torch.equal(tok, g["tokens"])
+
+
+def test_layout_weight_packing():
+    from surya_b200.config import layout_tiny
+    from surya_b200.layout import _sincos_table
+    from oracle.layout_oracle import sincos_2d
+
+    assert torch.equal(_sincos_table(16, 12, 256), sincos_2d(16, 12, 256)[0])
+    cfg = layout_tiny()
+    assert cfg.encoder.hidden_size == 1024 and cfg.encoder.grid == (64, 64)
