@@ -254,6 +254,15 @@ int sb_bbox_embed_sum(int dtype, const long long* boxes, const void* const* tabl
 int sb_attn_single_query(int dtype, const void* q, int ldq, const void* K, const void* V, long long batch_stride,
                          long long head_stride, long long token_stride, void* out, int ldo, int B, int nh, int nkv, int head_dim,
                          int n_keys, float scale, void* stream);
+/* LabelEmbedding (table_rec/model/decoder.py:46-73): boxes int64 [n,10]; tables = 13 device pointers (w,h,cx,cy,xskew,yskew,
+ * x1,y1,x3,y3 of width box_w; category, merge, colspan of width prop_w); out [n, box_w + prop_w]. */
+int sb_label_embed(int dtype, const long long* boxes, const void* const* tables, void* out, int n, int box_w, int prop_w,
+                   int bbox_size, int vocab, void* stream);
+/* Per-step token formation of LayoutPredictor / TableRecPredictor (layout/__init__.py:125-137; table_rec/__init__.py:76-97 +
+ * shaper.py:12-52): out int64 [B, 6 + n_heads] = trunc(clamp(bbox * bbox_size)) x6, then per head argmax (mode 0) or
+ * round(max(v, 1)) (mode 1, colspan); done[b] = head `done_head`'s token is eos or pad (may be NULL). */
+int sb_box_next_token(const float* bbox, const float* const* heads, const int* head_n, const int* head_mode, int n_heads,
+                      float bbox_size, long long* out, unsigned char* done, int done_head, int eos, int pad, int B, void* stream);
 
 #ifdef __cplusplus
 }

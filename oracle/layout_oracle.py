@@ -170,6 +170,25 @@ def bbox_embedding(sd: SD, cfg, boxes: torch.Tensor) -> torch.Tensor:
     return e("label", label) + size + skew + corner
 
 
+def label_embedding(sd: SD, cfg, boxes: torch.Tensor) -> torch.Tensor:
+    """LabelEmbedding.forward — table_rec/model/decoder.py:46-73 (columns: cx cy w h xskew yskew | category merges colspan
+    is_header, shaper.py:54-80; is_header is not embedded)."""
+    e = lambda n, i: sd[f"model.embed_tokens.{n}_embed.weight"][i]
+    boxes = boxes.to(torch.long).clamp(0, cfg.vocab_size)
+    cx, cy, w, h, xs, ys, cat, mrg, col, _hdr = boxes.unbind(dim=-1)
+    xa = ((xs - cfg.bbox_size // 2) / 2).to(torch.long)
+    ya = ((ys - cfg.bbox_size // 2) / 2).to(torch.long)
+    cl = lambda t: t.clamp(0, cfg.bbox_size).to(torch.long)
+    x1, y1 = cl(cx - w // 2 - xa), cl(cy - h // 2 - ya)
+    x3, y3 = cl(cx + w // 2 + xa), cl(cy + h // 2 + ya)
+    size = e("w", w) + e("h", h) + e("cx", cx) + e("cy", cy)
+    skew = e("xskew", xs) + e("yskew", ys)
+    corner = e("x1", x1) + e("y1", y1) + e("x3", x3) + e("y3", y3)
+    box = size + skew + corner
+    prop = e("category", cat) + e("merge", mrg) + e("colspan", col)
+    return torch.cat([box, prop], dim=-1)
+
+
 def _rot_half(x):
     h = x.shape[-1] // 2
     return torch.cat((-x[..., h:], x[..., :h]), -1)
@@ -190,7 +209,7 @@ def adetr_forward(sd: SD, cfg, boxes: torch.Tensor, enc: torch.Tensor, cache_pos
     for layout), cross attention :150-194, self attention :238-290 (dynamic cache), MLP :342-357, mask :620-637."""
     B, q, _ = boxes.shape
     nh, nkv, hd = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
-    x = bbox_embedding(sd, cfg, boxes)
+    x = label_embedding(sd, cfg, boxes) if cfg.kind == "table" else bbox_embedding(sd, cfg, boxes)
     dt = x.dtype
     pos = cache_position.unsqueeze(0)
     inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
@@ -233,6 +252,10 @@ def adetr_forward(sd: SD, cfg, boxes: torch.Tensor, enc: torch.Tensor, cache_pos
         x = F.linear(m, sd[p + "mlp_block.down_proj.weight"]) + res
     x = adetr_rmsnorm(x, sd["model.final_norm.weight"], cfg.rms_norm_eps)
     h = F.layer_norm(x, (x.shape[-1],), sd["pre_output_norm.weight"], sd["pre_output_norm.bias"], cfg.layer_norm_eps)
+    if cfg.kind == "table":      # SuryaTableRecDecoder.forward — table_rec/model/decoder.py:121-155
+        out = {k: F.linear(h, sd[f"box_property_heads.{k}.weight"]) for k in ("bbox", "category", "merges", "colspan", "is_header")}
+        out["bbox"] = torch.sigmoid(out["bbox"])
+        return out
     return torch.sigmoid(F.linear(h, sd["bbox_head.weight"], sd["bbox_head.bias"])), F.linear(h, sd["lm_head.weight"])
 
 
@@ -262,3 +285,39 @@ def layout_greedy(sd_enc: SD, sd_dec: SD, cfg, pixel_values: torch.Tensor, steps
     if return_logits:
         out = out + (torch.stack(bl, 1), torch.stack(cl, 1))
     return out
+
+
+def table_next_tokens(out: dict, cfg):
+    """TableRecPredictor.inference_loop's per-step processing (table_rec/__init__.py:76-121) + LabelShaper.dict_to_labels
+    (shaper.py:12-52) + torch.tensor(..., dtype=long): -> tokens [B, 10] int64, done [B] bool."""
+    last = {k: v[:, -1, :] for k, v in out.items()}
+    cat = last["category"].argmax(-1)
+    done = (cat == cfg.eos_token_id) | (cat == cfg.pad_token_id)
+    bbox = (last["bbox"] * cfg.bbox_size).float().clamp(0, cfg.bbox_size)
+    colspan = torch.round(torch.clamp(last["colspan"], min=1))[:, 0]
+    tok = torch.cat([bbox.to(torch.long), cat[:, None], last["merges"].argmax(-1)[:, None], colspan.to(torch.long)[:, None],
+                     last["is_header"].argmax(-1)[:, None]], dim=1)
+    return tok, done
+
+
+def table_greedy(sd_enc: SD, sd_dec: SD, cfg, pixel_values: torch.Tensor, prompt: torch.Tensor, steps: int):
+    """Encoder + row/column decoding pass of TableRecPredictor (table_rec/__init__.py:33-131, 180-190): multi-token prompt
+    prefill, then `steps` greedy box tokens.  Returns tokens [B, steps, 10], done [B, steps], encoder states, and the per-step
+    head outputs (dict of [B, steps, n])."""
+    d = cfg.decoder
+    with torch.inference_mode():
+        enc = swin_forward(sd_enc, cfg.encoder, pixel_values)
+        ids = prompt.clone()
+        cache_position = torch.arange(ids.shape[1])
+        st = AdetrState(d.num_hidden_layers)
+        toks, dones, outs = [], [], []
+        for _ in range(steps):
+            out = adetr_forward(sd_dec, d, ids, enc, cache_position, st)
+            cache_position = cache_position[-1:] + 1
+            tok, done = table_next_tokens(out, d)
+            ids = tok.unsqueeze(1)
+            toks.append(tok)
+            dones.append(done)
+            outs.append({k: v[:, -1].float().clone() for k, v in out.items()})
+    heads = {k: torch.stack([o[k] for o in outs], 1) for k in outs[0]}
+    return torch.stack(toks, 1), torch.stack(dones, 1), enc, heads

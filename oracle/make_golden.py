@@ -120,6 +120,41 @@ def make_layout_golden():
     print(f"[golden] layout_tiny: tokens[0,:2]={g['tokens'][0, :2].tolist()} min class margin={(top2[..., 0] - top2[..., 1]).min():.4f}")
 
 
+def make_table_golden():
+    """Reference table_rec encoder + decoder driven like TableRecPredictor.inference_loop (table_rec/__init__.py:33-131):
+    3-token query prompt prefill, then greedy steps with the predictor's own token formation."""
+    from oracle import layout_oracle as L
+    from surya_b200.config import table_tiny
+    from surya_b200.synth import adetr_table_state_dict, layout_synthetic_pages, swin_state_dict, table_query_tokens
+
+    cfg = table_tiny()
+    e, d = cfg.encoder, cfg.decoder
+    sde, sdd = swin_state_dict(e, 1), adetr_table_state_dict(d, 1)
+    enc, dec = ref_shim.build_reference_table_models(cfg, sde, sdd)
+    x = layout_synthetic_pages(2, e.image_size, seed=9)
+    ids = table_query_tokens(d, 2)
+    steps = 8
+    with torch.inference_mode():
+        ref_enc = enc(pixel_values=x).last_hidden_state
+        dec.model._setup_cache(dec.config, 2, "cpu", torch.float32)
+        pos = torch.ones_like(ids[0, :, 0], dtype=torch.int64).cumsum(0) - 1
+        toks, heads = [], []
+        for s in range(steps):
+            out = dec(input_ids=ids, encoder_hidden_states=ref_enc, cache_position=pos, use_cache=True, prefill=(s == 0))
+            pos = pos[-1:] + 1
+            logits = out["box_property_logits"]
+            tok, done = L.table_next_tokens(logits, d)
+            ids = tok.unsqueeze(1)
+            toks.append(tok)
+            heads.append({k: v[:, -1].float().clone() for k, v in logits.items()})
+    g = {"encoder": ref_enc.float().clone(), "tokens": torch.stack(toks, 1),
+         "heads": {k: torch.stack([h[k] for h in heads], 1) for k in heads[0]}, "input_checksum": x.double().sum(),
+         "meta": {"kind": "table_tiny", "steps": steps, "seed": 1, "page_seed": 9, "torch": str(torch.__version__),
+                  "reference": "VikParuchuri/surya@80e9a7e (v0.14.6), fp32 CPU, eager attention"}}
+    torch.save(g, GOLDEN / "table_tiny.pt")
+    print(f"[golden] table_tiny: tokens[0,:2]={g['tokens'][0, :2].tolist()}")
+
+
 def make_det_golden():
     """Reference EfficientViT segmentation logits for one seeded 512x512 page (surya/detection/__init__.py:94-104)."""
     from surya_b200.config import det_default
@@ -142,9 +177,11 @@ def make_det_golden():
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
-    which = set(sys.argv[1:]) or {"rec", "det", "layout"}
+    which = set(sys.argv[1:]) or {"rec", "det", "layout", "table"}
     if "layout" in which:
         make_layout_golden()
+    if "table" in which:
+        make_table_golden()
     if "det" in which:
         make_det_golden()
     if "rec" not in which:

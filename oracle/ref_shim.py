@@ -110,6 +110,29 @@ def build_reference_layout_models(cfg, sd_enc, sd_dec):
     return enc, dec
 
 
+def build_reference_table_models(cfg, sd_enc, sd_dec):
+    """Reference DonutSwinModel + SuryaTableRecDecoder (surya/table_rec/model/{encoder,decoder}.py) with synthetic weights."""
+    install()
+    from surya.common.adetr.decoder import SuryaADETRDecoderPreTrainedModel
+    from surya.common.donut.encoder import DonutSwinPreTrainedModel
+    from surya.table_rec.model.config import DonutSwinTableRecConfig, SuryaTableRecDecoderConfig
+    from surya.table_rec.model.decoder import SuryaTableRecDecoder
+    from surya.table_rec.model.encoder import DonutSwinModel
+
+    SuryaADETRDecoderPreTrainedModel.tie_weights = lambda self, **k: None
+    SuryaADETRDecoderPreTrainedModel._tie_weights = lambda self, **k: None
+    DonutSwinPreTrainedModel.get_head_mask = lambda self, head_mask, n, *a, **k: [None] * n
+    e, d = cfg.encoder, cfg.decoder
+    enc = DonutSwinModel(DonutSwinTableRecConfig(image_size=e.image_size, depths=list(e.depths),
+                                                 encoder_length=e.encoder_length)).eval()
+    miss, unexp = enc.load_state_dict(sd_enc, strict=False)
+    assert not [m for m in miss if "relative_position_index" not in m] and not unexp, (miss, unexp)
+    dec = SuryaTableRecDecoder(SuryaTableRecDecoderConfig(num_hidden_layers=d.num_hidden_layers)).eval()
+    miss, unexp = dec.load_state_dict(sd_dec, strict=False)
+    assert not miss and not unexp, (miss, unexp)
+    return enc, dec
+
+
 def build_reference_det_model(cfg, state_dict):
     """Reference EfficientViTForSemanticSegmentation (surya/detection/model/encoderdecoder.py) with the synthetic weights."""
     install()

@@ -177,6 +177,19 @@ class AdetrConfig:
     pause_token_count: int = 0
     double_residual_flow: bool = True
     max_boxes: int = 100
+    # table_rec variant (SuryaTableRecDecoderConfig, surya/table_rec/model/config.py:142-226): LabelEmbedding widths, property
+    # head sizes (classification counts include the 5 special tokens), 10-column tokens
+    kind: str = "layout"
+    box_embed_size: int = 0
+    property_embed_size: int = 0
+    category_count: int = 0
+    merge_count: int = 0
+    header_count: int = 0
+    query_end_token_id: int = 4
+
+    @property
+    def token_width(self) -> int:
+        return 7 if self.kind == "layout" else 10
 
     @property
     def head_dim(self) -> int:
@@ -194,6 +207,21 @@ class LayoutConfig:
 
 def layout_default() -> LayoutConfig:
     return LayoutConfig()
+
+
+def table_decoder(num_hidden_layers: int = 6) -> AdetrConfig:
+    return AdetrConfig(num_hidden_layers=num_hidden_layers, hidden_size=512, intermediate_size=2048, num_attention_heads=8,
+                       num_key_value_heads=4, special_token_count=5, double_residual_flow=False, max_boxes=150, kind="table",
+                       box_embed_size=448, property_embed_size=64, category_count=10, merge_count=9, header_count=7, label_count=0)
+
+
+def table_default() -> LayoutConfig:
+    """DonutSwinTableRecConfig + SuryaTableRecDecoderConfig defaults (surya/table_rec/model/config.py:89-226)."""
+    return LayoutConfig(encoder=SwinConfig(depths=(2, 2, 12, 2), encoder_length=1024), decoder=table_decoder())
+
+
+def table_tiny() -> LayoutConfig:
+    return LayoutConfig(encoder=SwinConfig(image_size=(256, 256), depths=(2, 2, 2, 2), encoder_length=64), decoder=table_decoder(2))
 
 
 def layout_tiny() -> LayoutConfig:

@@ -124,5 +124,14 @@ int sb_attn_single_query(int dtype, const void* q, int ldq, const void* K, const
   return attn_single_query(dtype, q, ldq, K, V, batch_stride, head_stride, token_stride, out, ldo, B, nh, nkv, head_dim, n_keys,
                            scale, static_cast<cudaStream_t>(stream));
 }
+int sb_label_embed(int dtype, const long long* boxes, const void* const* tables, void* out, int n, int box_w, int prop_w,
+                   int bbox_size, int vocab, void* stream) {
+  return label_embed(dtype, boxes, tables, out, n, box_w, prop_w, bbox_size, vocab, static_cast<cudaStream_t>(stream));
+}
+int sb_box_next_token(const float* bbox, const float* const* heads, const int* head_n, const int* head_mode, int n_heads,
+                      float bbox_size, long long* out, unsigned char* done, int done_head, int eos, int pad, int B, void* stream) {
+  return box_next_token(bbox, heads, head_n, head_mode, n_heads, bbox_size, out, done, done_head, eos, pad, B,
+                        static_cast<cudaStream_t>(stream));
+}
 
 }  // extern "C"

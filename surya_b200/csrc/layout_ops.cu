@@ -508,4 +508,97 @@ int attn_single_query(int dtype, const void* q, int ldq, const void* K, const vo
   return rc;
 }
 
+// ------------------------------------------------------------------------------------------------ table_rec LabelEmbedding
+// LabelEmbedding.forward (table_rec/model/decoder.py:46-73): out[:, :box_w] = (size + skew) + corner with corner = x1+y1+x3+y3,
+// out[:, box_w:] = (category + merges) + colspan; every add rounds to T like the eager graph does.
+struct LabelTables { const void* t[13]; };   // w,h,cx,cy,xskew,yskew,x1,y1,x3,y3 (width box_w) | category,merge,colspan (width prop_w)
+
+template <typename T>
+__global__ void label_embed_kernel(const long long* __restrict__ boxes, LabelTables tabs, T* __restrict__ out, int n, int box_w,
+                                   int prop_w, int bbox_size, int vocab) {
+  const int r = blockIdx.x;
+  if (r >= n) return;
+  const long long* bx = boxes + static_cast<size_t>(r) * 10;
+  auto cv = [&](long long v) { return v < 0 ? 0LL : (v > vocab ? static_cast<long long>(vocab) : v); };
+  const long long cx = cv(bx[0]), cy = cv(bx[1]), w = cv(bx[2]), h = cv(bx[3]), xs = cv(bx[4]), ys = cv(bx[5]);
+  const long long cat = cv(bx[6]), mrg = cv(bx[7]), col = cv(bx[8]);
+  auto trunc_div2 = [](long long v) { return static_cast<long long>(static_cast<double>(v) / 2.0); };
+  const long long xa = trunc_div2(xs - bbox_size / 2), ya = trunc_div2(ys - bbox_size / 2);
+  auto cl = [&](long long v) { return v < 0 ? 0LL : (v > bbox_size ? static_cast<long long>(bbox_size) : v); };
+  const long long hw = w / 2, hh = h / 2;
+  const long long idx[13] = {w, h, cx, cy, xs, ys, cl(cx - hw - xa), cl(cy - hh - ya), cl(cx + hw + xa), cl(cy + hh + ya),
+                             cat, mrg, col};
+  T* o = out + static_cast<size_t>(r) * (box_w + prop_w);
+  for (int c = threadIdx.x; c < box_w + prop_w; c += blockDim.x) {
+    float e;
+    if (c < box_w) {
+      auto f = [&](int i) { return to_f<T>(reinterpret_cast<const T*>(tabs.t[i])[static_cast<size_t>(idx[i]) * box_w + c]); };
+      const float size = rnd<T>(rnd<T>(rnd<T>(f(0) + f(1)) + f(2)) + f(3));
+      const float skew = rnd<T>(f(4) + f(5));
+      const float corner = rnd<T>(rnd<T>(rnd<T>(f(6) + f(7)) + f(8)) + f(9));
+      e = rnd<T>(rnd<T>(size + skew) + corner);
+    } else {
+      const int pc = c - box_w;
+      auto f = [&](int i) { return to_f<T>(reinterpret_cast<const T*>(tabs.t[i])[static_cast<size_t>(idx[i]) * prop_w + pc]); };
+      e = rnd<T>(rnd<T>(f(10) + f(11)) + f(12));
+    }
+    o[c] = from_f<T>(e);
+  }
+}
+
+int label_embed(int dtype, const long long* boxes, const void* const* tables, void* out, int n, int box_w, int prop_w,
+                int bbox_size, int vocab, cudaStream_t st) {
+  if (n <= 0) return 0;
+  LabelTables tb;
+  for (int i = 0; i < 13; ++i) tb.t[i] = tables[i];
+  if (dtype == DT_F16) label_embed_kernel<__half><<<n, 128, 0, st>>>(boxes, tb, (__half*)out, n, box_w, prop_w, bbox_size, vocab);
+  else label_embed_kernel<__nv_bfloat16><<<n, 128, 0, st>>>(boxes, tb, (__nv_bfloat16*)out, n, box_w, prop_w, bbox_size, vocab);
+  return launch_ok();
+}
+
+// ------------------------------------------------------------------------------------------------ next box token
+// The predictors' per-step token formation, on the device: columns 0..5 = trunc(clamp(bbox * bbox_size, 0, bbox_size))
+// (layout/__init__.py:125-137; table_rec/__init__.py:88-93 + shaper.dict_to_labels), then one column per head:
+// mode 0 = argmax (first maximum), mode 1 = round-half-even(max(v, 1)) (table colspan).  done[b] = token of head `done_head`
+// is eos or pad (table_rec/__init__.py:84-87).
+struct StepHeads { const float* p[4]; int n[4]; int mode[4]; };
+
+__global__ void box_next_token_kernel(const float* __restrict__ bbox, StepHeads hd, int n_heads, float bbox_size,
+                                      long long* __restrict__ out, unsigned char* __restrict__ done, int done_head, int eos,
+                                      int pad, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  long long* o = out + static_cast<size_t>(b) * (6 + n_heads);
+  for (int i = 0; i < 6; ++i) {
+    float v = bbox[b * 6 + i] * bbox_size;
+    v = fminf(fmaxf(v, 0.f), bbox_size);
+    o[i] = static_cast<long long>(v);
+  }
+  for (int k = 0; k < n_heads; ++k) {
+    const float* p = hd.p[k] + static_cast<size_t>(b) * hd.n[k];
+    long long tok;
+    if (hd.mode[k] == 1) {
+      tok = static_cast<long long>(rintf(fmaxf(p[0], 1.f)));
+    } else {
+      int best = 0;
+      float bv = p[0];
+      for (int j = 1; j < hd.n[k]; ++j)
+        if (p[j] > bv) { bv = p[j]; best = j; }
+      tok = best;
+    }
+    o[6 + k] = tok;
+    if (done && k == done_head) done[b] = (tok == eos || tok == pad) ? 1 : 0;
+  }
+}
+
+int box_next_token(const float* bbox, const float* const* heads, const int* head_n, const int* head_mode, int n_heads,
+                   float bbox_size, long long* out, unsigned char* done, int done_head, int eos, int pad, int B, cudaStream_t st) {
+  if (B <= 0) return 0;
+  if (n_heads < 0 || n_heads > 4) { set_error("box_next_token: at most 4 heads"); return -1; }
+  StepHeads h{};
+  for (int i = 0; i < n_heads; ++i) { h.p[i] = heads[i]; h.n[i] = head_n[i]; h.mode[i] = head_mode[i]; }
+  box_next_token_kernel<<<(B + 63) / 64, 64, 0, st>>>(bbox, h, n_heads, bbox_size, out, done, done_head, eos, pad, B);
+  return launch_ok();
+}
+
 }  // namespace sb

@@ -76,6 +76,10 @@ int bbox_embed_sum(int dtype, const long long* boxes, const void* const* tables,
                    cudaStream_t st);
 int attn_single_query(int dtype, const void* q, int ldq, const void* K, const void* V, long long bs, long long hs, long long ts,
                       void* out, int ldo, int B, int nh, int nkv, int head_dim, int n_keys, float scale, cudaStream_t st);
+int label_embed(int dtype, const long long* boxes, const void* const* tables, void* out, int n, int box_w, int prop_w,
+                int bbox_size, int vocab, cudaStream_t st);
+int box_next_token(const float* bbox, const float* const* heads, const int* head_n, const int* head_mode, int n_heads,
+                   float bbox_size, long long* out, unsigned char* done, int done_head, int eos, int pad, int B, cudaStream_t st);
 
 // Single-token decode attention over the slot KV cache, fused with RoPE(q,k) and the in-place cache append.
 //   qkv[b] = [q(nh*d) | k(nkv*d) | v(nkv*d)] for batch row b; slot[b], pos[b] (= number of cached tokens) on device.

@@ -20,7 +20,7 @@ import torch
 
 from . import _lib, ops
 from .config import LayoutConfig
-from .synth import LAYOUT_EMBED_TABLES
+from .synth import LAYOUT_EMBED_TABLES, TABLE_HEADS
 
 
 def _sincos_table(width: int, height: int, dim: int) -> torch.Tensor:
@@ -83,7 +83,11 @@ class LayoutEngine:
 
         # ---- ADETR decoder
         nh, nkv, hd, H = d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.hidden_size
-        order = list(LAYOUT_EMBED_TABLES) + ["label"]
+        self.kind = d.kind
+        if d.kind == "table":
+            order = ["w", "h", "cx", "cy", "xskew", "yskew", "x1", "y1", "x3", "y3", "category", "merge", "colspan"]
+        else:
+            order = list(LAYOUT_EMBED_TABLES) + ["label"]
         self.tables = [T(sd_dec[f"model.embed_tokens.{t}_embed.weight"]) for t in order]
         self.layers = []
         for l in range(d.num_hidden_layers):
@@ -103,10 +107,13 @@ class LayoutEngine:
             })
         self.final_norm = T(sd_dec["model.final_norm.weight"])
         self.out_ln = (T(sd_dec["pre_output_norm.weight"]), T(sd_dec["pre_output_norm.bias"]))
-        self.cls_w = T(sd_dec["lm_head.weight"])
-        self.bbox_w, self.bbox_b = T(sd_dec["bbox_head.weight"]), T(sd_dec["bbox_head.bias"])
+        if d.kind == "table":
+            self.head_w = {k: T(sd_dec[f"box_property_heads.{k}.weight"]) for k in TABLE_HEADS}
+        else:
+            self.cls_w = T(sd_dec["lm_head.weight"])
+            self.bbox_w, self.bbox_b = T(sd_dec["bbox_head.weight"]), T(sd_dec["bbox_head.bias"])
         self.inv_freq = (1.0 / (d.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).to(dev)
-        self.s_max = d.max_boxes + 8
+        self.s_max = d.max_boxes + (72 if d.kind == "table" else 8)     # table prompts carry the query + column boxes
         self._cache_batch = 0
         self.cross_kv: List[Optional[torch.Tensor]] = [None] * d.num_hidden_layers
         self.kcache: List[torch.Tensor] = []
@@ -172,7 +179,10 @@ class LayoutEngine:
         if position >= self.s_max:
             raise _lib.SuryaB200Error("decoder position exceeds the allocated self-attention cache")
         scale = hd ** -0.5
-        x = ops.bbox_embed_sum(boxes, self.tables, H, d.bbox_size, self.dtype)
+        if self.kind == "table":
+            x = ops.label_embed(boxes, self.tables, d.box_embed_size, d.property_embed_size, d.bbox_size, d.vocab_size, self.dtype)
+        else:
+            x = ops.bbox_embed_sum(boxes, self.tables, H, d.bbox_size, self.dtype)
         pos = torch.full((B,), position, dtype=torch.int32, device=self.device)
         enc2d = enc.reshape(B * Lk, -1)
         for l, L in enumerate(self.layers):
@@ -192,9 +202,30 @@ class LayoutEngine:
             x = ops.gemm(m, L["down_w"], residual=res)
         x = ops.rmsnorm_adetr(x, self.final_norm, d.rms_norm_eps)
         h = ops.layernorm(x, *self.out_ln, eps=d.layer_norm_eps)
+        if self.kind == "table":     # SuryaTableRecDecoder.forward (surya/table_rec/model/decoder.py:121-155): 5 bias-free heads
+            return {k: ops.small_head(h, self.head_w[k], None, sigmoid=(k == "bbox"))[0] for k in TABLE_HEADS}
         bbox, _ = ops.small_head(h, self.bbox_w, self.bbox_b, sigmoid=True)
         cls, _ = ops.small_head(h, self.cls_w, None, sigmoid=False)
         return bbox, cls
+
+
+    def decode_prompt(self, ids: torch.Tensor, enc: torch.Tensor, start: int = 0):
+        """q_len > 1 call (the table query prompt, surya/table_rec/processor.py:68-82): causal self-attention makes the
+        batched prefill identical to feeding the tokens one position at a time; only the last position's outputs are used
+        by the predictors (table_rec/__init__.py:78)."""
+        out = None
+        for j in range(ids.shape[1]):
+            out = self.decode_step(ids[:, j].contiguous(), enc, start + j)
+        return out
+
+    def next_tokens(self, out):
+        """Per-step token formation on the device (layout/__init__.py:125-137; table_rec/__init__.py:76-121)."""
+        d = self.cfg.decoder
+        if self.kind == "table":
+            return ops.box_next_token(out["bbox"], [out["category"], out["merges"], out["colspan"], out["is_header"]], [0, 0, 1, 0],
+                                      d.bbox_size, done_head=0, eos=d.eos_token_id, pad=d.pad_token_id)
+        bbox, cls = out
+        return ops.box_next_token(bbox, [cls], [0], d.bbox_size)
 
 
 class _Ns:
@@ -257,9 +288,73 @@ def layout_greedy(engine: LayoutEngine, pixel_values: torch.Tensor, steps: int):
     toks, bbs, cls_all = [], [], []
     for s in range(steps):
         bbox, cls = engine.decode_step(boxes, enc, s)
-        pred = cls.argmax(-1)
-        boxes = torch.cat([(bbox * d.bbox_size).to(torch.int64), pred.unsqueeze(1)], dim=1)
-        toks.append(boxes.clone())
+        boxes, _ = engine.next_tokens((bbox, cls))
+        toks.append(boxes)
         bbs.append(bbox)
         cls_all.append(cls)
     return torch.stack(toks, 1), torch.stack(bbs, 1), torch.stack(cls_all, 1), enc
+
+
+class B200TableRecModel:
+    """Attribute-compatible with what TableRecPredictor uses on `self.model` (surya/table_rec/__init__.py:56-87, 182):
+    model.encoder(pixel_values=).last_hidden_state; model.decoder(input_ids=i64[B,q,10], encoder_hidden_states=,
+    cache_position=, use_cache=True, prefill=) -> {"box_property_logits": {k: [B,1,n_k]}}; _setup_cache; config ids."""
+
+    def __init__(self, engine: LayoutEngine):
+        if engine.kind != "table":
+            raise _lib.SuryaB200Error("B200TableRecModel needs an engine built from a table_rec config")
+        self.engine = engine
+        self.device, self.dtype = engine.device, engine.dtype
+        dec_cfg = _Ns(**engine.cfg.decoder.__dict__)
+        self.config = _Ns(decoder=dec_cfg, encoder=_Ns(**engine.cfg.encoder.__dict__))
+        outer = self
+
+        class _Inner:
+            def _setup_cache(self, config, batch, device, dtype):
+                outer.engine.setup_cache(batch)
+
+            def _clear_cache(self):
+                outer.engine.clear_cache()
+
+        class _Decoder:
+            config = dec_cfg
+            model = _Inner()
+
+            def __call__(self, input_ids=None, encoder_hidden_states=None, cache_position=None, use_cache=True, prefill=False, **kw):
+                if prefill:
+                    outer.engine.setup_cache(input_ids.shape[0])
+                out = outer.engine.decode_prompt(input_ids.to(torch.int64), encoder_hidden_states, int(cache_position[0]))
+                return {"box_property_logits": {k: v.to(outer.dtype).unsqueeze(1) for k, v in out.items()}}
+
+        self.decoder = _Decoder()
+
+    def encoder(self, pixel_values=None, **kw):
+        return _Ns(last_hidden_state=self.engine.encode(pixel_values))
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+
+def table_greedy(engine: LayoutEngine, pixel_values: torch.Tensor, prompt: torch.Tensor, steps: int):
+    """Device part of TableRecPredictor's row/column pass (surya/table_rec/__init__.py:33-131, 180-190): encoder once, prompt
+    prefill, `steps` greedy tokens.  Returns tokens [B, steps, 10], done [B, steps] (uint8), per-step head outputs, enc."""
+    enc = engine.encode(pixel_values)
+    B = enc.shape[0]
+    engine.setup_cache(B)
+    ids = prompt.to(engine.device)
+    out = engine.decode_prompt(ids, enc, 0)
+    pos = ids.shape[1]
+    toks, dones, heads = [], [], []
+    for s in range(steps):
+        tok, done = engine.next_tokens(out)
+        toks.append(tok)
+        dones.append(done)
+        heads.append(out)
+        if s == steps - 1:
+            break
+        out = engine.decode_step(tok, enc, pos + s)
+    hs = {k: torch.stack([h[k] for h in heads], 1) for k in heads[0]}
+    return torch.stack(toks, 1), torch.stack(dones, 1), hs, enc

@@ -277,3 +277,32 @@ def attn_single_query(q, kv, n_keys, nh, nkv, hd, scale):
                                    c_int(_rowmajor(out)), c_int(B), c_int(nh), c_int(nkv), c_int(hd), c_int(n_keys), c_float(scale),
                                    stream_ptr()), "sb_attn_single_query")
     return out
+
+
+def label_embed(boxes, tables, box_w, prop_w, bbox_size, vocab, dtype):
+    """boxes int64 [n, 10]; tables: 13 device tensors (w,h,cx,cy,xskew,yskew,x1,y1,x3,y3 | category,merge,colspan)."""
+    lib = _lib.load()
+    n = boxes.shape[0]
+    out = torch.empty((n, box_w + prop_w), device=boxes.device, dtype=dtype)
+    arr = (_lib.c_void_p * 13)(*[t.data_ptr() for t in tables])
+    check(lib.sb_label_embed(dt_code(dtype), ptr(boxes.contiguous()), arr, ptr(out), c_int(n), c_int(box_w), c_int(prop_w),
+                             c_int(bbox_size), c_int(vocab), stream_ptr()), "sb_label_embed")
+    return out
+
+
+def box_next_token(bbox, heads, modes, bbox_size, done_head=-1, eos=1, pad=0, out=None, done=None):
+    """bbox fp32 [B,6]; heads: list of fp32 [B,n_k]; modes: 0 argmax / 1 colspan rounding -> tokens int64 [B, 6+len(heads)]."""
+    lib = _lib.load()
+    B, k = bbox.shape[0], len(heads)
+    if out is None:
+        out = torch.empty((B, 6 + k), device=bbox.device, dtype=torch.int64)
+    if done is None and done_head >= 0:
+        done = torch.empty((B,), device=bbox.device, dtype=torch.uint8)
+    hp = (_lib.c_void_p * max(k, 1))(*[h.data_ptr() for h in heads])
+    hn = (ctypes.c_int * max(k, 1))(*[h.shape[1] for h in heads])
+    hm = (ctypes.c_int * max(k, 1))(*modes)
+    for h in heads:
+        assert h.dtype == torch.float32 and h.is_contiguous()
+    check(lib.sb_box_next_token(ptr(bbox), hp, hn, hm, c_int(k), c_float(float(bbox_size)), ptr(out), ptr(done), c_int(done_head),
+                                c_int(eos), c_int(pad), c_int(B), stream_ptr()), "sb_box_next_token")
+    return out, done

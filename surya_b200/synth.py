@@ -238,6 +238,39 @@ def adetr_layout_state_dict(cfg, seed: int = 0) -> Dict[str, torch.Tensor]:
     return sd
 
 
+TABLE_BOX_TABLES = ("w", "h", "cx", "cy", "xskew", "yskew", "x1", "y1", "x2", "y2", "x3", "y3", "x4", "y4")
+TABLE_HEADS = ("bbox", "category", "merges", "colspan", "is_header")
+
+
+def table_head_sizes(cfg) -> Dict[str, int]:
+    return {"bbox": 6, "category": cfg.category_count, "merges": cfg.merge_count, "colspan": 1, "is_header": cfg.header_count}
+
+
+def adetr_table_state_dict(cfg, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """fp32 state dict for SuryaTableRecDecoder (surya/table_rec/model/decoder.py:12-119): the layout decoder's layer
+    stack with LabelEmbedding tables and five bias-free property heads.  The category / merge embedding tables carry the
+    special-token offset twice (decoder.py:36-37 adds it on top of get_box_property's), the heads once."""
+    base = adetr_layout_state_dict(cfg, seed)
+    sd = {k: v for k, v in base.items() if k.startswith("model.layers.") or k.startswith("model.final_norm") or k.startswith("pre_output_norm")}
+    for t in TABLE_BOX_TABLES:
+        sd[f"model.embed_tokens.{t}_embed.weight"] = _normal(f"temb.{t}", (cfg.vocab_size, cfg.box_embed_size), 0.25, seed)
+    sd["model.embed_tokens.category_embed.weight"] = _normal("temb.cat", (cfg.category_count + cfg.special_token_count, cfg.property_embed_size), 0.25, seed)
+    sd["model.embed_tokens.merge_embed.weight"] = _normal("temb.merge", (cfg.merge_count + cfg.special_token_count, cfg.property_embed_size), 0.25, seed)
+    sd["model.embed_tokens.colspan_embed.weight"] = _normal("temb.colspan", (cfg.vocab_size, cfg.property_embed_size), 0.25, seed)
+    H = cfg.hidden_size
+    for k, n in table_head_sizes(cfg).items():
+        sd[f"box_property_heads.{k}.weight"] = _normal(f"thead.{k}", (n, H), H ** -0.5, seed)
+    return sd
+
+
+def table_query_tokens(cfg, n: int, seed: int = 0) -> torch.Tensor:
+    """The row/column-pass prompt SuryaTableRecProcessor builds (surya/table_rec/processor.py:65-76): [bos x10], the query
+    box (whole-image table polygon -> cx, cy, w, h, skews, category 'Table' + specials, 0 + specials x3), [query_end x10]."""
+    lab = [512, 512, 1024, 1024, 512, 512, 4 + cfg.special_token_count, cfg.special_token_count, 0, cfg.special_token_count]
+    tok = torch.tensor([[cfg.bos_token_id] * 10, lab, [cfg.query_end_token_id] * 10], dtype=torch.long)
+    return tok.unsqueeze(0).repeat(n, 1, 1)
+
+
 def layout_synthetic_pages(n: int, size=(768, 768), seed: int = 1234) -> torch.Tensor:
     """BASELINE config 4 input: uint8 noise pages through the Donut processor's rescale + normalise
     (surya/common/donut/processor.py:61-116: resize is a no-op at the native size); NCHW fp32."""

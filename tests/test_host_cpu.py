@@ -250,3 +250,20 @@ def test_layout_weight_packing():
     assert torch.equal(_sincos_table(16, 12, 256), sincos_2d(16, 12, 256)[0])
     cfg = layout_tiny()
     assert cfg.encoder.hidden_size == 1024 and cfg.encoder.grid == (64, 64)
+
+
+def test_table_oracle_pinned_to_reference_golden():
+    """oracle (fp32) == reference table_rec encoder + decoder on the seeded case, incl. the 3-token prompt prefill."""
+    from oracle import layout_oracle as L
+    from surya_b200.config import table_tiny
+    from surya_b200.synth import adetr_table_state_dict, layout_synthetic_pages, swin_state_dict, table_query_tokens
+
+    g = torch.load(GOLDEN / "table_tiny.pt")
+    cfg = table_tiny()
+    sde, sdd = swin_state_dict(cfg.encoder, 1), adetr_table_state_dict(cfg.decoder, 1)
+    x = layout_synthetic_pages(2, cfg.encoder.image_size, seed=g["meta"]["page_seed"])
+    tok, done, enc, heads = L.table_greedy(sde, sdd, cfg, x, table_query_tokens(cfg.decoder, 2), g["meta"]["steps"])
+    assert (enc - g["encoder"]).abs().max().item() < 1e-5
+    for k, v in g["heads"].items():
+        assert (heads[k] - v).abs().max().item() < 1e-4, k
+    assert torch.equal(tok, g["tokens"])
