@@ -431,7 +431,7 @@ def main():
 
     # ---- e2e: public API from pinned host buffers, results read back to the host
     def e2e_step():
-        runner.run_preprocessed(tiles, grids, seqs, fixed_steps=True)
+        runner.run_preprocessed(tiles_host, grids, seqs, fixed_steps=True)
 
     log(f"prefill {ms_prefill:.2f} ms, decode {ms_decode:.2f} ms; e2e")
     e2e_step()

@@ -90,65 +90,103 @@ int det_stem_conv(int dtype, const void* in, int in_f32, const float* w, const f
 }
 
 // ------------------------------------------------------------------------------------------------ depthwise conv
-// in NHWC [B,H,W,C]; w: T [k*k][C] (tap-major); bias fp32 [C] or null; one thread = 8 channels of one output pixel.
-template <typename T, int KS>
-__global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, const T* __restrict__ w,
-                                                     const float* __restrict__ bias, T* __restrict__ out, int B, int H,
-                                                     int W, int C, int stride, int pad, int act) {
-  const int Ho = (H + 2 * pad - KS) / stride + 1, Wo = (W + 2 * pad - KS) / stride + 1;
-  const int cv = C >> 3;
-  const long long total = static_cast<long long>(B) * Ho * Wo * cv;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c8 = (idx % cv) * 8;
-    const long long pix = idx / cv;
-    const int ox = pix % Wo;
-    const int oy = (pix / Wo) % Ho;
-    const int b = pix / (static_cast<long long>(Wo) * Ho);
-    float acc[8];
+// in NHWC [B,H,W,C]; w: T [k*k][C] (tap-major); bias fp32 [C] or null.
+// CTA = 32 output columns x 8 channel vectors (64 channels = one 128 B line per pixel); every thread owns 8 channels of one
+// output column and walks TY output rows with the k x k weights in registers, so each input row it touches is loaded once per
+// column instead of once per tap row (L1 absorbs the overlap between neighbouring columns).  fp32 accumulation in tap order
+// (r, s) — the same order as a direct per-pixel loop.
+template <typename T, int KS, int STRIDE, int TY>
+__global__ void __launch_bounds__(256, 2) dwconv_kernel(const T* __restrict__ in, const T* __restrict__ w,
+                                                     const float* __restrict__ bias, T* __restrict__ out, int H, int W, int C,
+                                                     int Ho, int Wo, int pad, int act, int c_blocks) {
+  constexpr int ROWS = (TY - 1) * STRIDE + KS;
+  const int cvec = threadIdx.x & 7, xl = threadIdx.x >> 3;
+  const int cb = blockIdx.x % c_blocks, xb = blockIdx.x / c_blocks;
+  const int c8 = (cb * 8 + cvec) * 8;
+  const int ox = xb * 32 + xl;
+  const int oy0 = blockIdx.y * TY;
+  const int b = blockIdx.z;
+  __shared__ uint4 wsm[KS * KS][8];
+  for (int i = threadIdx.x; i < KS * KS * 8; i += 256) {
+    const int t = i >> 3, cv = i & 7, cc = (cb * 8 + cv) * 8;
+    wsm[t][cv] = cc < C ? *reinterpret_cast<const uint4*>(w + static_cast<size_t>(t) * C + cc) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  if (c8 >= C || ox >= Wo) return;
+  float acc[TY][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int y = 0; y < TY; ++y)
 #pragma unroll
-    for (int r = 0; r < KS; ++r) {
-      const int iy = oy * stride + r - pad;
-      if (iy < 0 || iy >= H) continue;
+    for (int j = 0; j < 8; ++j) acc[y][j] = 0.f;
+  const T* img = in + static_cast<size_t>(b) * H * W * C + c8;
+  const int ix0 = ox * STRIDE - pad, iy0 = oy0 * STRIDE - pad;
 #pragma unroll
-      for (int s = 0; s < KS; ++s) {
-        const int ix = ox * stride + s - pad;
-        if (ix < 0 || ix >= W) continue;
-        const uint4 xv = *reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(b) * H + iy) * W + ix) * C + c8);
-        const uint4 wv = *reinterpret_cast<const uint4*>(w + static_cast<size_t>(r * KS + s) * C + c8);
-        const T* xe = reinterpret_cast<const T*>(&xv);
-        const T* we = reinterpret_cast<const T*>(&wv);
+  for (int rr = 0; rr < ROWS; ++rr) {
+    const int iy = iy0 + rr;
+    const bool row_ok = iy >= 0 && iy < H;
+    uint4 xv[KS];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += to_f<T>(xe[j]) * to_f<T>(we[j]);
+    for (int s_ = 0; s_ < KS; ++s_) {
+      const int ix = ix0 + s_;
+      xv[s_] = make_uint4(0u, 0u, 0u, 0u);
+      if (row_ok && ix >= 0 && ix < W) xv[s_] = *reinterpret_cast<const uint4*>(img + (static_cast<size_t>(iy) * W + ix) * C);
+    }
+#pragma unroll
+    for (int y = 0; y < TY; ++y) {
+      const int r = rr - y * STRIDE;          // tap row of output row y that reads input row rr (compile-time after unrolling)
+      if (r < 0 || r >= KS) continue;
+#pragma unroll
+      for (int s_ = 0; s_ < KS; ++s_) {
+        const T* xe = reinterpret_cast<const T*>(&xv[s_]);
+        const uint4 wq = wsm[r * KS + s_][cvec];
+        const T* we = reinterpret_cast<const T*>(&wq);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[y][j] += to_f<T>(xe[j]) * to_f<T>(we[j]);
       }
     }
+  }
+  float bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bv[j] = bias ? bias[c8 + j] : 0.f;
+#pragma unroll
+  for (int y = 0; y < TY; ++y) {
+    const int oy = oy0 + y;
+    if (oy >= Ho) break;
     uint4 pack;
     T* pe = reinterpret_cast<T*>(&pack);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float y = rnd<T>(acc[j] + (bias ? bias[c8 + j] : 0.f));
-      if (act == ACT_HARDSWISH) y = hardswish_f(y);
-      pe[j] = from_f<T>(y);
+      float v = rnd<T>(acc[y][j] + bv[j]);
+      if (act == ACT_HARDSWISH) v = hardswish_f(v);
+      pe[j] = from_f<T>(v);
     }
-    *reinterpret_cast<uint4*>(out + pix * C + c8) = pack;
+    *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * C + c8) = pack;
   }
+}
+
+template <typename T, int KS, int STRIDE, int TY>
+static void launch_dw(const void* in, const void* w, const float* bias, void* out, int B, int H, int W, int C, int Ho, int Wo,
+                      int pad, int act, cudaStream_t st) {
+  const int c_blocks = (C + 63) / 64;
+  dim3 grid(c_blocks * ((Wo + 31) / 32), (Ho + TY - 1) / TY, B);
+  dwconv_kernel<T, KS, STRIDE, TY><<<grid, 256, 0, st>>>((const T*)in, (const T*)w, bias, (T*)out, H, W, C, Ho, Wo, pad, act, c_blocks);
 }
 
 int det_dwconv(int dtype, const void* in, const void* w, const float* bias, void* out, int B, int H, int W, int C, int ks,
                int stride, int pad, int act, cudaStream_t st) {
   if (C % 8) { set_error("det_dwconv: C must be a multiple of 8"); return -1; }
+  if (B > 65535) { set_error("det_dwconv: batch too large for the grid"); return -1; }
   const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
-  const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
-  int grid = static_cast<int>((total + 255) / 256);
-  if (grid > num_sms() * 16) grid = num_sms() * 16;
-#define DW(T_, KS_) dwconv_kernel<T_, KS_><<<grid, 256, 0, st>>>((const T_*)in, (const T_*)w, bias, (T_*)out, B, H, W, C, stride, pad, act)
-  if (dtype == DT_F16) {
-    if (ks == 3) DW(__half, 3); else if (ks == 5) DW(__half, 5); else { set_error("det_dwconv: kernel size 3 or 5"); return -1; }
-  } else {
-    if (ks == 3) DW(__nv_bfloat16, 3); else if (ks == 5) DW(__nv_bfloat16, 5); else { set_error("det_dwconv: kernel size 3 or 5"); return -1; }
-  }
+  if (Ho <= 0 || Wo <= 0) return 0;
+#define DW(T_) \
+  do { \
+    if (ks == 3 && stride == 1) launch_dw<T_, 3, 1, 4>(in, w, bias, out, B, H, W, C, Ho, Wo, pad, act, st); \
+    else if (ks == 3 && stride == 2) launch_dw<T_, 3, 2, 4>(in, w, bias, out, B, H, W, C, Ho, Wo, pad, act, st); \
+    else if (ks == 5 && stride == 1) launch_dw<T_, 5, 1, 2>(in, w, bias, out, B, H, W, C, Ho, Wo, pad, act, st); \
+    else if (ks == 5 && stride == 2) launch_dw<T_, 5, 2, 1>(in, w, bias, out, B, H, W, C, Ho, Wo, pad, act, st); \
+    else { set_error("det_dwconv: kernel size 3 or 5, stride 1 or 2"); return -1; } \
+  } while (0)
+  if (dtype == DT_F16) DW(__half); else DW(__nv_bfloat16);
 #undef DW
   return launch_ok();
 }
@@ -158,85 +196,82 @@ int det_dwconv(int dtype, const void* in, const void* w, const float* bias, void
 // [h*3*DIM, (h+1)*3*DIM) = (q | k | v).  out: [B*HW, 2*heads*DIM], channel = (s*heads + h)*DIM + d.
 // One CTA per (image, scale*heads + h).  fp32 throughout; rounded to T once at the end (reference: .float() ... .to(dtype)).
 template <typename T, int DIM>
-__global__ void __launch_bounds__(256) lite_mla_kernel(const T* __restrict__ qkv_a, const T* __restrict__ qkv_b,
+__global__ void __launch_bounds__(256, 2) lite_mla_kernel(const T* __restrict__ qkv_a, const T* __restrict__ qkv_b,
                                                        T* __restrict__ out, int HW, int heads, float eps) {
-  constexpr int DV = DIM + 1;
-  __shared__ float kv[DIM * DV];
-  __shared__ float tk[64][DIM + 1];
-  __shared__ float tv[64][DIM + 1];
+  static_assert(DIM == 32, "thread mapping below assumes 32-wide heads");
+  constexpr int DVP = 36;                       // 33 columns (v | ones) padded to a float4 multiple
+  constexpr int TT = 64;                        // tokens staged per tile
+  __shared__ __align__(16) float kv[DIM * DVP];
+  __shared__ __align__(16) float tk[TT][DIM];
+  __shared__ __align__(16) float tv[TT][DIM];
   const int b = blockIdx.x, hh = blockIdx.y;
   const int scale = hh / heads, h = hh % heads;
-  const T* src = (scale == 0 ? qkv_a : qkv_b) + static_cast<size_t>(b) * HW * (3 * heads * DIM) + h * 3 * DIM;
   const int ld = 3 * heads * DIM;
+  const T* src = (scale == 0 ? qkv_a : qkv_b) + static_cast<size_t>(b) * HW * ld + h * 3 * DIM;
   const int tid = threadIdx.x;
-  // each thread owns up to ceil(DIM*DV/256) entries of kv
-  float acc[(DIM * DV + 255) / 256];
-#pragma unroll
-  for (int i = 0; i < (DIM * DV + 255) / 256; ++i) acc[i] = 0.f;
-  for (int t0 = 0; t0 < HW; t0 += 64) {
+  // ---- phase 1: kv[i][j] = sum_t relu(k[t][i]) * [v[t] | 1][j]; thread = (i, 4 consecutive j); j-group 0 also owns the ones column
+  const int ki = tid >> 3, vj = (tid & 7) * 4;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a1s = 0.f;
+  for (int t0 = 0; t0 < HW; t0 += TT) {
     __syncthreads();
-    for (int i = tid; i < 64 * DIM; i += 256) {
-      const int t = i / DIM, d = i % DIM;
-      float kx = 0.f, vx = 0.f;
-      if (t0 + t < HW) {
-        const T* row = src + static_cast<size_t>(t0 + t) * ld;
-        kx = fmaxf(to_f<T>(row[DIM + d]), 0.f);
-        vx = to_f<T>(row[2 * DIM + d]);
+#pragma unroll
+    for (int rep = 0; rep < (TT * 8) / 256; ++rep) {
+      const int i = tid + rep * 256;
+      const int t = i >> 3, part = i & 7;        // parts 0..3 = k, 4..7 = v (k | v are 128 contiguous bytes per token)
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (t0 + t < HW) u = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(t0 + t) * ld + DIM + part * 8);
+      const T* e = reinterpret_cast<const T*>(&u);
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = to_f<T>(e[j]);
+      if (part < 4) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
       }
-      tk[t][d] = kx;
-      tv[t][d] = vx;
+      float* dstp = part < 4 ? &tk[t][part * 8] : &tv[t][(part - 4) * 8];
+      *reinterpret_cast<float4*>(dstp) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(dstp + 4) = make_float4(f[4], f[5], f[6], f[7]);
     }
     __syncthreads();
-    const int nt = min(64, HW - t0);
-#pragma unroll
-    for (int i = 0; i < (DIM * DV + 255) / 256; ++i) {
-      const int e = tid + i * 256;
-      if (e < DIM * DV) {
-        const int ki = e / DV, vj = e % DV;
-        float a = acc[i];
-        if (vj < DIM) {
-          for (int t = 0; t < nt; ++t) a += tk[t][ki] * tv[t][vj];
-        } else {
-          for (int t = 0; t < nt; ++t) a += tk[t][ki];  // ones column
-        }
-        acc[i] = a;
-      }
+#pragma unroll 8
+    for (int t = 0; t < TT; ++t) {               // rows past HW were staged as zeros
+      const float kx = tk[t][ki];
+      const float4 v4 = *reinterpret_cast<const float4*>(&tv[t][vj]);
+      a0 += kx * v4.x; a1 += kx * v4.y; a2 += kx * v4.z; a3 += kx * v4.w;
+      a1s += kx;
     }
   }
-#pragma unroll
-  for (int i = 0; i < (DIM * DV + 255) / 256; ++i) {
-    const int e = tid + i * 256;
-    if (e < DIM * DV) kv[e] = acc[i];
-  }
+  *reinterpret_cast<float4*>(&kv[ki * DVP + vj]) = make_float4(a0, a1, a2, a3);
+  if ((tid & 7) == 0) { kv[ki * DVP + DIM] = a1s; kv[ki * DVP + DIM + 1] = 0.f; kv[ki * DVP + DIM + 2] = 0.f; kv[ki * DVP + DIM + 3] = 0.f; }
   __syncthreads();
+  // ---- phase 2: out[t] = relu(q[t]) kv; out[:-1] / (out[-1] + eps); one token per thread, kv rows broadcast from smem
   T* dst = out + static_cast<size_t>(b) * HW * (2 * heads * DIM) + (scale * heads + h) * DIM;
   const int ldo = 2 * heads * DIM;
   for (int t = tid; t < HW; t += 256) {
-    const T* row = src + static_cast<size_t>(t) * ld;
-    float q[DIM];
+    uint4 qa[DIM / 8];
 #pragma unroll
-    for (int d = 0; d < DIM; d += 8) {
-      uint4 u = *reinterpret_cast<const uint4*>(row + d);
-      const T* e = reinterpret_cast<const T*>(&u);
+    for (int d = 0; d < DIM / 8; ++d) qa[d] = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(t) * ld + d * 8);
+    float oa[DVP];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) q[d + j] = fmaxf(to_f<T>(e[j]), 0.f);
-    }
-    float o[DV];
-#pragma unroll
-    for (int j = 0; j < DV; ++j) o[j] = 0.f;
+    for (int j = 0; j < DVP; ++j) oa[j] = 0.f;
 #pragma unroll
     for (int i = 0; i < DIM; ++i) {
+      const float x = fmaxf(to_f<T>(reinterpret_cast<const T*>(&qa[i >> 3])[i & 7]), 0.f);
 #pragma unroll
-      for (int j = 0; j < DV; ++j) o[j] += q[i] * kv[i * DV + j];
+      for (int j4 = 0; j4 < DVP / 4; ++j4) {
+        const float4 k4 = *reinterpret_cast<const float4*>(&kv[i * DVP + j4 * 4]);
+        oa[j4 * 4 + 0] += x * k4.x; oa[j4 * 4 + 1] += x * k4.y; oa[j4 * 4 + 2] += x * k4.z; oa[j4 * 4 + 3] += x * k4.w;
+      }
+      if (i & 1) asm volatile("" ::: "memory");   // keep ptxas from hoisting all 288 kv loads (register blow-up)
     }
-    const float den = o[DIM] + eps;
+    const float da = oa[DIM] + eps;
 #pragma unroll
     for (int d = 0; d < DIM; d += 8) {
-      uint4 pack;
-      T* pe = reinterpret_cast<T*>(&pack);
+      uint4 pa;
+      T* ea = reinterpret_cast<T*>(&pa);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) pe[j] = from_f<T>(o[d + j] / den);
-      *reinterpret_cast<uint4*>(dst + static_cast<size_t>(t) * ldo + d) = pack;
+      for (int j = 0; j < 8; ++j) ea[j] = from_f<T>(oa[d + j] / da);
+      *reinterpret_cast<uint4*>(dst + static_cast<size_t>(t) * ldo + d) = pa;
     }
   }
 }
