@@ -243,7 +243,7 @@ def detection_bench(dev, peaks, world, steps, warmup):
     import torch.distributed as dist
 
     from surya_b200.config import det_default
-    from surya_b200.detection import DetEngine, detect_heatmaps
+    from surya_b200.detection import DetEngine, detect_pages_host
     from surya_b200.synth import det_normalize, det_state_dict, det_synthetic_pages
 
     B, S = 32, 1024
@@ -274,8 +274,7 @@ def detection_bench(dev, peaks, world, steps, warmup):
         eng.forward(x)
 
     def e2e():
-        up = detect_heatmaps(eng, x_host.to(dev, non_blocking=True))
-        out_host.copy_(up, non_blocking=True)
+        detect_pages_host(eng, x_host, out_host, chunk=8)
         torch.cuda.synchronize()
 
     for _ in range(max(3, warmup)):
@@ -288,13 +287,78 @@ def detection_bench(dev, peaks, world, steps, warmup):
     res = {"metric": "pages/sec (detection)", "value": B * world / (ms * 1e-3), "unit": "pages/s", "ms_per_step": ms,
            "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "pages/s", "h2d_bytes_per_step": x_host.numel() * 2,
                    "d2h_bytes_per_step": out_host.numel() * 4,
-                   "api": "surya_b200.detection.detect_heatmaps (pinned fp16 NCHW pages -> fp32 full-res heatmaps on host)"},
+                   "api": "surya_b200.detection.detect_pages_host (pinned fp16 NCHW pages -> fp32 full-res heatmaps on host; chunks of 8 pipelined over 3 streams)"},
            "config": {"workload": f"detection: {B} synthetic {S}x{S} pages per GPU, EfficientViT-L seg forward (default config)",
                       "dtype": "f16"},
            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                         "frac": tf / peaks["tf_sustained"], "alg_gflop_per_page": gflop_page, "scope": "whole forward"},
            "engine_workspace_gb": eng.workspace_bytes / 1e9}
     eng.close()
+    return res
+
+
+def layout_bench(dev, peaks, world, kind, steps, warmup):
+    """BASELINE config 4 (parity-test configs, reported for completeness): 16 synthetic 768x768 pages per GPU through the Swin
+    encoder + ADETR decoder; layout = 100 greedy box steps, table_rec = 3-token query prompt + 150 steps (row/column pass)."""
+    import torch.distributed as dist
+
+    from surya_b200.config import layout_default, table_default
+    from surya_b200.layout import LayoutEngine, layout_greedy, table_greedy
+    from surya_b200.synth import (adetr_layout_state_dict, adetr_table_state_dict, layout_synthetic_pages, swin_state_dict,
+                                  table_query_tokens)
+
+    B = 16
+    cfg = layout_default() if kind == "layout" else table_default()
+    sdd = adetr_layout_state_dict(cfg.decoder, 0) if kind == "layout" else adetr_table_state_dict(cfg.decoder, 0)
+    eng = LayoutEngine(cfg, swin_state_dict(cfg.encoder, 0), sdd, dtype=torch.float16, device=dev)
+    x_host = layout_synthetic_pages(B, cfg.encoder.image_size, seed=1234).half().pin_memory()
+    x = x_host.to(dev)
+    n_steps = 100 if kind == "layout" else 150
+    prompt = table_query_tokens(cfg.decoder, B).to(dev) if kind == "table" else None
+
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms / k
+
+    def whole(px):
+        if kind == "layout":
+            return layout_greedy(eng, px, n_steps)[0]
+        return table_greedy(eng, px, prompt, n_steps)[0]
+
+    def e2e():
+        tok = whole(x_host.to(dev, non_blocking=True))
+        tok.cpu()
+
+    for _ in range(max(3, warmup)):
+        eng.encode(x)
+    ms_enc = timed(lambda: eng.encode(x), max(1, steps))
+    whole(x)
+    k = max(1, min(steps, 2))
+    ms_all = timed(lambda: whole(x), k)
+    ms_e2e = timed(e2e, k)
+    gflop = 326.6 if kind == "layout" else 268.6
+    tf = gflop * B / (ms_enc * 1e-3) / 1e3
+    res = {"metric": f"pages/sec ({kind})", "value": B * world / (ms_all * 1e-3), "unit": "pages/s", "ms_per_step": ms_all,
+           "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "pages/s", "h2d_bytes_per_step": x_host.numel() * 2,
+                   "d2h_bytes_per_step": B * n_steps * (7 if kind == "layout" else 10) * 8},
+           "config": {"workload": f"{kind}: {B} synthetic 768x768 pages per GPU, Swin encoder + {n_steps} greedy decoder steps",
+                      "dtype": "f16"},
+           "phases_ms": {"encoder": ms_enc, "decode": ms_all - ms_enc, "decode_step": (ms_all - ms_enc) / n_steps},
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                        "frac": tf / peaks["tf_sustained"], "alg_gflop_per_page": gflop, "scope": "Swin encoder (linear layers)"}}
     return res
 
 
@@ -306,6 +370,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-detection", action="store_true")
+    ap.add_argument("--no-layout", action="store_true", help="skip the layout / table_rec (config 4) secondary numbers")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -446,6 +511,14 @@ def main():
         eng_ws = eng.workspace_bytes
         det = detection_bench(dev, peaks, world, args.steps, args.warmup)
         log(f"detection: {det['value']:.1f} pages/s resident, {det['e2e']['value']:.1f} e2e")
+    lay = None
+    if not args.no_layout:
+        lay = {}
+        for kind in ("layout", "table"):
+            log(f"{kind} (config 4)")
+            lay[kind] = layout_bench(dev, peaks, world, kind, args.steps, args.warmup)
+            log(f"{kind}: {lay[kind]['value']:.1f} pages/s (encoder {lay[kind]['phases_ms']['encoder']:.2f} ms, "
+                f"decode step {lay[kind]['phases_ms']['decode_step']:.3f} ms)")
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -474,6 +547,7 @@ def main():
             "phases_ms": {"prefill(vision+decoder)": ms_prefill, f"decode x{MAX_TOKENS - 1}": ms_decode,
                           "decode_step": ms_decode / (MAX_TOKENS - 1)},
             "algorithmic": alg, "engine_workspace_gb": eng.workspace_bytes / 1e9, "detection": det,
+            "layout": lay["layout"] if lay else None, "table_rec": lay["table"] if lay else None,
         }))
     eng.close()
     if world > 1:

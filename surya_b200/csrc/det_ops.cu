@@ -20,55 +20,57 @@ __device__ __forceinline__ float hardswish_f(float x) { return x * fminf(fmaxf(x
 // in: NCHW [B,3,H,W] (T or float); w: fp32 [32][r][s][c] (27 per output channel, BN folded); out NHWC [B,H/2,W/2,CO].
 template <typename T, typename InT, int CO>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const InT* __restrict__ in, const float* __restrict__ w,
-                                                        const float* __restrict__ bias, T* __restrict__ out, int B,
-                                                        int H, int W) {
-  __shared__ float sw[CO * 27];
-  __shared__ float sb_[CO];
-  for (int i = threadIdx.x; i < CO * 27; i += blockDim.x) sw[i] = w[i];
+                                                        const float* __restrict__ bias, T* __restrict__ out, int H, int W) {
+  // weights transposed to [27 taps][CO] so one LDS.128 feeds four output channels of a tap (broadcast across the warp)
+  __shared__ __align__(16) float sw[27][CO];
+  __shared__ __align__(16) float sb_[CO];
+  for (int i = threadIdx.x; i < CO * 27; i += blockDim.x) sw[i % 27][i / 27] = w[i];
   for (int i = threadIdx.x; i < CO; i += blockDim.x) sb_[i] = bias[i];
   __syncthreads();
   const int Ho = H >> 1, Wo = W >> 1;
-  const long long total = static_cast<long long>(B) * Ho * Wo;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int ox = idx % Wo;
-    const int oy = (idx / Wo) % Ho;
-    const int b = idx / (static_cast<long long>(Wo) * Ho);
-    float x[27];
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y, b = blockIdx.z;
+  if (ox >= Wo) return;
+  float x[27];
+  const InT* img = in + static_cast<size_t>(b) * 3 * H * W;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int iy = oy * 2 + r - 1;
+  for (int r = 0; r < 3; ++r) {
+    const int iy = oy * 2 + r - 1;
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int ix = ox * 2 + s - 1;
-        const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+    for (int s = 0; s < 3; ++s) {
+      const int ix = ox * 2 + s - 1;
+      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float v = 0.f;
-          if (ok) {
-            const InT* p = in + ((static_cast<size_t>(b) * 3 + c) * H + iy) * W + ix;
-            if constexpr (sizeof(InT) == 4) v = rnd<T>(static_cast<float>(*p));  // .to(model dtype) of the pixel batch
-            else v = to_f<InT>(*p);
-          }
-          x[(r * 3 + s) * 3 + c] = v;
+      for (int c = 0; c < 3; ++c) {
+        float v = 0.f;
+        if (ok) {
+          const InT* p = img + (static_cast<size_t>(c) * H + iy) * W + ix;
+          if constexpr (sizeof(InT) == 4) v = rnd<T>(static_cast<float>(*p));  // .to(model dtype) of the pixel batch
+          else v = to_f<InT>(*p);
         }
+        x[(r * 3 + s) * 3 + c] = v;
       }
     }
-    T* o = out + idx * CO;
+  }
+  float acc[CO];
 #pragma unroll
-    for (int co8 = 0; co8 < CO; co8 += 8) {
-      uint4 pack;
-      T* pe = reinterpret_cast<T*>(&pack);
+  for (int j = 0; j < CO; ++j) acc[j] = sb_[j];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float* wr = sw + (co8 + j) * 27;
-        float acc = sb_[co8 + j];
+  for (int k = 0; k < 27; ++k) {
 #pragma unroll
-        for (int k = 0; k < 27; ++k) acc += x[k] * wr[k];
-        pe[j] = from_f<T>(hardswish_f(rnd<T>(acc)));
-      }
-      *reinterpret_cast<uint4*>(o + co8) = pack;
+    for (int j4 = 0; j4 < CO / 4; ++j4) {
+      const float4 w4 = *reinterpret_cast<const float4*>(&sw[k][j4 * 4]);
+      acc[j4 * 4 + 0] += x[k] * w4.x; acc[j4 * 4 + 1] += x[k] * w4.y; acc[j4 * 4 + 2] += x[k] * w4.z; acc[j4 * 4 + 3] += x[k] * w4.w;
     }
+    if ((k & 3) == 3) asm volatile("" ::: "memory");   // bound the number of hoisted weight loads
+  }
+  T* o = out + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * CO;
+#pragma unroll
+  for (int co8 = 0; co8 < CO; co8 += 8) {
+    uint4 pack;
+    T* pe = reinterpret_cast<T*>(&pack);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pe[j] = from_f<T>(hardswish_f(rnd<T>(acc[co8 + j])));
+    *reinterpret_cast<uint4*>(o + co8) = pack;
   }
 }
 
@@ -76,15 +78,14 @@ int det_stem_conv(int dtype, const void* in, int in_f32, const float* w, const f
                   int W, int cout, cudaStream_t st) {
   if (cout != 32) { set_error("det_stem_conv: only 32 output channels are instantiated (got %d)", cout); return -1; }
   if ((H | W) & 1) { set_error("det_stem_conv: H and W must be even"); return -1; }
-  const long long total = static_cast<long long>(B) * (H / 2) * (W / 2);
-  int grid = static_cast<int>((total + 127) / 128);
-  if (grid > num_sms() * 32) grid = num_sms() * 32;
+  if (B > 65535 || H / 2 > 65535) { set_error("det_stem_conv: batch / height too large for the grid"); return -1; }
+  dim3 grid((W / 2 + 127) / 128, H / 2, B);
   if (dtype == DT_F16) {
-    if (in_f32) stem_conv_kernel<__half, float, 32><<<grid, 128, 0, st>>>((const float*)in, w, bias, (__half*)out, B, H, W);
-    else stem_conv_kernel<__half, __half, 32><<<grid, 128, 0, st>>>((const __half*)in, w, bias, (__half*)out, B, H, W);
+    if (in_f32) stem_conv_kernel<__half, float, 32><<<grid, 128, 0, st>>>((const float*)in, w, bias, (__half*)out, H, W);
+    else stem_conv_kernel<__half, __half, 32><<<grid, 128, 0, st>>>((const __half*)in, w, bias, (__half*)out, H, W);
   } else {
-    if (in_f32) stem_conv_kernel<__nv_bfloat16, float, 32><<<grid, 128, 0, st>>>((const float*)in, w, bias, (__nv_bfloat16*)out, B, H, W);
-    else stem_conv_kernel<__nv_bfloat16, __nv_bfloat16, 32><<<grid, 128, 0, st>>>((const __nv_bfloat16*)in, w, bias, (__nv_bfloat16*)out, B, H, W);
+    if (in_f32) stem_conv_kernel<__nv_bfloat16, float, 32><<<grid, 128, 0, st>>>((const float*)in, w, bias, (__nv_bfloat16*)out, H, W);
+    else stem_conv_kernel<__nv_bfloat16, __nv_bfloat16, 32><<<grid, 128, 0, st>>>((const __nv_bfloat16*)in, w, bias, (__nv_bfloat16*)out, H, W);
   }
   return launch_ok();
 }
@@ -300,44 +301,39 @@ template <typename T>
 __global__ void __launch_bounds__(256) upsample_cat_kernel(const UpcatParams p, T* __restrict__ dst) {
   const int cv = p.CS >> 3;
   const int CT = p.n_src * p.CS;
-  const long long total = static_cast<long long>(p.B) * p.HO * p.WO * p.n_src * cv;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c8 = (idx % cv) * 8;
-    long long r = idx / cv;
-    const int si = r % p.n_src;
-    r /= p.n_src;
-    const int ox = r % p.WO;
-    const int oy = (r / p.WO) % p.HO;
-    const int b = r / (static_cast<long long>(p.WO) * p.HO);
-    const T* src = reinterpret_cast<const T*>(p.src[si]);
-    const int hs = p.hs[si], ws = p.ws[si];
-    uint4 pack;
-    if (hs == p.HO && ws == p.WO) {
-      pack = *reinterpret_cast<const uint4*>(src + ((static_cast<size_t>(b) * hs + oy) * ws + ox) * p.CS + c8);
-    } else {
-      // torch upsample_bilinear2d, align_corners=False: src = (dst + 0.5) * (in/out) - 0.5, clamped at 0
-      const float sy = fmaxf((oy + 0.5f) * (static_cast<float>(hs) / p.HO) - 0.5f, 0.f);
-      const float sx = fmaxf((ox + 0.5f) * (static_cast<float>(ws) / p.WO) - 0.5f, 0.f);
-      const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
-      const int y1 = y0 + (y0 < hs - 1 ? 1 : 0), x1 = x0 + (x0 < ws - 1 ? 1 : 0);
-      const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
-      const size_t base = static_cast<size_t>(b) * hs * ws;
-      const uint4 v00 = *reinterpret_cast<const uint4*>(src + (base + static_cast<size_t>(y0) * ws + x0) * p.CS + c8);
-      const uint4 v01 = *reinterpret_cast<const uint4*>(src + (base + static_cast<size_t>(y0) * ws + x1) * p.CS + c8);
-      const uint4 v10 = *reinterpret_cast<const uint4*>(src + (base + static_cast<size_t>(y1) * ws + x0) * p.CS + c8);
-      const uint4 v11 = *reinterpret_cast<const uint4*>(src + (base + static_cast<size_t>(y1) * ws + x1) * p.CS + c8);
-      const T *e00 = reinterpret_cast<const T*>(&v00), *e01 = reinterpret_cast<const T*>(&v01);
-      const T *e10 = reinterpret_cast<const T*>(&v10), *e11 = reinterpret_cast<const T*>(&v11);
-      T* pe = reinterpret_cast<T*>(&pack);
+  const int t = blockIdx.x * 256 + threadIdx.x;        // (ox, source, channel vector) within one output row
+  if (t >= p.WO * p.n_src * cv) return;
+  const int c8 = (t % cv) * 8;
+  const int r = t / cv;
+  const int si = r % p.n_src, ox = r / p.n_src;
+  const int oy = blockIdx.y, b = blockIdx.z;
+  const T* src = reinterpret_cast<const T*>(p.src[si]);
+  const int hs = p.hs[si], ws = p.ws[si];
+  uint4 pack;
+  if (hs == p.HO && ws == p.WO) {
+    pack = *reinterpret_cast<const uint4*>(src + ((static_cast<size_t>(b) * hs + oy) * ws + ox) * p.CS + c8);
+  } else {
+    // torch upsample_bilinear2d, align_corners=False: src = (dst + 0.5) * (in/out) - 0.5, clamped at 0
+    const float sy = fmaxf((oy + 0.5f) * (static_cast<float>(hs) / p.HO) - 0.5f, 0.f);
+    const float sx = fmaxf((ox + 0.5f) * (static_cast<float>(ws) / p.WO) - 0.5f, 0.f);
+    const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+    const int y1 = y0 + (y0 < hs - 1 ? 1 : 0), x1 = x0 + (x0 < ws - 1 ? 1 : 0);
+    const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    const T* base = src + static_cast<size_t>(b) * hs * ws * p.CS + c8;
+    const uint4 v00 = *reinterpret_cast<const uint4*>(base + (y0 * ws + x0) * p.CS);
+    const uint4 v01 = *reinterpret_cast<const uint4*>(base + (y0 * ws + x1) * p.CS);
+    const uint4 v10 = *reinterpret_cast<const uint4*>(base + (y1 * ws + x0) * p.CS);
+    const uint4 v11 = *reinterpret_cast<const uint4*>(base + (y1 * ws + x1) * p.CS);
+    const T *e00 = reinterpret_cast<const T*>(&v00), *e01 = reinterpret_cast<const T*>(&v01);
+    const T *e10 = reinterpret_cast<const T*>(&v10), *e11 = reinterpret_cast<const T*>(&v11);
+    T* pe = reinterpret_cast<T*>(&pack);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float v = hy * (hx * to_f<T>(e00[j]) + lx * to_f<T>(e01[j])) + ly * (hx * to_f<T>(e10[j]) + lx * to_f<T>(e11[j]));
-        pe[j] = from_f<T>(v);
-      }
+    for (int j = 0; j < 8; ++j) {
+      float v = hy * (hx * to_f<T>(e00[j]) + lx * to_f<T>(e01[j])) + ly * (hx * to_f<T>(e10[j]) + lx * to_f<T>(e11[j]));
+      pe[j] = from_f<T>(v);
     }
-    *reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(b) * p.HO + oy) * p.WO + ox) * CT + p.ch_off[si] + c8) = pack;
   }
+  *reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(b) * p.HO + oy) * p.WO + ox) * CT + p.ch_off[si] + c8) = pack;
 }
 
 int det_upsample_cat(int dtype, const void* const* src, const int* hs, const int* ws, const int* ch_off, int n_src, int CS,
@@ -346,9 +342,8 @@ int det_upsample_cat(int dtype, const void* const* src, const int* hs, const int
   UpcatParams p;
   for (int i = 0; i < n_src; ++i) { p.src[i] = src[i]; p.hs[i] = hs[i]; p.ws[i] = ws[i]; p.ch_off[i] = ch_off[i]; }
   p.n_src = n_src; p.CS = CS; p.HO = HO; p.WO = WO; p.B = B;
-  const long long total = static_cast<long long>(B) * HO * WO * n_src * (CS / 8);
-  int grid = static_cast<int>((total + 255) / 256);
-  if (grid > num_sms() * 16) grid = num_sms() * 16;
+  if (B > 65535 || HO > 65535) { set_error("det_upsample_cat: batch / height too large for the grid"); return -1; }
+  dim3 grid((WO * n_src * (CS / 8) + 255) / 256, HO, B);
   if (dtype == DT_F16) upsample_cat_kernel<__half><<<grid, 256, 0, st>>>(p, (__half*)dst);
   else upsample_cat_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, (__nv_bfloat16*)dst);
   return launch_ok();
@@ -404,32 +399,45 @@ int det_classifier(int dtype, const void* x, const void* w, const void* b, void*
 
 // ------------------------------------------------------------------------------------------------ x4 bilinear to fp32 (NCHW)
 template <typename T>
-__global__ void __launch_bounds__(256) upsample_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int planes,
-                                                            int hs, int ws, int HO, int WO) {
-  const long long total = static_cast<long long>(planes) * HO * WO;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int ox = idx % WO;
-    const int oy = (idx / WO) % HO;
-    const int pl = idx / (static_cast<long long>(WO) * HO);
-    const float sy = fmaxf((oy + 0.5f) * (static_cast<float>(hs) / HO) - 0.5f, 0.f);
+__global__ void __launch_bounds__(256) upsample_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int hs, int ws,
+                                                            int HO, int WO) {
+  // one thread = 4 consecutive output columns of row blockIdx.y in plane blockIdx.z (float4 store when WO % 4 == 0)
+  const int ox0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (ox0 >= WO) return;
+  const int oy = blockIdx.y, pl = blockIdx.z;
+  const float sy = fmaxf((oy + 0.5f) * (static_cast<float>(hs) / HO) - 0.5f, 0.f);
+  const int y0 = static_cast<int>(sy);
+  const int y1 = y0 + (y0 < hs - 1 ? 1 : 0);
+  const float ly = sy - y0, hy = 1.f - ly;
+  const T* r0 = in + (static_cast<size_t>(pl) * hs + y0) * ws;
+  const T* r1 = in + (static_cast<size_t>(pl) * hs + y1) * ws;
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ox = min(ox0 + j, WO - 1);
     const float sx = fmaxf((ox + 0.5f) * (static_cast<float>(ws) / WO) - 0.5f, 0.f);
-    const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
-    const int y1 = y0 + (y0 < hs - 1 ? 1 : 0), x1 = x0 + (x0 < ws - 1 ? 1 : 0);
-    const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
-    const T* p = in + static_cast<size_t>(pl) * hs * ws;
-    float v = hy * (hx * to_f<T>(p[y0 * ws + x0]) + lx * to_f<T>(p[y0 * ws + x1])) +
-              ly * (hx * to_f<T>(p[y1 * ws + x0]) + lx * to_f<T>(p[y1 * ws + x1]));
-    out[idx] = rnd<T>(v);  // F.interpolate runs in the model dtype; .float() afterwards
+    const int x0 = static_cast<int>(sx);
+    const int x1 = x0 + (x0 < ws - 1 ? 1 : 0);
+    const float lx = sx - x0, hx = 1.f - lx;
+    const float t = hy * (hx * to_f<T>(r0[x0]) + lx * to_f<T>(r0[x1])) + ly * (hx * to_f<T>(r1[x0]) + lx * to_f<T>(r1[x1]));
+    v[j] = rnd<T>(t);  // F.interpolate runs in the model dtype; .float() afterwards
+  }
+  float* o = out + (static_cast<size_t>(pl) * HO + oy) * WO + ox0;
+  if ((WO & 3) == 0) {
+    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (ox0 + j < WO) o[j] = v[j];
   }
 }
 
 int det_upsample_nchw(int dtype, const void* in, float* out, int planes, int hs, int ws, int HO, int WO, cudaStream_t st) {
-  const long long total = static_cast<long long>(planes) * HO * WO;
-  int grid = static_cast<int>((total + 255) / 256);
-  if (grid > num_sms() * 16) grid = num_sms() * 16;
-  if (dtype == DT_F16) upsample_nchw_kernel<__half><<<grid, 256, 0, st>>>((const __half*)in, out, planes, hs, ws, HO, WO);
-  else upsample_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, out, planes, hs, ws, HO, WO);
+  if (planes <= 0) return 0;
+  if (planes > 65535 || HO > 65535) { set_error("det_upsample_nchw: too many planes / rows for the grid"); return -1; }
+  dim3 grid((WO + 1023) / 1024, HO, planes);
+  if (dtype == DT_F16) upsample_nchw_kernel<__half><<<grid, 256, 0, st>>>((const __half*)in, out, hs, ws, HO, WO);
+  else upsample_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, out, hs, ws, HO, WO);
   return launch_ok();
 }
 

@@ -241,10 +241,11 @@ class DetEngine:
                                           c_int(W), ptr(out[b0:b1]), stream_ptr()), "sb_det_forward")
         return out
 
-    def upsample(self, logits: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
+    def upsample(self, logits: torch.Tensor, size: Tuple[int, int], out: torch.Tensor | None = None) -> torch.Tensor:
         """F.interpolate(logits, size, mode='bilinear', align_corners=False).float() (surya/detection/__init__.py:120-132)."""
         B, L, hs, ws = logits.shape
-        out = torch.empty((B, L, size[0], size[1]), dtype=torch.float32, device=logits.device)
+        if out is None:
+            out = torch.empty((B, L, size[0], size[1]), dtype=torch.float32, device=logits.device)
         check(self.lib.sb_det_upsample(c_int(dt_code(logits.dtype)), ptr(logits.contiguous()), ptr(out), c_int(B * L), c_int(hs),
                                        c_int(ws), c_int(size[0]), c_int(size[1]), stream_ptr()), "sb_det_upsample")
         return out
@@ -292,3 +293,56 @@ def detect_heatmaps(engine: DetEngine, pixel_values: torch.Tensor, out_size: Tup
     logits = engine.forward(pixel_values)
     size = out_size or tuple(pixel_values.shape[2:])
     return engine.upsample(logits, size)
+
+
+def detect_pages_host(engine: DetEngine, pages_host: torch.Tensor, out_host: torch.Tensor | None = None, chunk: int = 8,
+                      out_size: Tuple[int, int] | None = None) -> torch.Tensor:
+    """Host-to-host variant of detect_heatmaps for a whole batch (DetectionPredictor.batch_detection,
+    surya/detection/__init__.py:94-132: pixel batch up, fp32 full-resolution heatmaps down): the batch is cut into chunks and
+    the upload of chunk i+1, the forward + upsample of chunk i and the download of chunk i-1 run on three streams, so PCIe
+    time hides behind the kernels.  pages_host: pinned NCHW fp16/fp32 [B,3,H,W]; returns pinned fp32 [B, labels, H, W]."""
+    B, _, H, W = pages_host.shape
+    size = out_size or (H, W)
+    L = engine.cfg.num_labels
+    dev = engine.device
+    if out_host is None:
+        out_host = torch.empty((B, L, size[0], size[1]), dtype=torch.float32).pin_memory()
+    st = getattr(engine, "_pipe", None)
+    key = (chunk, H, W, size, pages_host.dtype)
+    if st is None or st["key"] != key:
+        st = {"key": key, "s_in": torch.cuda.Stream(dev), "s_c": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
+              "x": [torch.empty((chunk, 3, H, W), dtype=pages_host.dtype, device=dev) for _ in range(2)],
+              "up": [torch.empty((chunk, L, size[0], size[1]), dtype=torch.float32, device=dev) for _ in range(2)],
+              "lg": [torch.empty((chunk, L, H // 4, W // 4), dtype=engine.dtype, device=dev) for _ in range(2)]}
+        engine._pipe = st
+    s_in, s_c, s_out = st["s_in"], st["s_c"], st["s_out"]
+    cur = torch.cuda.current_stream(dev)
+    for s_ in (s_in, s_c, s_out):
+        s_.wait_stream(cur)
+    ev_c = [None, None]      # compute finished on buffer k  (guards re-upload into x[k])
+    ev_o = [None, None]      # download finished on buffer k (guards re-use of up[k])
+    for i, b0 in enumerate(range(0, B, chunk)):
+        b1 = min(B, b0 + chunk)
+        n, k = b1 - b0, i & 1
+        with torch.cuda.stream(s_in):
+            if ev_c[k] is not None:
+                s_in.wait_event(ev_c[k])
+            st["x"][k][:n].copy_(pages_host[b0:b1], non_blocking=True)
+            ev_in = torch.cuda.Event()
+            ev_in.record(s_in)
+        with torch.cuda.stream(s_c):
+            s_c.wait_event(ev_in)
+            if ev_o[k] is not None:
+                s_c.wait_event(ev_o[k])
+            engine.forward(st["x"][k][:n], out=st["lg"][k][:n])
+            engine.upsample(st["lg"][k][:n], size, out=st["up"][k][:n])
+            ev_c[k] = torch.cuda.Event()
+            ev_c[k].record(s_c)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_c[k])
+            out_host[b0:b1].copy_(st["up"][k][:n], non_blocking=True)
+            ev_o[k] = torch.cuda.Event()
+            ev_o[k].record(s_out)
+    cur.wait_stream(s_out)
+    cur.wait_stream(s_c)
+    return out_host

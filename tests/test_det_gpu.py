@@ -148,3 +148,21 @@ def test_engine_vs_reference_golden(built_lib):
     assert err16 < 5e-3, f"vs the reference's fp16 path: {err16}"
     assert err < 2.5 * ref_gap, f"engine error {err} vs the reference's own fp16-fp32 gap {ref_gap}"
     eng.close()
+
+
+def test_pipelined_host_path_equals_single_shot(built_lib):
+    """detect_pages_host (chunks over three streams, host in / host out) == forward + upsample of the whole batch, bit for bit
+    (also exercises batch invariance: 5 pages in chunks of 2 vs all at once)."""
+    from surya_b200.config import det_tiny
+    from surya_b200.detection import DetEngine, detect_heatmaps, detect_pages_host
+    from surya_b200.synth import det_normalize, det_state_dict, det_synthetic_pages
+
+    cfg = det_tiny()
+    eng = DetEngine(cfg, det_state_dict(cfg, seed=0), torch.float16, max_batch=5, max_hw=(256, 256))
+    x = det_normalize(det_synthetic_pages(5, 256, seed=5)).half().pin_memory()
+    ref = detect_heatmaps(eng, x.cuda()).cpu()
+    for _ in range(2):      # second call reuses the staging buffers
+        got = detect_pages_host(eng, x, chunk=2)
+        torch.cuda.synchronize()
+        assert got.is_pinned() and torch.equal(got, ref)
+    eng.close()
