@@ -260,9 +260,14 @@ int sb_label_embed(int dtype, const long long* boxes, const void* const* tables,
                    int bbox_size, int vocab, void* stream);
 /* Per-step token formation of LayoutPredictor / TableRecPredictor (layout/__init__.py:125-137; table_rec/__init__.py:76-97 +
  * shaper.py:12-52): out int64 [B, 6 + n_heads] = trunc(clamp(bbox * bbox_size)) x6, then per head argmax (mode 0) or
- * round(max(v, 1)) (mode 1, colspan); done[b] = head `done_head`'s token is eos or pad (may be NULL). */
+ * round(max(v, 1)) (mode 1, colspan); done[b] = head `done_head`'s token is eos or pad (may be NULL).
+ * Optional loop state (all may be NULL) so a whole decode step can be replayed as a CUDA graph: cache_pos[b] += 1
+ * (decoder_position_ids + 1, layout/__init__.py:124, table_rec/__init__.py:71) after the step's tokens [hist_T][B][6+n_heads],
+ * bbox [hist_T][B][6], raw head outputs [hist_T][B][n_k] and done flags were appended at row cache_pos[b] - hist_base[0]. */
 int sb_box_next_token(const float* bbox, const float* const* heads, const int* head_n, const int* head_mode, int n_heads,
-                      float bbox_size, long long* out, unsigned char* done, int done_head, int eos, int pad, int B, void* stream);
+                      float bbox_size, long long* out, unsigned char* done, int done_head, int eos, int pad, int B, int* cache_pos,
+                      const int* hist_base, int hist_T, long long* hist_tok, float* hist_bbox, float* const* hist_heads,
+                      unsigned char* hist_done, void* stream);
 
 #ifdef __cplusplus
 }

@@ -129,9 +129,11 @@ int sb_label_embed(int dtype, const long long* boxes, const void* const* tables,
   return label_embed(dtype, boxes, tables, out, n, box_w, prop_w, bbox_size, vocab, static_cast<cudaStream_t>(stream));
 }
 int sb_box_next_token(const float* bbox, const float* const* heads, const int* head_n, const int* head_mode, int n_heads,
-                      float bbox_size, long long* out, unsigned char* done, int done_head, int eos, int pad, int B, void* stream) {
-  return box_next_token(bbox, heads, head_n, head_mode, n_heads, bbox_size, out, done, done_head, eos, pad, B,
-                        static_cast<cudaStream_t>(stream));
+                      float bbox_size, long long* out, unsigned char* done, int done_head, int eos, int pad, int B, int* cache_pos,
+                      const int* hist_base, int hist_T, long long* hist_tok, float* hist_bbox, float* const* hist_heads,
+                      unsigned char* hist_done, void* stream) {
+  return box_next_token(bbox, heads, head_n, head_mode, n_heads, bbox_size, out, done, done_head, eos, pad, B, cache_pos,
+                        hist_base, hist_T, hist_tok, hist_bbox, hist_heads, hist_done, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -560,44 +560,76 @@ int label_embed(int dtype, const long long* boxes, const void* const* tables, vo
 // The predictors' per-step token formation, on the device: columns 0..5 = trunc(clamp(bbox * bbox_size, 0, bbox_size))
 // (layout/__init__.py:125-137; table_rec/__init__.py:88-93 + shaper.dict_to_labels), then one column per head:
 // mode 0 = argmax (first maximum), mode 1 = round-half-even(max(v, 1)) (table colspan).  done[b] = token of head `done_head`
-// is eos or pad (table_rec/__init__.py:84-87).
-struct StepHeads { const float* p[4]; int n[4]; int mode[4]; };
+// is eos or pad (table_rec/__init__.py:84-87).  Optional decode-loop state so that a whole step can live in a CUDA graph:
+// cache_pos[b] is advanced (decoder_position_ids + 1) and the step's tokens / raw head outputs are appended to history
+// arrays at row (cache_pos[b] - hist_base[0]).
+struct StepHeads { const float* p[4]; int n[4]; int mode[4]; float* hist[4]; };
 
 __global__ void box_next_token_kernel(const float* __restrict__ bbox, StepHeads hd, int n_heads, float bbox_size,
                                       long long* __restrict__ out, unsigned char* __restrict__ done, int done_head, int eos,
-                                      int pad, int B) {
+                                      int pad, int B, int* __restrict__ cache_pos, const int* __restrict__ hist_base, int hist_T,
+                                      long long* __restrict__ hist_tok, float* __restrict__ hist_bbox,
+                                      unsigned char* __restrict__ hist_done) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  long long* o = out + static_cast<size_t>(b) * (6 + n_heads);
+  const int ncol = 6 + n_heads;
+  long long tok[10];
   for (int i = 0; i < 6; ++i) {
     float v = bbox[b * 6 + i] * bbox_size;
     v = fminf(fmaxf(v, 0.f), bbox_size);
-    o[i] = static_cast<long long>(v);
+    tok[i] = static_cast<long long>(v);
   }
+  unsigned char dn = 0;
   for (int k = 0; k < n_heads; ++k) {
     const float* p = hd.p[k] + static_cast<size_t>(b) * hd.n[k];
-    long long tok;
+    long long t;
     if (hd.mode[k] == 1) {
-      tok = static_cast<long long>(rintf(fmaxf(p[0], 1.f)));
+      t = static_cast<long long>(rintf(fmaxf(p[0], 1.f)));
     } else {
       int best = 0;
       float bv = p[0];
       for (int j = 1; j < hd.n[k]; ++j)
         if (p[j] > bv) { bv = p[j]; best = j; }
-      tok = best;
+      t = best;
     }
-    o[6 + k] = tok;
-    if (done && k == done_head) done[b] = (tok == eos || tok == pad) ? 1 : 0;
+    tok[6 + k] = t;
+    if (k == done_head) dn = (t == eos || t == pad) ? 1 : 0;
   }
+  int row = -1;
+  if (cache_pos) {
+    const int pos = cache_pos[b];
+    if (hist_base) row = pos - hist_base[0];
+    cache_pos[b] = pos + 1;
+  }
+  if (row >= 0 && row < hist_T) {
+    const size_t r = static_cast<size_t>(row) * B + b;
+    if (hist_tok)
+      for (int i = 0; i < ncol; ++i) hist_tok[r * ncol + i] = tok[i];
+    if (hist_bbox)
+      for (int i = 0; i < 6; ++i) hist_bbox[r * 6 + i] = bbox[b * 6 + i];
+    for (int k = 0; k < n_heads; ++k)
+      if (hd.hist[k])
+        for (int j = 0; j < hd.n[k]; ++j) hd.hist[k][r * hd.n[k] + j] = hd.p[k][static_cast<size_t>(b) * hd.n[k] + j];
+    if (hist_done && done_head >= 0) hist_done[r] = dn;
+  }
+  // the token buffer may alias nothing this step still reads: written last
+  for (int i = 0; i < ncol; ++i) out[static_cast<size_t>(b) * ncol + i] = tok[i];
+  if (done && done_head >= 0) done[b] = dn;
 }
 
 int box_next_token(const float* bbox, const float* const* heads, const int* head_n, const int* head_mode, int n_heads,
-                   float bbox_size, long long* out, unsigned char* done, int done_head, int eos, int pad, int B, cudaStream_t st) {
+                   float bbox_size, long long* out, unsigned char* done, int done_head, int eos, int pad, int B, int* cache_pos,
+                   const int* hist_base, int hist_T, long long* hist_tok, float* hist_bbox, float* const* hist_heads,
+                   unsigned char* hist_done, cudaStream_t st) {
   if (B <= 0) return 0;
   if (n_heads < 0 || n_heads > 4) { set_error("box_next_token: at most 4 heads"); return -1; }
   StepHeads h{};
-  for (int i = 0; i < n_heads; ++i) { h.p[i] = heads[i]; h.n[i] = head_n[i]; h.mode[i] = head_mode[i]; }
-  box_next_token_kernel<<<(B + 63) / 64, 64, 0, st>>>(bbox, h, n_heads, bbox_size, out, done, done_head, eos, pad, B);
+  for (int i = 0; i < n_heads; ++i) {
+    h.p[i] = heads[i]; h.n[i] = head_n[i]; h.mode[i] = head_mode[i];
+    h.hist[i] = hist_heads ? hist_heads[i] : nullptr;
+  }
+  box_next_token_kernel<<<(B + 63) / 64, 64, 0, st>>>(bbox, h, n_heads, bbox_size, out, done, done_head, eos, pad, B, cache_pos,
+                                                      hist_base, hist_T, hist_tok, hist_bbox, hist_done);
   return launch_ok();
 }
 

@@ -79,7 +79,9 @@ int attn_single_query(int dtype, const void* q, int ldq, const void* K, const vo
 int label_embed(int dtype, const long long* boxes, const void* const* tables, void* out, int n, int box_w, int prop_w,
                 int bbox_size, int vocab, cudaStream_t st);
 int box_next_token(const float* bbox, const float* const* heads, const int* head_n, const int* head_mode, int n_heads,
-                   float bbox_size, long long* out, unsigned char* done, int done_head, int eos, int pad, int B, cudaStream_t st);
+                   float bbox_size, long long* out, unsigned char* done, int done_head, int eos, int pad, int B, int* cache_pos,
+                   const int* hist_base, int hist_T, long long* hist_tok, float* hist_bbox, float* const* hist_heads,
+                   unsigned char* hist_done, cudaStream_t st);
 
 // Single-token decode attention over the slot KV cache, fused with RoPE(q,k) and the in-place cache append.
 //   qkv[b] = [q(nh*d) | k(nkv*d) | v(nkv*d)] for batch row b; slot[b], pos[b] (= number of cached tokens) on device.

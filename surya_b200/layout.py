@@ -169,21 +169,23 @@ class LayoutEngine:
     def clear_cache(self):
         self.cross_kv = [None] * self.cfg.decoder.num_hidden_layers
 
-    def decode_step(self, boxes: torch.Tensor, enc: torch.Tensor, position: int):
+    def decode_step(self, boxes: torch.Tensor, enc: torch.Tensor, position, caches=None):
         """One q_len = 1 decoder call (SuryaLayoutDecoder.forward, surya/layout/model/decoder.py:95-126).
-        boxes int64 [B, 7]; enc [B, L, Henc]; position = cache position of this token.  Returns (bbox sigmoid [B,6] fp32,
-        class logits [B, label_count] fp32 holding the dtype-rounded values)."""
+        boxes int64 [B, 7|10]; enc [B, L, Henc]; position = cache position of this token (int, or an int32 device tensor [B]
+        when the step is replayed from a CUDA graph).  Returns (bbox sigmoid [B,6] fp32, class logits [B, label_count] fp32
+        holding the dtype-rounded values) for layout, the dict of five head outputs for table_rec."""
         d = self.cfg.decoder
         nh, nkv, hd, H = d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.hidden_size
         B, Lk = enc.shape[0], enc.shape[1]
-        if position >= self.s_max:
+        if not torch.is_tensor(position) and position >= self.s_max:
             raise _lib.SuryaB200Error("decoder position exceeds the allocated self-attention cache")
+        kcache, vcache, slot = caches if caches is not None else (self.kcache, self.vcache, self._slot)
         scale = hd ** -0.5
         if self.kind == "table":
             x = ops.label_embed(boxes, self.tables, d.box_embed_size, d.property_embed_size, d.bbox_size, d.vocab_size, self.dtype)
         else:
             x = ops.bbox_embed_sum(boxes, self.tables, H, d.bbox_size, self.dtype)
-        pos = torch.full((B,), position, dtype=torch.int32, device=self.device)
+        pos = position if torch.is_tensor(position) else torch.full((B,), position, dtype=torch.int32, device=self.device)
         enc2d = enc.reshape(B * Lk, -1)
         for l, L in enumerate(self.layers):
             raw = x
@@ -195,7 +197,7 @@ class LayoutEngine:
             cross = ops.gemm(a, L["co_w"], bias=L["co_b"], residual=raw)
             n = ops.rmsnorm_adetr(cross, L["self_norm"], d.rms_norm_eps)
             qkv = ops.gemm(n, L["sqkv_w"])
-            a = ops.decode_attn(qkv, self.kcache[l], self.vcache[l], self._slot, pos, self.inv_freq, nh, nkv, hd, scale)
+            a = ops.decode_attn(qkv, kcache[l], vcache[l], slot, pos, self.inv_freq, nh, nkv, hd, scale)
             res = ops.gemm(a, L["so_w"], bias=L["so_b"], residual=raw if d.double_residual_flow else cross)
             n = ops.rmsnorm_adetr(res, L["mlp_norm"], d.rms_norm_eps)
             m = ops.gemm(n, L["gu_w"], act="gelu_tanh", swiglu=True)
@@ -218,14 +220,82 @@ class LayoutEngine:
             out = self.decode_step(ids[:, j].contiguous(), enc, start + j)
         return out
 
-    def next_tokens(self, out):
+    def next_tokens(self, out, **loop):
         """Per-step token formation on the device (layout/__init__.py:125-137; table_rec/__init__.py:76-121)."""
         d = self.cfg.decoder
         if self.kind == "table":
             return ops.box_next_token(out["bbox"], [out["category"], out["merges"], out["colspan"], out["is_header"]], [0, 0, 1, 0],
-                                      d.bbox_size, done_head=0, eos=d.eos_token_id, pad=d.pad_token_id)
+                                      d.bbox_size, done_head=0, eos=d.eos_token_id, pad=d.pad_token_id, **loop)
         bbox, cls = out
-        return ops.box_next_token(bbox, [cls], [0], d.bbox_size)
+        return ops.box_next_token(bbox, [cls], [0], d.bbox_size, **loop)
+
+    # ---------------------------------------------------------------------------------------------- graph-replayed decode loop
+    def _loop_state(self, B: int, Lk: int, T: int):
+        d = self.cfg.decoder
+        st = self._loops.get(B) if hasattr(self, "_loops") else None
+        if not hasattr(self, "_loops"):
+            self._loops = {}
+        if st is not None and st["Lk"] == Lk and st["T"] >= T:
+            return st
+        dev, ncol = self.device, d.token_width
+        shape = (B, d.num_key_value_heads, self.s_max, d.head_dim)
+        head_n = [d.category_count, d.merge_count, 1, d.header_count] if self.kind == "table" else [d.label_count]
+        st = {"Lk": Lk, "T": T, "graph": None,
+              "tok": torch.zeros((B, ncol), dtype=torch.int64, device=dev), "pos": torch.zeros((B,), dtype=torch.int32, device=dev),
+              "base": torch.zeros((1,), dtype=torch.int32, device=dev),
+              "enc": torch.empty((B, Lk, d.encoder_hidden_size), dtype=self.dtype, device=dev),
+              "ckv": [torch.empty((B * Lk, 2 * d.num_key_value_heads * d.head_dim), dtype=self.dtype, device=dev) for _ in self.layers],
+              "caches": ([torch.zeros(shape, dtype=self.dtype, device=dev) for _ in self.layers],
+                         [torch.zeros(shape, dtype=self.dtype, device=dev) for _ in self.layers],
+                         torch.arange(B, dtype=torch.int32, device=dev)),
+              "hist": {"tok": torch.zeros((T, B, ncol), dtype=torch.int64, device=dev),
+                       "bbox": torch.zeros((T, B, 6), dtype=torch.float32, device=dev),
+                       "heads": [torch.zeros((T, B, n), dtype=torch.float32, device=dev) for n in head_n],
+                       "done": torch.zeros((T, B), dtype=torch.uint8, device=dev)}}
+        self._loops[B] = st
+        return st
+
+    def _loop_body(self, st):
+        out = self.decode_step(st["tok"], st["enc"], st["pos"], caches=st["caches"])
+        self.next_tokens(out, out=st["tok"], cache_pos=st["pos"], hist_base=st["base"], hist=st["hist"])
+
+    def run_loop(self, enc: torch.Tensor, prompt: torch.Tensor, n_steps: int, use_graph: bool = True):
+        """The predictors' whole decode pass on the device: prompt prefill, then n_steps greedy tokens with the per-step
+        kernels (embedding -> layers -> heads -> token formation + position advance + history append) replayed as ONE CUDA
+        graph per step — no host work between steps.  enc [B, Lk, Henc]; prompt int64 [B, q, ncol].
+        Returns history views: tokens [n, B, ncol], bbox [n, B, 6], heads (list of [n, B, n_k]), done [n, B]."""
+        d = self.cfg.decoder
+        B, Lk = enc.shape[0], enc.shape[1]
+        q = prompt.shape[1]
+        if q - 1 + n_steps > self.s_max:
+            raise _lib.SuryaB200Error("prompt + steps exceed the allocated self-attention cache")
+        st = self._loop_state(B, Lk, n_steps)
+        st["enc"].copy_(enc)
+        enc2d = st["enc"].view(B * Lk, -1)
+        self.cross_kv = [ops.gemm(enc2d, L["ckv_w"], out=st["ckv"][l]) for l, L in enumerate(self.layers)]
+        prompt = prompt.to(self.device)
+        for j in range(q - 1):
+            self.decode_step(prompt[:, j].contiguous(), st["enc"], j, caches=st["caches"])
+        st["tok"].copy_(prompt[:, q - 1])
+        st["pos"].fill_(q - 1)
+        st["base"].fill_(q - 1)
+        self._loop_body(st)                       # first step eagerly (also warms every kernel before a capture)
+        if n_steps > 1:
+            if use_graph:
+                if st["graph"] is None:
+                    torch.cuda.synchronize(self.device)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._loop_body(st)
+                    st["graph"] = g
+                    # the capture did not execute; positions/history are untouched
+                for _ in range(n_steps - 1):
+                    st["graph"].replay()
+            else:
+                for _ in range(n_steps - 1):
+                    self._loop_body(st)
+        h = st["hist"]
+        return h["tok"][:n_steps], h["bbox"][:n_steps], [x[:n_steps] for x in h["heads"]], h["done"][:n_steps]
 
 
 class _Ns:
@@ -276,23 +346,16 @@ class B200LayoutModel:
         return self
 
 
-def layout_greedy(engine: LayoutEngine, pixel_values: torch.Tensor, steps: int):
+def layout_greedy(engine: LayoutEngine, pixel_values: torch.Tensor, steps: int, use_graph: bool = True):
     """Device part of LayoutPredictor.batch_layout_detection (surya/layout/__init__.py:106-137, 183): encoder once, then
     `steps` greedy decoder calls; next input = [trunc(bbox * bbox_size) x 6, argmax class].  Returns tokens [B, steps, 7],
-    bbox [B, steps, 6] and class logits [B, steps, label_count] (fp32 tensors on the device)."""
+    bbox [B, steps, 6] and class logits [B, steps, label_count] (fp32 tensors on the device) and the encoder states."""
     d = engine.cfg.decoder
     enc = engine.encode(pixel_values)
     B = enc.shape[0]
-    engine.setup_cache(B)
-    boxes = torch.full((B, 7), d.bos_token_id, dtype=torch.int64, device=engine.device)
-    toks, bbs, cls_all = [], [], []
-    for s in range(steps):
-        bbox, cls = engine.decode_step(boxes, enc, s)
-        boxes, _ = engine.next_tokens((bbox, cls))
-        toks.append(boxes)
-        bbs.append(bbox)
-        cls_all.append(cls)
-    return torch.stack(toks, 1), torch.stack(bbs, 1), torch.stack(cls_all, 1), enc
+    bos = torch.full((B, 1, 7), d.bos_token_id, dtype=torch.int64, device=engine.device)
+    tok, bbox, heads, _ = engine.run_loop(enc, bos, steps, use_graph=use_graph)
+    return tok.transpose(0, 1).contiguous(), bbox.transpose(0, 1).contiguous(), heads[0].transpose(0, 1).contiguous(), enc
 
 
 class B200TableRecModel:
@@ -338,23 +401,12 @@ class B200TableRecModel:
         return self
 
 
-def table_greedy(engine: LayoutEngine, pixel_values: torch.Tensor, prompt: torch.Tensor, steps: int):
+def table_greedy(engine: LayoutEngine, pixel_values: torch.Tensor, prompt: torch.Tensor, steps: int, use_graph: bool = True):
     """Device part of TableRecPredictor's row/column pass (surya/table_rec/__init__.py:33-131, 180-190): encoder once, prompt
     prefill, `steps` greedy tokens.  Returns tokens [B, steps, 10], done [B, steps] (uint8), per-step head outputs, enc."""
     enc = engine.encode(pixel_values)
-    B = enc.shape[0]
-    engine.setup_cache(B)
-    ids = prompt.to(engine.device)
-    out = engine.decode_prompt(ids, enc, 0)
-    pos = ids.shape[1]
-    toks, dones, heads = [], [], []
-    for s in range(steps):
-        tok, done = engine.next_tokens(out)
-        toks.append(tok)
-        dones.append(done)
-        heads.append(out)
-        if s == steps - 1:
-            break
-        out = engine.decode_step(tok, enc, pos + s)
-    hs = {k: torch.stack([h[k] for h in heads], 1) for k in heads[0]}
-    return torch.stack(toks, 1), torch.stack(dones, 1), hs, enc
+    tok, bbox, heads, done = engine.run_loop(enc, prompt, steps, use_graph=use_graph)
+    hs = {"bbox": bbox.transpose(0, 1).contiguous()}
+    for k, h in zip(("category", "merges", "colspan", "is_header"), heads):
+        hs[k] = h.transpose(0, 1).contiguous()
+    return tok.transpose(0, 1).contiguous(), done.transpose(0, 1).contiguous(), hs, enc

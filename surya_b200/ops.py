@@ -290,8 +290,11 @@ def label_embed(boxes, tables, box_w, prop_w, bbox_size, vocab, dtype):
     return out
 
 
-def box_next_token(bbox, heads, modes, bbox_size, done_head=-1, eos=1, pad=0, out=None, done=None):
-    """bbox fp32 [B,6]; heads: list of fp32 [B,n_k]; modes: 0 argmax / 1 colspan rounding -> tokens int64 [B, 6+len(heads)]."""
+def box_next_token(bbox, heads, modes, bbox_size, done_head=-1, eos=1, pad=0, out=None, done=None, cache_pos=None,
+                   hist_base=None, hist=None):
+    """bbox fp32 [B,6]; heads: list of fp32 [B,n_k]; modes: 0 argmax / 1 colspan rounding -> tokens int64 [B, 6+len(heads)].
+    Loop state (optional): cache_pos int32 [B] is advanced; hist = {"tok": i64 [T,B,ncol], "bbox": f32 [T,B,6],
+    "heads": [f32 [T,B,n_k]...], "done": u8 [T,B]} rows are written at cache_pos - hist_base[0]."""
     lib = _lib.load()
     B, k = bbox.shape[0], len(heads)
     if out is None:
@@ -303,6 +306,11 @@ def box_next_token(bbox, heads, modes, bbox_size, done_head=-1, eos=1, pad=0, ou
     hm = (ctypes.c_int * max(k, 1))(*modes)
     for h in heads:
         assert h.dtype == torch.float32 and h.is_contiguous()
+    hist = hist or {}
+    hh = hist.get("heads")
+    hhp = (_lib.c_void_p * max(k, 1))(*[t.data_ptr() for t in hh]) if hh else None
+    T = hist["tok"].shape[0] if "tok" in hist else 0
     check(lib.sb_box_next_token(ptr(bbox), hp, hn, hm, c_int(k), c_float(float(bbox_size)), ptr(out), ptr(done), c_int(done_head),
-                                c_int(eos), c_int(pad), c_int(B), stream_ptr()), "sb_box_next_token")
+                                c_int(eos), c_int(pad), c_int(B), ptr(cache_pos), ptr(hist_base), c_int(T), ptr(hist.get("tok")),
+                                ptr(hist.get("bbox")), hhp, ptr(hist.get("done")), stream_ptr()), "sb_box_next_token")
     return out, done
