@@ -8,6 +8,7 @@
 #include "ops.cuh"
 #include "sb_ptx.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,6 +43,12 @@ struct sb_rec_engine {
   // the legacy default stream cannot be captured: decode_steps hops onto an engine-owned stream, ordered by events
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // decode chains: the batch is cut into row groups whose (strictly sequential, latency-bound) kernel chains run side by side
+  // on forked streams inside one step / one CUDA graph
+  static constexpr int MAX_CHAINS = 4;
+  int n_chains = 2;
+  cudaStream_t chain_stream[MAX_CHAINS] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHAINS] = {nullptr, nullptr, nullptr, nullptr};
   const void* graph_key[8] = {nullptr};
 
   const void* W(int idx) const { return w[idx]; }
@@ -183,28 +190,79 @@ static int run_decoder_prefill(sb_rec_engine* e, const long long* ids, int n_tok
   return run_heads(e, e->xl, n_seq, logits, tok, score, bbox, bbox_sig, done, next_ids, st);
 }
 
-static int run_decode_step(sb_rec_engine* e, const long long* ids, const int* slot, const int* pos, int B, void* logits,
+// One greedy decode step for batch rows [r0, r0 + B): every workspace is row-major, so a row group is a pointer offset.
+static int run_decode_step(sb_rec_engine* e, const long long* ids, const int* slot, const int* pos, int r0, int B, void* logits,
                            long long* tok, float* score, long long* bbox, float* bbox_sig, unsigned char* done,
                            long long* next_ids, cudaStream_t st) {
   const sb_rec_config& c = e->c;
   const int D = c.dec_hidden, nh = c.dec_heads, nkv = c.dec_kv_heads, hd = c.dec_head_dim;
   const int Q = (nh + 2 * nkv) * hd;
   const int dt = c.dtype;
-  CK(embed_rows(dt, ids, e->W(SB_RW_EMBED), e->x, D, B, D, st));
+  auto rows = [&](void* base, size_t width) { return static_cast<void*>(static_cast<uint8_t*>(base) + static_cast<size_t>(r0) * width * e->esz); };
+  void* x = rows(e->x, D);
+  void* nbuf = rows(e->nbuf, D);
+  void* qkv = rows(e->qkv, Q);
+  void* ao = rows(e->ao, nh * hd);
+  void* act = rows(e->act, c.dec_inter_pad);
+  void* xl = rows(e->xl, D);
+  ids += r0; slot += r0; pos += r0;
+  CK(embed_rows(dt, ids, e->W(SB_RW_EMBED), x, D, B, D, st));
   for (int l = 0; l < c.dec_layers; ++l) {
-    CK(rmsnorm(dt, e->x, D, e->WD(l, SB_RWD_IN_NORM), e->nbuf, D, B, D, c.rms_eps, nullptr, st));
-    CK(linear(e, e->nbuf, D, e->WD(l, SB_RWD_QKV_W), D, e->qkv, Q, B, Q, D, e->WD(l, SB_RWD_QKV_B), nullptr, 0, ACT_NONE, 0, st));
+    CK(rmsnorm(dt, x, D, e->WD(l, SB_RWD_IN_NORM), nbuf, D, B, D, c.rms_eps, nullptr, st));
+    CK(linear(e, nbuf, D, e->WD(l, SB_RWD_QKV_W), D, qkv, Q, B, Q, D, e->WD(l, SB_RWD_QKV_B), nullptr, 0, ACT_NONE, 0, st));
     DecodeAttnArgs a;
-    a.dtype = dt; a.qkv = e->qkv; a.ld = Q; a.kcache = e->kc(l); a.vcache = e->vc(l); a.slot = slot; a.pos = pos;
+    a.dtype = dt; a.qkv = qkv; a.ld = Q; a.kcache = e->kc(l); a.vcache = e->vc(l); a.slot = slot; a.pos = pos;
     a.inv_freq = static_cast<const float*>(e->W(SB_RW_DEC_INV_FREQ));
-    a.out = e->ao; a.ldo = nh * hd; a.batch = B; a.n_heads = nh; a.n_kv_heads = nkv; a.head_dim = hd; a.s_max = c.s_max;
+    a.out = ao; a.ldo = nh * hd; a.batch = B; a.n_heads = nh; a.n_kv_heads = nkv; a.head_dim = hd; a.s_max = c.s_max;
     a.scale = 1.0f / sqrtf(static_cast<float>(hd));
     CK(decode_attn(a, st));
-    CK(linear(e, e->ao, nh * hd, e->WD(l, SB_RWD_O_W), nh * hd, e->x, D, B, D, nh * hd, nullptr, e->x, D, ACT_NONE, 0, st));
-    CK(dec_mlp_block(e, l, B, st));
+    CK(linear(e, ao, nh * hd, e->WD(l, SB_RWD_O_W), nh * hd, x, D, B, D, nh * hd, nullptr, x, D, ACT_NONE, 0, st));
+    CK(rmsnorm(dt, x, D, e->WD(l, SB_RWD_POST_NORM), nbuf, D, B, D, c.rms_eps, nullptr, st));
+    CK(linear(e, nbuf, D, e->WD(l, SB_RWD_GU_W), D, act, c.dec_inter_pad, B, 2 * c.dec_inter_pad, D, nullptr, nullptr, 0,
+              ACT_SILU, 1, st));
+    CK(linear(e, act, c.dec_inter_pad, e->WD(l, SB_RWD_DOWN_W), c.dec_inter_pad, x, D, B, D, c.dec_inter_pad, nullptr, x, D,
+              ACT_NONE, 0, st));
   }
-  CK(rmsnorm(dt, e->x, D, e->W(SB_RW_DEC_NORM), e->xl, D, B, D, c.rms_eps, nullptr, st));
-  return run_heads(e, e->xl, B, logits, tok, score, bbox, bbox_sig, done, next_ids, st);
+  CK(rmsnorm(dt, x, D, e->W(SB_RW_DEC_NORM), xl, D, B, D, c.rms_eps, nullptr, st));
+  void* lg = logits ? static_cast<void*>(static_cast<uint8_t*>(logits) + static_cast<size_t>(r0) * c.vocab * e->esz)
+                    : rows(e->logits, c.vocab);
+  return run_heads(e, xl, B, lg, tok ? tok + r0 : nullptr, score ? score + r0 : nullptr, bbox ? bbox + static_cast<size_t>(r0) * 6 : nullptr,
+                   bbox_sig ? bbox_sig + static_cast<size_t>(r0) * 6 : nullptr, done ? done + r0 : nullptr,
+                   next_ids ? next_ids + r0 : nullptr, st);
+}
+
+// The whole batch as n_chains row groups on forked streams (joined back into `st`); works eagerly and under stream capture.
+static int run_decode_step_chained(sb_rec_engine* e, const long long* ids, const int* slot, const int* pos, int B, void* logits,
+                                   long long* tok, float* score, long long* bbox, float* bbox_sig, unsigned char* done,
+                                   long long* next_ids, cudaStream_t st) {
+  int nc = e->n_chains;
+  if (nc > sb_rec_engine::MAX_CHAINS) nc = sb_rec_engine::MAX_CHAINS;
+  while (nc > 1 && B / nc < 32) --nc;            // do not cut below one warp-row group
+  if (nc <= 1) return run_decode_step(e, ids, slot, pos, 0, B, logits, tok, score, bbox, bbox_sig, done, next_ids, st);
+  if (!e->ev_fork) {
+    if (cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); set_error("chain event"); return -20; }
+    for (int i = 1; i < sb_rec_engine::MAX_CHAINS; ++i) {
+      if (cudaStreamCreateWithFlags(&e->chain_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError(); set_error("chain stream"); return -20;
+      }
+    }
+  }
+  const int per = ((B + nc - 1) / nc + 7) & ~7;   // row groups in multiples of 8
+  if (cudaEventRecord(e->ev_fork, st) != cudaSuccess) { cudaGetLastError(); set_error("chain fork"); return -21; }
+  for (int i = 0; i < nc; ++i) {
+    const int r0 = i * per;
+    const int n = (r0 + per <= B) ? per : B - r0;
+    if (n <= 0) break;
+    cudaStream_t s = i == 0 ? st : e->chain_stream[i];
+    if (i) cudaStreamWaitEvent(s, e->ev_fork, 0);
+    CK(run_decode_step(e, ids, slot, pos, r0, n, logits, tok, score, bbox, bbox_sig, done, next_ids, s));
+    if (i) {
+      cudaEventRecord(e->ev_join[i], s);
+      cudaStreamWaitEvent(st, e->ev_join[i], 0);
+    }
+  }
+  return 0;
 }
 
 // Device-side bookkeeping between two greedy steps: history append, token feedback, position increment.
@@ -245,6 +303,10 @@ int sb_rec_create(const sb_rec_config* cfg, const void* const* weights, int n_we
     if (!weights[i]) { set_error("sb_rec_create: weight pointer %d is null", i); return -5; }
   auto* e = new sb_rec_engine();
   e->c = *cfg;
+  if (const char* ev = getenv("SB_DECODE_CHAINS")) {
+    const int v = atoi(ev);
+    if (v >= 1 && v <= sb_rec_engine::MAX_CHAINS) e->n_chains = v;
+  }
   e->w.assign(weights, weights + n_weights);
   const sb_rec_config& c = e->c;
   const size_t es = e->esz;
@@ -291,6 +353,11 @@ void sb_rec_destroy(sb_rec_engine* e) {
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  for (int i = 1; i < sb_rec_engine::MAX_CHAINS; ++i) {
+    if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+    if (e->chain_stream[i]) cudaStreamDestroy(e->chain_stream[i]);
+  }
   if (e->arena) cudaFree(e->arena);
   delete e;
 }
@@ -326,7 +393,7 @@ int sb_rec_decode(sb_rec_engine* e, const long long* input_ids, const int* slot,
                   long long* next_ids, void* stream) {
   if (!e) { set_error("sb_rec_decode: null engine"); return -1; }
   if (batch > e->c.max_slots || batch > e->c.max_tokens) { set_error("sb_rec_decode: batch %d exceeds capacity", batch); return -2; }
-  return run_decode_step(e, input_ids, slot, pos, batch, logits, tok, score, bbox, bbox_sig, done, next_ids,
+  return run_decode_step(e, input_ids, slot, pos, 0, batch, logits, tok, score, bbox, bbox_sig, done, next_ids,
                          static_cast<cudaStream_t>(stream));
 }
 
@@ -358,8 +425,8 @@ int sb_rec_decode_steps(sb_rec_engine* e, long long* ids_io, const int* slot, in
   } rejoin{hop, e->own_stream, caller, e->ev_out};
   if (cudaMemsetAsync(e->st_step, 0, sizeof(int), st) != cudaSuccess) { cudaGetLastError(); set_error("memset failed"); return -3; }
   auto one_step = [&](cudaStream_t s) -> int {
-    CK(run_decode_step(e, ids_io, slot, pos_io, batch, nullptr, e->st_tok, e->st_score, e->st_bbox, nullptr, e->st_done,
-                       e->st_next, s));
+    CK(run_decode_step_chained(e, ids_io, slot, pos_io, batch, nullptr, e->st_tok, e->st_score, e->st_bbox, nullptr,
+                               e->st_done, e->st_next, s));
     launch_pdl(record_step_kernel, dim3(1), dim3(256), 0, s, e->st_step, batch, (const long long*)e->st_tok,
                (const float*)e->st_score, (const long long*)e->st_bbox, (const unsigned char*)e->st_done,
                (const long long*)e->st_next, tok_hist, score_hist, bbox_hist, done_hist, ids_io, pos_io);
@@ -396,6 +463,14 @@ int sb_rec_decode_steps(sb_rec_engine* e, long long* ids_io, const int* slot, in
     if (cudaGraphLaunch(e->graph_exec, st) != cudaSuccess) { cudaGetLastError(); set_error("cudaGraphLaunch failed"); return -7; }
     count_launches(e->graph_nodes);
   }
+  return 0;
+}
+
+int sb_rec_set_decode_chains(sb_rec_engine* e, int n_chains) {
+  if (!e) { set_error("sb_rec_set_decode_chains: null engine"); return -1; }
+  if (n_chains < 1 || n_chains > sb_rec_engine::MAX_CHAINS) { set_error("sb_rec_set_decode_chains: 1..%d", sb_rec_engine::MAX_CHAINS); return -2; }
+  if (n_chains != e->n_chains && e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+  e->n_chains = n_chains;
   return 0;
 }
 

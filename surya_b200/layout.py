@@ -220,13 +220,14 @@ class LayoutEngine:
             out = self.decode_step(ids[:, j].contiguous(), enc, start + j)
         return out
 
-    def next_tokens(self, out, **loop):
+    def next_tokens(self, head_out, **loop):
         """Per-step token formation on the device (layout/__init__.py:125-137; table_rec/__init__.py:76-121)."""
         d = self.cfg.decoder
         if self.kind == "table":
-            return ops.box_next_token(out["bbox"], [out["category"], out["merges"], out["colspan"], out["is_header"]], [0, 0, 1, 0],
+            o = head_out
+            return ops.box_next_token(o["bbox"], [o["category"], o["merges"], o["colspan"], o["is_header"]], [0, 0, 1, 0],
                                       d.bbox_size, done_head=0, eos=d.eos_token_id, pad=d.pad_token_id, **loop)
-        bbox, cls = out
+        bbox, cls = head_out
         return ops.box_next_token(bbox, [cls], [0], d.bbox_size, **loop)
 
     # ---------------------------------------------------------------------------------------------- graph-replayed decode loop

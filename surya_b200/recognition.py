@@ -366,6 +366,10 @@ class RecEngine:
                                      ptr(out["done"]), ptr(out["next_ids"]), stream_ptr()), "sb_rec_decode")
         return out
 
+    def set_decode_chains(self, n: int):
+        """Row groups whose decode kernel chains overlap on forked streams (sb_rec_set_decode_chains); results unchanged."""
+        check(self.lib.sb_rec_set_decode_chains(self._h, c_int(n)), "sb_rec_set_decode_chains")
+
     def decode_steps(self, ids_io: torch.Tensor, slot: torch.Tensor, pos_io: torch.Tensor, n_steps: int,
                      hist: Optional[dict] = None, use_graph: bool = True):
         """n_steps greedy steps on the device; ids_io / pos_io advance in place. Returns step-major histories."""

@@ -265,4 +265,9 @@ def test_fullsize_properties_synrec(built_lib):
     finally:
         R.RecEngine.decode_steps = orig
     assert tokens_e == tokens
+    # decode chains (row groups on forked streams inside the step graph) never change a result
+    for chains in (1, 4, 2):
+        eng.set_decode_chains(chains)
+        tokens_c, scores_c, bboxes_c = runner.run_preprocessed(tiles, grids, seqs, fixed_steps=True)
+        assert tokens_c == tokens and scores_c == scores and np.array_equal(bboxes_c, bboxes), f"chains={chains}"
     eng.close()
