@@ -52,6 +52,7 @@ def det(batch: int = 4, size: int = 1024):
 
 if __name__ == "__main__":
     if "--det" in sys.argv:
-        det()
+        b = int(sys.argv[sys.argv.index("--batch") + 1]) if "--batch" in sys.argv else 4
+        det(batch=b)
     else:
         rec()
