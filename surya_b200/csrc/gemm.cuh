@@ -35,6 +35,9 @@ struct GemmArgs {
 
 // Returns cudaSuccess or an error; sets a message retrievable through sb_last_error().
 int gemm_launch(const GemmArgs& a, cudaStream_t stream);
+// split-K over a thread-block cluster (gemm_splitk.cu): plan returns the split factor (0 = use the plain kernel)
+int splitk_plan(const GemmArgs& a, int* bn_out);
+int gemm_splitk_launch(const GemmArgs& a, int pk, int bn, cudaStream_t stream);
 
 void set_error(const char* fmt, ...);
 const char* last_error();

@@ -235,6 +235,11 @@ bool pdl_enabled() {
   if (v < 0) { const char* e = getenv("SB_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
+bool splitk_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SB_SPLITK"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 void count_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int launch_ok() {
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -383,6 +388,12 @@ static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
 template <typename T>
 static int launch_typed(const GemmArgs& a, cudaStream_t stream) {
   int bn = a.force_bn;
+  if (bn >= 1000) return gemm_splitk_launch(a, bn / 1000, bn % 1000, stream);   // forced split-K: 1000 * pk + BN
+  if (bn == 0 && splitk_enabled()) {
+    int sbn = 0;
+    const int pk = splitk_plan(a, &sbn);
+    if (pk >= 2) return gemm_splitk_launch(a, pk, sbn, stream);
+  }
   if (bn == 0) {
     // Big problems: 128x256 tiles (highest flop per byte of smem fill).  Otherwise the main loop is bound by DRAM latency x
     // bytes in flight per SM, so prefer a single wave of many small tiles: cost = waves * bytes per k-block, with a penalty

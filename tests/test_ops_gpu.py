@@ -321,3 +321,46 @@ def test_embed_splice_and_heads(built_lib, dtype):
     ref_sig = torch.sigmoid(lin.float()).to(dtype).float()
     assert (sig - ref_sig).abs().max().item() <= 2 * _ulp(dtype)
     assert (box - (sig * 1025.0).to(torch.int64)).abs().max().item() == 0
+
+
+# ------------------------------------------------------------------------------------------------ split-K cluster GEMM
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize(
+    "M,N,K,pk,bn,epi",
+    [
+        (256, 1280, 1280, 7, 128, "res"), (256, 1920, 1280, 4, 128, "bias"), (200, 1280, 3424, 7, 128, "res"),
+        (256, 1280, 1280, 2, 64, "none"), (256, 1280, 1280, 3, 64, "bias_res_gelu"), (16, 1024, 1024, 8, 128, "none"),
+        (130, 1000, 640, 5, 128, "bias"), (256, 512, 1280, 8, 64, "swiglu"), (96, 4096, 1024, 2, 128, "geglu"),
+        (256, 1280, 1280, 0, 0, "res"), (256, 1920, 1280, 0, 0, "bias"), (16, 512, 1024, 0, 0, "none"),
+    ],
+)
+def test_gemm_splitk_cluster(built_lib, dtype, M, N, K, pk, bn, epi):
+    """Split-K over a thread-block cluster with the DSMEM reduce-scatter (gemm_splitk.cu); pk = 0 rows exercise the automatic
+    plan that decode-sized GEMMs take.  Same contract and tolerance as the plain kernel; deterministic across runs."""
+    from surya_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + pk)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(dtype)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(dtype)
+    bias = torch.randn(N, device="cuda", generator=g).to(dtype).float() if "bias" in epi else None
+    swi = epi in ("swiglu", "geglu")
+    res = torch.randn(M, N, device="cuda", generator=g).to(dtype) if "res" in epi else None
+    act = "silu" if epi == "swiglu" else "gelu_tanh" if epi == "geglu" else "gelu" if "gelu" in epi else "none"
+    force = 1000 * pk + bn if pk else 0
+    out = ops.gemm(a, w, bias=bias, residual=res, act=act, swiglu=swi, force_bn=force)
+    out2 = ops.gemm(a, w, bias=bias, residual=res, act=act, swiglu=swi, force_bn=force)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2), "split-K reduction must be deterministic"
+    lin = a.float() @ w.float().t()
+    if bias is not None:
+        lin = lin + bias
+    lin = lin.to(dtype)
+    if swi:
+        gate, up = lin[:, 0::2], lin[:, 1::2]
+        ref = (_act_ref(gate.float(), act).to(dtype).float() * up.float()).to(dtype)
+        _close(out, ref, dtype, ulps=3.0, what=f"splitk {epi}")
+        return
+    y = _act_ref(lin.float(), act).to(dtype) if act != "none" else lin
+    ref = (y.float() + res.float()).to(dtype) if res is not None else y
+    scale = torch.maximum(lin.float().abs(), res.float().abs()) if res is not None else None
+    _close(out, ref, dtype, ulps=3.0, what=f"splitk {M}x{N}x{K} pk={pk} bn={bn} {epi}", scale=scale)
