@@ -177,7 +177,7 @@ int sb_rec_decode_steps(sb_rec_engine* eng, long long* ids_io, const int* slot, 
                         long long* tok_hist, float* score_hist, long long* bbox_hist, unsigned char* done_hist,
                         int use_graph, void* stream);
 
-/* Decode-step scheduling: the batch rows are cut into n_chains (1..4, default 2 or $SB_DECODE_CHAINS) groups whose kernel
+/* Decode-step scheduling: the batch rows are cut into n_chains (1..4, default 1 or $SB_DECODE_CHAINS) groups whose kernel
  * chains run concurrently on forked streams inside the step / CUDA graph.  q_len = 1 decoding is a strictly sequential chain
  * of ~90 latency-bound kernels (decoder/__init__.py:417-490 per step); independent row groups overlap each other's launch
  * gaps, prologues and drains.  Results are bit-identical for any setting. */

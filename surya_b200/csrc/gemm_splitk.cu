@@ -302,36 +302,21 @@ static int launch_splitk(const GemmArgs& a, int pk, cudaStream_t stream) {
   return launch_ok();
 }
 
-// Chooses a split for skinny GEMMs; returns 0 when the plain kernel should be used.  Callers: gemm_launch (auto) and
-// GemmArgs.split_k (forced, tests).
+// Chooses a split for skinny GEMMs; returns 0 when the plain kernel should be used.  Measured on B200 inside CUDA-graph
+// replays (tools/bench_gemm.py, profiles/r01_gemm_decode_microbench.md): a cluster launch costs ~2 us more than a plain one
+// and clusters of >= 5 CTAs are 2-3x slower (GPC placement), so the split only pays when the per-CTA k-chain is long —
+// the down projections (K = 3424 / 4096: 16.3 -> 13.0 us with 3 x BN64).  Everything else stays on the plain kernel.
 int splitk_plan(const GemmArgs& a, int* bn_out) {
-  if (a.out_f32 || a.group_k || a.M > 256) return 0;
-  const int sms = num_sms();
-  const int m_blocks = (a.M + 127) / 128;
+  if (a.out_f32 || a.group_k || a.M > 256 || a.swiglu) return 0;
   const int k_blocks = (a.K + 63) / 64;
-  int best_pk = 0, best_bn = 0;
-  double best = 1e30;
-  const int bns[2] = {128, 64};
-  for (int bi = 0; bi < 2; ++bi) {
-    const int bn = bns[bi];
-    if (a.N < bn) continue;
-    const int tiles = m_blocks * ((a.N + bn - 1) / bn);
-    for (int pk = 2; pk <= SK_MAX_PK; ++pk) {
-      if (tiles * pk > sms) break;
-      if (k_blocks / pk < 2) break;
-      if (sk_smem(bn, sk_stages(bn), pk) > 227 * 1024) continue;
-      // per-CTA ingest (A + W slice) plus the partial tile it pushes / pulls through DSMEM, in bytes
-      const double kslice = 64.0 * ((k_blocks + pk - 1) / pk);
-      const double cost = 2.0 * kslice * (128 + bn) + 128.0 * bn * 4.0 * 0.5;
-      if (cost < best) { best = cost; best_pk = pk; best_bn = bn; }
-    }
-  }
-  if (!best_pk) return 0;
-  // plain-kernel estimate: one wave of 128 x 32..96 tiles over all of K
-  const double plain = 2.0 * a.K * (128 + 32);
-  if (best > 0.8 * plain) return 0;
-  *bn_out = best_bn;
-  return best_pk;
+  if (k_blocks < 40 || a.N < 64) return 0;
+  const int sms = num_sms();
+  const int tiles = ((a.M + 127) / 128) * ((a.N + 63) / 64);
+  int pk = 3;
+  while (pk >= 2 && tiles * pk > sms) --pk;
+  if (pk < 2) return 0;
+  *bn_out = 64;
+  return pk;
 }
 
 int gemm_splitk_launch(const GemmArgs& a, int pk, int bn, cudaStream_t stream) {

@@ -46,7 +46,7 @@ struct sb_rec_engine {
   // decode chains: the batch is cut into row groups whose (strictly sequential, latency-bound) kernel chains run side by side
   // on forked streams inside one step / one CUDA graph
   static constexpr int MAX_CHAINS = 4;
-  int n_chains = 2;
+  int n_chains = 1;
   cudaStream_t chain_stream[MAX_CHAINS] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHAINS] = {nullptr, nullptr, nullptr, nullptr};
   const void* graph_key[8] = {nullptr};

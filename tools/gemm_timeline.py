@@ -46,6 +46,7 @@ def run(M, N, K, bias=True, residual=False, swiglu=False, bn=0, reps=5, label=""
 
 
 if __name__ == "__main__":
+    run(16, 1024, 1024, bias=False, label="tiny (layout q_proj)")
     run(256, 1920, 1280, label="qkv")
     run(256, 1280, 1280, bias=False, residual=True, label="o_proj")
     run(256, 6848, 1280, bias=False, swiglu=True, label="gate_up")
