@@ -40,7 +40,9 @@ long long sb_launch_count(void);
  * nn.Linear (+bias, activation, residual, SwiGLU) : torch.nn.functional.linear -> cuBLAS in the reference,
  * e.g. surya/common/surya/decoder/__init__.py:37-50,147-158; encoder/__init__.py:22-35,140-141,115-119.
  * C[M,Nout] = epi(A[M,K] @ W[N,K]^T).  bias is fp32 [N] or NULL; residual [M,Nout] or NULL.
- * swiglu=1: W rows interleaved (gate_i, up_i), Nout = N/2, out = act(gate)*up.  out_f32: C is float32. */
+ * swiglu=1: W rows interleaved (gate_i, up_i), Nout = N/2, out = act(gate)*up.  out_f32: C is float32.
+ * force_bn: 0 = tile heuristic; 32/64/96/128/256 = fixed tile width; -1 = heuristic that may also pick the split-K cluster
+ * kernel (fp32 partials summed in a fixed order over <= 3 K slices; for decode-sized M <= 256 callers); 1000*pk + BN forces it. */
 int sb_gemm(int dtype, const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
             const float* bias, const void* residual, int ldr, int act, int swiglu, int out_f32, int force_bn,
             void* stream);

@@ -16,7 +16,9 @@ int sb_gemm(int dtype, const void* A, int lda, const void* W, int ldw, void* C, 
   GemmArgs a;
   a.dtype = dtype; a.A = A; a.lda = lda; a.W = W; a.ldw = ldw; a.C = C; a.ldc = ldc;
   a.M = M; a.N = N; a.K = K; a.bias = bias; a.residual = residual; a.ldr = ldr;
-  a.act = act; a.swiglu = swiglu; a.out_f32 = out_f32; a.force_bn = force_bn;
+  a.act = act; a.swiglu = swiglu; a.out_f32 = out_f32;
+  a.force_bn = force_bn < 0 ? 0 : force_bn;
+  a.allow_splitk = force_bn < 0 ? 1 : 0;
   return gemm_launch(a, static_cast<cudaStream_t>(stream));
 }
 

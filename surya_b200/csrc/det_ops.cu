@@ -98,70 +98,87 @@ int det_stem_conv(int dtype, const void* in, int in_f32, const float* w, const f
 // (r, s) — the same order as a direct per-pixel loop.
 template <typename T, int KS, int STRIDE, int TY>
 __global__ void __launch_bounds__(256, 2) dwconv_kernel(const T* __restrict__ in, const T* __restrict__ w,
-                                                     const float* __restrict__ bias, T* __restrict__ out, int H, int W, int C,
-                                                     int Ho, int Wo, int pad, int act, int c_blocks) {
+                                                        const float* __restrict__ bias, T* __restrict__ out, int H, int W, int C,
+                                                        int Ho, int Wo, int pad, int act, int c_blocks, int groups_per_cta) {
   constexpr int ROWS = (TY - 1) * STRIDE + KS;
   const int cvec = threadIdx.x & 7, xl = threadIdx.x >> 3;
   const int cb = blockIdx.x % c_blocks, xb = blockIdx.x / c_blocks;
   const int c8 = (cb * 8 + cvec) * 8;
   const int ox = xb * 32 + xl;
-  const int oy0 = blockIdx.y * TY;
   const int b = blockIdx.z;
   __shared__ uint4 wsm[KS * KS][8];
   for (int i = threadIdx.x; i < KS * KS * 8; i += 256) {
     const int t = i >> 3, cv = i & 7, cc = (cb * 8 + cv) * 8;
     wsm[t][cv] = cc < C ? *reinterpret_cast<const uint4*>(w + static_cast<size_t>(t) * C + cc) : make_uint4(0u, 0u, 0u, 0u);
   }
-  __syncthreads();
-  if (c8 >= C || ox >= Wo) return;
-  float acc[TY][8];
-#pragma unroll
-  for (int y = 0; y < TY; ++y)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[y][j] = 0.f;
-  const T* img = in + static_cast<size_t>(b) * H * W * C + c8;
-  const int ix0 = ox * STRIDE - pad, iy0 = oy0 * STRIDE - pad;
-#pragma unroll
-  for (int rr = 0; rr < ROWS; ++rr) {
-    const int iy = iy0 + rr;
-    const bool row_ok = iy >= 0 && iy < H;
-    uint4 xv[KS];
-#pragma unroll
-    for (int s_ = 0; s_ < KS; ++s_) {
-      const int ix = ix0 + s_;
-      xv[s_] = make_uint4(0u, 0u, 0u, 0u);
-      if (row_ok && ix >= 0 && ix < W) xv[s_] = *reinterpret_cast<const uint4*>(img + (static_cast<size_t>(iy) * W + ix) * C);
-    }
-#pragma unroll
-    for (int y = 0; y < TY; ++y) {
-      const int r = rr - y * STRIDE;          // tap row of output row y that reads input row rr (compile-time after unrolling)
-      if (r < 0 || r >= KS) continue;
+  const bool active = c8 < C && ox < Wo;
+  const T* img = in + static_cast<size_t>(b) * H * W * C + (active ? c8 : 0);
+  const int ix0 = ox * STRIDE - pad;
+  // each CTA walks `groups_per_cta` consecutive groups of TY output rows: the weight staging and CTA launch are paid once and
+  // the second CTA resident on the SM computes while this one waits for its loads
+  for (int gi = 0; gi < groups_per_cta; ++gi) {
+    const int oy0 = (blockIdx.y * groups_per_cta + gi) * TY;
+    if (oy0 >= Ho) break;
+    const int iy0 = oy0 * STRIDE - pad;
+    constexpr bool PRELOAD = KS == 3;    // 3x3: issue every load of the group up front; 5x5: stream rows (register budget)
+    constexpr int PR = PRELOAD ? ROWS : 1;
+    uint4 xv[PR][KS];
+    auto load_row = [&](int rr, uint4 (&dst)[KS]) {
+      const int iy = iy0 + rr;
+      const bool row_ok = active && iy >= 0 && iy < H;
 #pragma unroll
       for (int s_ = 0; s_ < KS; ++s_) {
-        const T* xe = reinterpret_cast<const T*>(&xv[s_]);
-        const uint4 wq = wsm[r * KS + s_][cvec];
-        const T* we = reinterpret_cast<const T*>(&wq);
+        const int ix = ix0 + s_;
+        dst[s_] = make_uint4(0u, 0u, 0u, 0u);
+        if (row_ok && ix >= 0 && ix < W) dst[s_] = *reinterpret_cast<const uint4*>(img + (static_cast<size_t>(iy) * W + ix) * C);
+      }
+    };
+    if constexpr (PRELOAD) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[y][j] += to_f<T>(xe[j]) * to_f<T>(we[j]);
+      for (int rr = 0; rr < ROWS; ++rr) load_row(rr, xv[rr]);
+    }
+    if (gi == 0) __syncthreads();        // weights staged (the first group's loads are already in flight)
+    float acc[TY][8];
+#pragma unroll
+    for (int y = 0; y < TY; ++y)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[y][j] = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) {
+      if constexpr (!PRELOAD) load_row(rr, xv[0]);
+#pragma unroll
+      for (int y = 0; y < TY; ++y) {
+        const int r = rr - y * STRIDE;          // tap row of output row y that reads input row rr (compile-time after unrolling)
+        if (r < 0 || r >= KS) continue;
+#pragma unroll
+        for (int s_ = 0; s_ < KS; ++s_) {
+          const T* xe = reinterpret_cast<const T*>(&xv[PRELOAD ? rr : 0][s_]);
+          const uint4 wq = wsm[r * KS + s_][cvec];
+          const T* we = reinterpret_cast<const T*>(&wq);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[y][j] += to_f<T>(xe[j]) * to_f<T>(we[j]);
+        }
       }
     }
-  }
-  float bv[8];
+    if (active) {
+      float bv[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) bv[j] = bias ? bias[c8 + j] : 0.f;
+      for (int j = 0; j < 8; ++j) bv[j] = bias ? __ldg(bias + c8 + j) : 0.f;
 #pragma unroll
-  for (int y = 0; y < TY; ++y) {
-    const int oy = oy0 + y;
-    if (oy >= Ho) break;
-    uint4 pack;
-    T* pe = reinterpret_cast<T*>(&pack);
+      for (int y = 0; y < TY; ++y) {
+        const int oy = oy0 + y;
+        if (oy >= Ho) break;
+        uint4 pack;
+        T* pe = reinterpret_cast<T*>(&pack);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = rnd<T>(acc[y][j] + bv[j]);
-      if (act == ACT_HARDSWISH) v = hardswish_f(v);
-      pe[j] = from_f<T>(v);
+        for (int j = 0; j < 8; ++j) {
+          float v = rnd<T>(acc[y][j] + bv[j]);
+          if (act == ACT_HARDSWISH) v = hardswish_f(v);
+          pe[j] = from_f<T>(v);
+        }
+        *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * C + c8) = pack;
+      }
     }
-    *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * C + c8) = pack;
   }
 }
 
@@ -169,8 +186,14 @@ template <typename T, int KS, int STRIDE, int TY>
 static void launch_dw(const void* in, const void* w, const float* bias, void* out, int B, int H, int W, int C, int Ho, int Wo,
                       int pad, int act, cudaStream_t st) {
   const int c_blocks = (C + 63) / 64;
-  dim3 grid(c_blocks * ((Wo + 31) / 32), (Ho + TY - 1) / TY, B);
-  dwconv_kernel<T, KS, STRIDE, TY><<<grid, 256, 0, st>>>((const T*)in, (const T*)w, bias, (T*)out, H, W, C, Ho, Wo, pad, act, c_blocks);
+  const int gx = c_blocks * ((Wo + 31) / 32);
+  const int groups = (Ho + TY - 1) / TY;
+  // keep >= ~8 CTAs per SM in the grid, otherwise walk up to 4 row groups per CTA
+  int per = 4;
+  while (per > 1 && static_cast<long long>(gx) * ((groups + per - 1) / per) * B < 8LL * num_sms()) per >>= 1;
+  dim3 grid(gx, (groups + per - 1) / per, B);
+  dwconv_kernel<T, KS, STRIDE, TY><<<grid, 256, 0, st>>>((const T*)in, (const T*)w, bias, (T*)out, H, W, C, Ho, Wo, pad, act, c_blocks,
+                                                         per);
 }
 
 int det_dwconv(int dtype, const void* in, const void* w, const float* bias, void* out, int B, int H, int W, int C, int ks,
@@ -182,7 +205,7 @@ int det_dwconv(int dtype, const void* in, const void* w, const float* bias, void
 #define DW(T_) \
   do { \
     if (ks == 3 && stride == 1) launch_dw<T_, 3, 1, 4>(in, w, bias, out, B, H, W, C, Ho, Wo, pad, act, st); \
-    else if (ks == 3 && stride == 2) launch_dw<T_, 3, 2, 4>(in, w, bias, out, B, H, W, C, Ho, Wo, pad, act, st); \
+    else if (ks == 3 && stride == 2) launch_dw<T_, 3, 2, 2>(in, w, bias, out, B, H, W, C, Ho, Wo, pad, act, st); \
     else if (ks == 5 && stride == 1) launch_dw<T_, 5, 1, 2>(in, w, bias, out, B, H, W, C, Ho, Wo, pad, act, st); \
     else if (ks == 5 && stride == 2) launch_dw<T_, 5, 2, 1>(in, w, bias, out, B, H, W, C, Ho, Wo, pad, act, st); \
     else { set_error("det_dwconv: kernel size 3 or 5, stride 1 or 2"); return -1; } \
@@ -297,6 +320,8 @@ struct UpcatParams {
   int n_src, CS, HO, WO, B;
 };
 
+constexpr int UPCAT_ROWS = 4;   // output rows per thread: 16 independent 16-byte loads in flight, one 16-byte store per row
+
 template <typename T>
 __global__ void __launch_bounds__(256) upsample_cat_kernel(const UpcatParams p, T* __restrict__ dst) {
   const int cv = p.CS >> 3;
@@ -306,34 +331,55 @@ __global__ void __launch_bounds__(256) upsample_cat_kernel(const UpcatParams p, 
   const int c8 = (t % cv) * 8;
   const int r = t / cv;
   const int si = r % p.n_src, ox = r / p.n_src;
-  const int oy = blockIdx.y, b = blockIdx.z;
+  const int oy0 = blockIdx.y * UPCAT_ROWS, b = blockIdx.z;
   const T* src = reinterpret_cast<const T*>(p.src[si]);
   const int hs = p.hs[si], ws = p.ws[si];
-  uint4 pack;
+  T* drow = dst + (static_cast<size_t>(b) * p.HO * p.WO + ox) * CT + p.ch_off[si] + c8;
   if (hs == p.HO && ws == p.WO) {
-    pack = *reinterpret_cast<const uint4*>(src + ((static_cast<size_t>(b) * hs + oy) * ws + ox) * p.CS + c8);
-  } else {
-    // torch upsample_bilinear2d, align_corners=False: src = (dst + 0.5) * (in/out) - 0.5, clamped at 0
+    uint4 v[UPCAT_ROWS];
+#pragma unroll
+    for (int y = 0; y < UPCAT_ROWS; ++y)
+      if (oy0 + y < p.HO) v[y] = *reinterpret_cast<const uint4*>(src + ((static_cast<size_t>(b) * hs + oy0 + y) * ws + ox) * p.CS + c8);
+#pragma unroll
+    for (int y = 0; y < UPCAT_ROWS; ++y)
+      if (oy0 + y < p.HO) *reinterpret_cast<uint4*>(drow + static_cast<size_t>(oy0 + y) * p.WO * CT) = v[y];
+    return;
+  }
+  // torch upsample_bilinear2d, align_corners=False: src = (dst + 0.5) * (in/out) - 0.5, clamped at 0
+  const float sx = fmaxf((ox + 0.5f) * (static_cast<float>(ws) / p.WO) - 0.5f, 0.f);
+  const int x0 = static_cast<int>(sx);
+  const int x1 = x0 + (x0 < ws - 1 ? 1 : 0);
+  const float lx = sx - x0, hx = 1.f - lx;
+  const T* base = src + static_cast<size_t>(b) * hs * ws * p.CS + c8;
+  uint4 v00[UPCAT_ROWS], v01[UPCAT_ROWS], v10[UPCAT_ROWS], v11[UPCAT_ROWS];
+  float ly[UPCAT_ROWS];
+#pragma unroll
+  for (int y = 0; y < UPCAT_ROWS; ++y) {
+    const int oy = min(oy0 + y, p.HO - 1);
     const float sy = fmaxf((oy + 0.5f) * (static_cast<float>(hs) / p.HO) - 0.5f, 0.f);
-    const float sx = fmaxf((ox + 0.5f) * (static_cast<float>(ws) / p.WO) - 0.5f, 0.f);
-    const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
-    const int y1 = y0 + (y0 < hs - 1 ? 1 : 0), x1 = x0 + (x0 < ws - 1 ? 1 : 0);
-    const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
-    const T* base = src + static_cast<size_t>(b) * hs * ws * p.CS + c8;
-    const uint4 v00 = *reinterpret_cast<const uint4*>(base + (y0 * ws + x0) * p.CS);
-    const uint4 v01 = *reinterpret_cast<const uint4*>(base + (y0 * ws + x1) * p.CS);
-    const uint4 v10 = *reinterpret_cast<const uint4*>(base + (y1 * ws + x0) * p.CS);
-    const uint4 v11 = *reinterpret_cast<const uint4*>(base + (y1 * ws + x1) * p.CS);
-    const T *e00 = reinterpret_cast<const T*>(&v00), *e01 = reinterpret_cast<const T*>(&v01);
-    const T *e10 = reinterpret_cast<const T*>(&v10), *e11 = reinterpret_cast<const T*>(&v11);
+    const int y0 = static_cast<int>(sy);
+    const int y1 = y0 + (y0 < hs - 1 ? 1 : 0);
+    ly[y] = sy - y0;
+    v00[y] = *reinterpret_cast<const uint4*>(base + (y0 * ws + x0) * p.CS);
+    v01[y] = *reinterpret_cast<const uint4*>(base + (y0 * ws + x1) * p.CS);
+    v10[y] = *reinterpret_cast<const uint4*>(base + (y1 * ws + x0) * p.CS);
+    v11[y] = *reinterpret_cast<const uint4*>(base + (y1 * ws + x1) * p.CS);
+  }
+#pragma unroll
+  for (int y = 0; y < UPCAT_ROWS; ++y) {
+    if (oy0 + y >= p.HO) break;
+    const float hy = 1.f - ly[y];
+    const T *e00 = reinterpret_cast<const T*>(&v00[y]), *e01 = reinterpret_cast<const T*>(&v01[y]);
+    const T *e10 = reinterpret_cast<const T*>(&v10[y]), *e11 = reinterpret_cast<const T*>(&v11[y]);
+    uint4 pack;
     T* pe = reinterpret_cast<T*>(&pack);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float v = hy * (hx * to_f<T>(e00[j]) + lx * to_f<T>(e01[j])) + ly * (hx * to_f<T>(e10[j]) + lx * to_f<T>(e11[j]));
+      float v = hy * (hx * to_f<T>(e00[j]) + lx * to_f<T>(e01[j])) + ly[y] * (hx * to_f<T>(e10[j]) + lx * to_f<T>(e11[j]));
       pe[j] = from_f<T>(v);
     }
+    *reinterpret_cast<uint4*>(drow + static_cast<size_t>(oy0 + y) * p.WO * CT) = pack;
   }
-  *reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(b) * p.HO + oy) * p.WO + ox) * CT + p.ch_off[si] + c8) = pack;
 }
 
 int det_upsample_cat(int dtype, const void* const* src, const int* hs, const int* ws, const int* ch_off, int n_src, int CS,
@@ -343,7 +389,7 @@ int det_upsample_cat(int dtype, const void* const* src, const int* hs, const int
   for (int i = 0; i < n_src; ++i) { p.src[i] = src[i]; p.hs[i] = hs[i]; p.ws[i] = ws[i]; p.ch_off[i] = ch_off[i]; }
   p.n_src = n_src; p.CS = CS; p.HO = HO; p.WO = WO; p.B = B;
   if (B > 65535 || HO > 65535) { set_error("det_upsample_cat: batch / height too large for the grid"); return -1; }
-  dim3 grid((WO * n_src * (CS / 8) + 255) / 256, HO, B);
+  dim3 grid((WO * n_src * (CS / 8) + 255) / 256, (HO + UPCAT_ROWS - 1) / UPCAT_ROWS, B);
   if (dtype == DT_F16) upsample_cat_kernel<__half><<<grid, 256, 0, st>>>(p, (__half*)dst);
   else upsample_cat_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, (__nv_bfloat16*)dst);
   return launch_ok();

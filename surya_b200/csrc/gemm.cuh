@@ -24,7 +24,9 @@ struct GemmArgs {
   int act = ACT_NONE;
   int swiglu = 0;
   int out_f32 = 0;                        // C is float32 (no final rounding) when set
-  int force_bn = 0;                       // 0 = heuristic, else 32/64/128/256
+  int force_bn = 0;                       // 0 = heuristic, else 32/64/96/128/256; 1000 * pk + BN forces split-K
+  int allow_splitk = 0;                   // the heuristic may pick the split-K cluster kernel (changes the fp32 summation
+                                          // order, so only callers whose M never crosses the 256-row limit opt in: decode steps)
   // grouped 1x1 convolution (block-diagonal weights): n-block g reads A columns [g*group_k, g*group_k + K) and
   // W rows [g*group_n, (g+1)*group_n); W is [N, K] with K the zero-padded per-group depth; a_cols = A's width.
   int group_k = 0, group_n = 0, a_cols = 0;

@@ -389,7 +389,7 @@ template <typename T>
 static int launch_typed(const GemmArgs& a, cudaStream_t stream) {
   int bn = a.force_bn;
   if (bn >= 1000) return gemm_splitk_launch(a, bn / 1000, bn % 1000, stream);   // forced split-K: 1000 * pk + BN
-  if (bn == 0 && splitk_enabled()) {
+  if (bn == 0 && a.allow_splitk && splitk_enabled()) {
     int sbn = 0;
     const int pk = splitk_plan(a, &sbn);
     if (pk >= 2) return gemm_splitk_launch(a, pk, sbn, stream);
@@ -400,7 +400,11 @@ static int launch_typed(const GemmArgs& a, cudaStream_t stream) {
     // when fewer than ~60 % of the SMs would be streaming the weight matrix.
     const int sms = num_sms();
     const int m_blocks = (a.M + 127) / 128;
-    if (m_blocks * ((a.N + 255) / 256) >= (sms * 3) / 4) {
+    if (a.N <= 128 && m_blocks >= sms) {
+      // narrow outputs over many rows (1x1 "project" convs): the launch streams A; a tile wider than N only adds zero-filled W
+      // loads and MMA / epilogue work (profiles/r01c_det_launch_summary.md: N = 64 ran on 256-wide tiles at 43 % of HBM peak)
+      bn = a.N <= 32 ? 32 : a.N <= 64 ? 64 : a.N <= 96 ? 96 : 128;
+    } else if (m_blocks * ((a.N + 255) / 256) >= (sms * 3) / 4) {
       bn = 256;
     } else {
       const int cands[5] = {256, 128, 96, 64, 32};

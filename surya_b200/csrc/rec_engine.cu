@@ -67,7 +67,8 @@ struct sb_rec_engine {
 static size_t al256(size_t v) { return (v + 255) & ~size_t(255); }
 
 static int linear(const sb_rec_engine* e, const void* A, int lda, const void* Wt, int ldw, void* C, int ldc, int M, int N,
-                  int K, const void* bias_f32, const void* residual, int ldr, int act, int swiglu, cudaStream_t st) {
+                  int K, const void* bias_f32, const void* residual, int ldr, int act, int swiglu, cudaStream_t st,
+                  int allow_splitk = 0) {
   GemmArgs a;
   a.dtype = e->c.dtype;
   a.A = A; a.lda = lda; a.W = Wt; a.ldw = ldw; a.C = C; a.ldc = ldc;
@@ -75,6 +76,7 @@ static int linear(const sb_rec_engine* e, const void* A, int lda, const void* Wt
   a.bias = static_cast<const float*>(bias_f32);
   a.residual = residual; a.ldr = ldr; a.act = act; a.swiglu = swiglu;
   a.w_constant = 1;   // engine weights are never written after packing
+  a.allow_splitk = allow_splitk;
   return gemm_launch(a, st);
 }
 
@@ -221,7 +223,7 @@ static int run_decode_step(sb_rec_engine* e, const long long* ids, const int* sl
     CK(linear(e, nbuf, D, e->WD(l, SB_RWD_GU_W), D, act, c.dec_inter_pad, B, 2 * c.dec_inter_pad, D, nullptr, nullptr, 0,
               ACT_SILU, 1, st));
     CK(linear(e, act, c.dec_inter_pad, e->WD(l, SB_RWD_DOWN_W), c.dec_inter_pad, x, D, B, D, c.dec_inter_pad, nullptr, x, D,
-              ACT_NONE, 0, st));
+              ACT_NONE, 0, st, /*allow_splitk=*/1));
   }
   CK(rmsnorm(dt, x, D, e->W(SB_RW_DEC_NORM), xl, D, B, D, c.rms_eps, nullptr, st));
   void* lg = logits ? static_cast<void*>(static_cast<uint8_t*>(logits) + static_cast<size_t>(r0) * c.vocab * e->esz)

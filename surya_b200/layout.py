@@ -201,7 +201,7 @@ class LayoutEngine:
             res = ops.gemm(a, L["so_w"], bias=L["so_b"], residual=raw if d.double_residual_flow else cross)
             n = ops.rmsnorm_adetr(res, L["mlp_norm"], d.rms_norm_eps)
             m = ops.gemm(n, L["gu_w"], act="gelu_tanh", swiglu=True)
-            x = ops.gemm(m, L["down_w"], residual=res)
+            x = ops.gemm(m, L["down_w"], residual=res, splitk=True)
         x = ops.rmsnorm_adetr(x, self.final_norm, d.rms_norm_eps)
         h = ops.layernorm(x, *self.out_ln, eps=d.layer_norm_eps)
         if self.kind == "table":     # SuryaTableRecDecoder.forward (surya/table_rec/model/decoder.py:121-155): 5 bias-free heads

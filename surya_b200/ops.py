@@ -28,8 +28,11 @@ def _rowmajor(t: torch.Tensor) -> int:
     return t.stride(0)
 
 
-def gemm(a, w, bias=None, residual=None, act="none", swiglu=False, out=None, out_f32=False, force_bn=0):
-    """out[M, Nout] = epi(a[M,K] @ w[N,K]^T); bias fp32 [N]; see sb_gemm."""
+def gemm(a, w, bias=None, residual=None, act="none", swiglu=False, out=None, out_f32=False, force_bn=0, splitk=False):
+    """out[M, Nout] = epi(a[M,K] @ w[N,K]^T); bias fp32 [N]; see sb_gemm.  splitk=True lets the heuristic use the split-K
+    cluster kernel (decode-sized M only)."""
+    if splitk and force_bn == 0:
+        force_bn = -1
     lib = _lib.load()
     M, K = a.shape
     N = w.shape[0]

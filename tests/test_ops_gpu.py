@@ -346,7 +346,7 @@ def test_gemm_splitk_cluster(built_lib, dtype, M, N, K, pk, bn, epi):
     swi = epi in ("swiglu", "geglu")
     res = torch.randn(M, N, device="cuda", generator=g).to(dtype) if "res" in epi else None
     act = "silu" if epi == "swiglu" else "gelu_tanh" if epi == "geglu" else "gelu" if "gelu" in epi else "none"
-    force = 1000 * pk + bn if pk else 0
+    force = 1000 * pk + bn if pk else -1     # -1: the automatic plan decode steps opt into
     out = ops.gemm(a, w, bias=bias, residual=res, act=act, swiglu=swi, force_bn=force)
     out2 = ops.gemm(a, w, bias=bias, residual=res, act=act, swiglu=swi, force_bn=force)
     torch.cuda.synchronize()
