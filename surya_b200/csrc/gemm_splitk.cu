@@ -45,10 +45,10 @@ constexpr int SK_MAX_PK = 8;
 // first 8-column unit owned by rank j when n_units units are dealt to pk ranks
 __device__ __host__ __forceinline__ int sk_first_unit(int j, int n_units, int pk) { return (j * n_units) / pk; }
 
-template <typename T, int BN, int STAGES>
+template <typename T, int BN>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 gemm_splitk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmKParams p,
-                   int pk, int rstride) {
+                   int pk, int rstride, int STAGES) {
   constexpr int BM = 128, BK = 64;
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
@@ -56,9 +56,11 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // STAGES (<= 8) is a launch parameter: as many pipeline stages as fit beside the receive buffer — the main loop needs
+  // ~150 KB in flight per SM to run at the SM's L2 read-port rate (profiles/r01_gemm_decode_microbench.md)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tfull_bar = empty_bar + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
   float* recv = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // [pk][128][rstride]
 
@@ -255,17 +257,24 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 }
 
 static int sk_rstride(int bn, int pk) { return ((bn / 8 + pk - 1) / pk) * 8 + 4; }   // +4 floats: rows land in different banks
-static size_t sk_smem(int bn, int stages, int pk) {
-  return static_cast<size_t>(stages) * (128 * 64 * 2 + bn * 64 * 2) + 1024 + 256 + static_cast<size_t>(pk) * 128 * sk_rstride(bn, pk) * 4;
+static size_t sk_recv_bytes(int bn, int pk) { return static_cast<size_t>(pk) * 128 * sk_rstride(bn, pk) * 4; }
+static int sk_stages(int bn, int pk, int k_blocks) {
+  const size_t stage = 128 * 64 * 2 + static_cast<size_t>(bn) * 64 * 2;
+  const size_t room = 227 * 1024 - 1024 - 256 - sk_recv_bytes(bn, pk);
+  int st = static_cast<int>(room / stage);
+  const int need = (k_blocks + pk - 1) / pk;
+  if (st > need) st = need;
+  if (st > 8) st = 8;
+  return st;
 }
-static int sk_stages(int bn) { return bn == 128 ? 3 : 4; }
 
-template <typename T, int BN, int STAGES>
+template <typename T, int BN>
 static int launch_splitk(const GemmArgs& a, int pk, cudaStream_t stream) {
   const int rstride = sk_rstride(BN, pk);
-  const size_t smem = sk_smem(BN, STAGES, pk);
-  if (smem > 227 * 1024) { set_error("split-K GEMM: %zu bytes of shared memory needed", smem); return -15; }
-  auto kern = gemm_splitk_kernel<T, BN, STAGES>;
+  const int stages = sk_stages(BN, pk, (a.K + 63) / 64);
+  if (stages < 2) { set_error("split-K GEMM: no room for the pipeline (BN=%d pk=%d)", BN, pk); return -15; }
+  const size_t smem = static_cast<size_t>(stages) * (128 * 64 * 2 + BN * 64 * 2) + 1024 + 256 + sk_recv_bytes(BN, pk);
+  auto kern = gemm_splitk_kernel<T, BN>;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -298,7 +307,7 @@ static int launch_splitk(const GemmArgs& a, int pk, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaLaunchKernelEx(&cfg, kern, ma, mb, p, pk, rstride);
+  cudaLaunchKernelEx(&cfg, kern, ma, mb, p, pk, rstride, stages);
   return launch_ok();
 }
 
@@ -320,14 +329,14 @@ int splitk_plan(const GemmArgs& a, int* bn_out) {
 }
 
 int gemm_splitk_launch(const GemmArgs& a, int pk, int bn, cudaStream_t stream) {
-  if (pk < 2 || pk > SK_MAX_PK) { set_error("split-K factor %d out of range", pk); return -16; }
+  if (pk < 1 || pk > SK_MAX_PK) { set_error("split-K factor %d out of range", pk); return -16; }   // pk = 1: cluster of one (benchmarks)
   if (a.out_f32 || a.group_k) { set_error("split-K GEMM: fp32 output / grouped mode not supported"); return -17; }
   if (a.dtype == DT_BF16) {
-    if (bn == 128) return launch_splitk<__nv_bfloat16, 128, 3>(a, pk, stream);
-    if (bn == 64) return launch_splitk<__nv_bfloat16, 64, 4>(a, pk, stream);
+    if (bn == 128) return launch_splitk<__nv_bfloat16, 128>(a, pk, stream);
+    if (bn == 64) return launch_splitk<__nv_bfloat16, 64>(a, pk, stream);
   } else if (a.dtype == DT_F16) {
-    if (bn == 128) return launch_splitk<__half, 128, 3>(a, pk, stream);
-    if (bn == 64) return launch_splitk<__half, 64, 4>(a, pk, stream);
+    if (bn == 128) return launch_splitk<__half, 128>(a, pk, stream);
+    if (bn == 64) return launch_splitk<__half, 64>(a, pk, stream);
   }
   set_error("split-K GEMM: unsupported dtype / BN (%d, %d)", a.dtype, bn);
   return -18;

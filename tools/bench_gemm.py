@@ -40,7 +40,7 @@ def main():
         out = torch.empty(M, N // 2 if swi else N, device="cuda", dtype=dt)
         res = []
         cfgs = [("bn32", 32), ("bn64", 64), ("bn96", 96), ("bn128", 128), ("bn256", 256)]
-        for pk in (2, 3, 4):
+        for pk in (1, 2, 3, 4):
             for bn in (64, 128):
                 cfgs.append((f"sk{pk}x{bn}", 1000 * pk + bn))
         for label, force in cfgs:
