@@ -231,8 +231,13 @@ def decode_gemm_roofline(eng, peaks, reps=20):
     ms_step = e0.elapsed_time(e1) / reps
     n = len(calls)
     achieved = nbytes / n / (ms_step / n * 1e-3) / 1e9
+    traffic = None          # DRAM bytes per launch from the committed ncu capture of the same launches (profiles/)
+    tp = Path(__file__).resolve().parent / "profiles" / "decode_gemm_traffic.json"
+    if tp.exists():
+        traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
     return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "traffic": None, "kernel": "gemm_tn_kernel (tcgen05), decode-step launches", "launches_per_decode_step": n,
+            "traffic": traffic, "traffic_src": "profiles/decode_gemm_traffic.json (ncu dram__bytes_read+write, per launch)",
+            "kernel": "gemm_tn_kernel / gemm_splitk_kernel (tcgen05), decode-step launches", "launches_per_decode_step": n,
             "alg_bytes_per_launch": nbytes / n, "avg_launch_us": ms_step / n * 1e3, "gemm_ms_per_decode_step": ms_step,
             "gemm_tflops_in_decode": flops / (ms_step * 1e-3) / 1e12, "peak_src": peaks["src"]}, ms_step
 

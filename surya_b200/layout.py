@@ -125,6 +125,8 @@ class LayoutEngine:
         """DonutSwinLayoutModel.forward (surya/layout/model/encoder.py:33-81): NCHW pixels -> [B, L, hidden]."""
         e = self.cfg.encoder
         B, _, Hi, Wi = pixel_values.shape
+        if B == 0:
+            raise _lib.SuryaB200Error("empty batch: the predictors return before calling the model (layout/__init__.py:193-195)")
         if (Hi, Wi) != tuple(e.image_size):
             raise _lib.SuryaB200Error(f"layout encoder expects {e.image_size} inputs, got {(Hi, Wi)}")
         if not pixel_values.is_cuda:

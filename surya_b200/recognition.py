@@ -584,6 +584,8 @@ class RecognitionRunner:
         eng, cfg = self.engine, self.engine.cfg
         dev = eng.device
         N = len(seqs)
+        if N == 0:       # the predictor returns before touching the model on empty input (surya/recognition/__init__.py:835-837)
+            return [], [], np.zeros((0, self.max_tokens, 6), dtype=np.int64)
         packed = None
         if not isinstance(tiles, (list, tuple)):
             packed = tiles if isinstance(tiles, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(tiles))

@@ -271,3 +271,23 @@ def test_fullsize_properties_synrec(built_lib):
         tokens_c, scores_c, bboxes_c = runner.run_preprocessed(tiles, grids, seqs, fixed_steps=True)
         assert tokens_c == tokens and scores_c == scores and np.array_equal(bboxes_c, bboxes), f"chains={chains}"
     eng.close()
+
+
+def test_empty_single_and_ragged_batches(built_lib):
+    """Edge cases of the runner: no crops, one crop, more crops than batch rows with ragged widths (prompts of different
+    lengths, different window counts) — every crop must decode exactly as it does alone."""
+    from surya_b200.config import tiny_rec
+    from surya_b200.recognition import RecognitionRunner
+    from surya_b200.synth import rec_state_dict, rec_synthetic_crops
+
+    cfg = tiny_rec()
+    eng = _engine(cfg, rec_state_dict(cfg, seed=0), torch.float16, max_slots=8, s_max=160, max_patches=4096, max_tokens=1024)
+    runner = RecognitionRunner(eng, batch_size=3, max_tokens=6)
+    tok, sc, bb = runner.run([])
+    assert tok == [] and sc == [] and bb.shape == (0, 6, 6)
+    crops = [rec_synthetic_crops(1, h, w, seed=s)[0] for s, (h, w) in enumerate([(48, 512), (40, 300), (64, 900), (48, 512), (32, 200), (56, 700), (48, 640)])]
+    alone = [runner.run([c], fixed_steps=True) for c in crops]
+    tok, sc, bb = runner.run(crops, fixed_steps=True)      # 7 crops through 3 batch rows: slots are recycled
+    for i in range(len(crops)):
+        assert tok[i] == alone[i][0][0] and sc[i] == alone[i][1][0] and np.array_equal(bb[i], alone[i][2][0]), i
+    eng.close()
