@@ -304,20 +304,41 @@ __global__ void argmax_score_kernel(const T* __restrict__ logits, int ld, int V,
   int mi = 0x7fffffff;
   float s = 0.f;  // running sum of exp(l - m)
   const int nv = V >> 3;
-  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-    uint4 u = *reinterpret_cast<const uint4*>(l + i * 8);
-    const T* e = reinterpret_cast<const T*>(&u);
+  // Chunks of CH 16-byte vectors per thread: all loads of a chunk are issued first, then the chunk maximum, then CH*8
+  // independent exps against it — one rescale of the running sum per chunk instead of a dependent exp per element.
+  constexpr int CH = 8;
+  for (int i0 = threadIdx.x; i0 < nv; i0 += blockDim.x * CH) {
+    uint4 u[CH];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = to_f<T>(e[j]);
-      if (v > m) {
-        s = s * __expf(m - v) + 1.f;
-        m = v;
-        mi = i * 8 + j;
-      } else {
-        s += __expf(v - m);
+    for (int c = 0; c < CH; ++c) {
+      const int i = i0 + c * blockDim.x;
+      if (i < nv) u[c] = *reinterpret_cast<const uint4*>(l + static_cast<size_t>(i) * 8);
+    }
+    float cm = -INFINITY;
+    int ci = 0x7fffffff;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int i = i0 + c * blockDim.x;
+      if (i >= nv) break;
+      const T* e = reinterpret_cast<const T*>(&u[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = to_f<T>(e[j]);
+        if (v > cm) { cm = v; ci = i * 8 + j; }      // ascending index within the thread: first maximum wins
       }
     }
+    if (cm == -INFINITY) continue;                    // all -inf (or empty): contributes nothing
+    if (cm > m) { s *= __expf(m - cm); m = cm; mi = ci; }
+    float add = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int i = i0 + c * blockDim.x;
+      if (i >= nv) break;
+      const T* e = reinterpret_cast<const T*>(&u[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) add += __expf(to_f<T>(e[j]) - m);
+    }
+    s += add;
   }
   for (int i = (nv << 3) + threadIdx.x; i < V; i += blockDim.x) {
     float v = to_f<T>(l[i]);
