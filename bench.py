@@ -204,7 +204,7 @@ def decode_gemm_roofline(eng, peaks, reps=20):
         add(x, w[1], qkv, bias=w[2])
         add(ao, w[3], x, residual=x)
         add(x, w[5], act, act="silu", swiglu=True)
-        add(act, w[6], x, residual=x)
+        add(act, w[6], x, residual=x, splitk=True)      # the engine's decode step lets the down projection use split-K
     add(x, eng.weights[8], logits, bias=eng.weights[9])
 
     def run():

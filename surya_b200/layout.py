@@ -36,6 +36,8 @@ def _sincos_table(width: int, height: int, dim: int) -> torch.Tensor:
 
 
 class LayoutEngine:
+    GRAPH_GROUP = 8      # decode steps per CUDA-graph replay in run_loop
+
     def __init__(self, cfg: LayoutConfig, sd_enc: Dict[str, torch.Tensor], sd_dec: Dict[str, torch.Tensor],
                  dtype: torch.dtype = torch.float16, device: str | torch.device = "cuda", max_batch: int = 16):
         _lib.load()
@@ -283,19 +285,27 @@ class LayoutEngine:
         st["pos"].fill_(q - 1)
         st["base"].fill_(q - 1)
         self._loop_body(st)                       # first step eagerly (also warms every kernel before a capture)
-        if n_steps > 1:
+        left = n_steps - 1
+        if left > 0:
             if use_graph:
                 if st["graph"] is None:
+                    # two graphs: GROUP steps per replay (one host launch per GROUP decode steps) and a single step for the tail
                     torch.cuda.synchronize(self.device)
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        self._loop_body(st)
-                    st["graph"] = g
-                    # the capture did not execute; positions/history are untouched
-                for _ in range(n_steps - 1):
-                    st["graph"].replay()
+                    graphs = {}
+                    for k in (self.GRAPH_GROUP, 1):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            for _ in range(k):
+                                self._loop_body(st)
+                        graphs[k] = g
+                    st["graph"] = graphs          # captures do not execute: positions / history are untouched
+                while left >= self.GRAPH_GROUP:
+                    st["graph"][self.GRAPH_GROUP].replay()
+                    left -= self.GRAPH_GROUP
+                for _ in range(left):
+                    st["graph"][1].replay()
             else:
-                for _ in range(n_steps - 1):
+                for _ in range(left):
                     self._loop_body(st)
         h = st["hist"]
         return h["tok"][:n_steps], h["bbox"][:n_steps], [x[:n_steps] for x in h["heads"]], h["done"][:n_steps]

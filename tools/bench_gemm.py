@@ -32,9 +32,12 @@ def timeit(fn, n=48, reps=5):
 def main():
     dt = torch.bfloat16
     shapes = [("qkv", 256, 1920, 1280, False), ("o", 256, 1280, 1280, False), ("gate_up", 256, 6848, 1280, True),
-              ("down", 256, 1280, 3424, False), ("layout_q", 16, 1024, 1024, False), ("layout_gu", 16, 8192, 1024, True)]
+              ("down", 256, 1280, 3424, False), ("lm_head", 256, 65792, 1280, False), ("layout_q", 16, 1024, 1024, False),
+              ("layout_gu", 16, 8192, 1024, True)]
+    if len(sys.argv) > 1:
+        shapes = [s for s in shapes if s[0] in sys.argv[1:]]
     for name, M, N, K, swi in shapes:
-        copies = max(2, int(300e6 // (N * K * 2)))          # > L2
+        copies = max(3, int(300e6 // (N * K * 2)))          # > L2
         ws = [torch.randn(N, K, device="cuda").to(dt) * 0.05 for _ in range(min(copies, 24))]
         a = torch.randn(M, K, device="cuda").to(dt)
         out = torch.empty(M, N // 2 if swi else N, device="cuda", dtype=dt)
