@@ -510,26 +510,38 @@ def main():
     ms_e2e_total = timed(e2e_step, max(1, min(args.steps, 3)))
     e2e_n = max(1, min(args.steps, 3))
     e2e_value = B_PER_GPU * world * e2e_n / (ms_e2e_total * 1e-3)
+    # secondary sections must never cost the headline line: a failure is reported inside the JSON instead (all ranks take the
+    # same path because the inputs are identical, so the collectives inside stay matched)
     det = None
     if not args.no_detection:
         log("detection (secondary metric)")
-        eng_ws = eng.workspace_bytes
-        det = detection_bench(dev, peaks, world, args.steps, args.warmup)
-        log(f"detection: {det['value']:.1f} pages/s resident, {det['e2e']['value']:.1f} e2e")
+        try:
+            det = detection_bench(dev, peaks, world, args.steps, args.warmup)
+            log(f"detection: {det['value']:.1f} pages/s resident, {det['e2e']['value']:.1f} e2e")
+        except Exception as e:      # noqa: BLE001
+            det = {"error": f"{type(e).__name__}: {e}"}
+            log(f"detection failed: {det['error']}")
     lay = None
     if not args.no_layout:
         lay = {}
         for kind in ("layout", "table"):
             log(f"{kind} (config 4)")
-            lay[kind] = layout_bench(dev, peaks, world, kind, args.steps, args.warmup)
-            log(f"{kind}: {lay[kind]['value']:.1f} pages/s (encoder {lay[kind]['phases_ms']['encoder']:.2f} ms, "
-                f"decode step {lay[kind]['phases_ms']['decode_step']:.3f} ms)")
+            try:
+                lay[kind] = layout_bench(dev, peaks, world, kind, args.steps, args.warmup)
+                log(f"{kind}: {lay[kind]['value']:.1f} pages/s (encoder {lay[kind]['phases_ms']['encoder']:.2f} ms, "
+                    f"decode step {lay[kind]['phases_ms']['decode_step']:.3f} ms)")
+            except Exception as e:      # noqa: BLE001
+                lay[kind] = {"error": f"{type(e).__name__}: {e}"}
+                log(f"{kind} failed: {lay[kind]['error']}")
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
         log(f"e2e {e2e_value:.1f} crops/s; roofline replay")
-        roof, gemm_ms = decode_gemm_roofline(eng, peaks)
-        roof["share_of_step"] = gemm_ms * (MAX_TOKENS - 1) / ms_step
+        try:
+            roof, gemm_ms = decode_gemm_roofline(eng, peaks)
+            roof["share_of_step"] = gemm_ms * (MAX_TOKENS - 1) / ms_step
+        except Exception as e:      # noqa: BLE001
+            roof = {"error": f"{type(e).__name__}: {e}"}
         # whole-step algorithmic bounds for context
         alg = {"decode_bytes_per_step_gb": 1.02, "decode_hbm_ms_at_peak": 1.02e9 * (MAX_TOKENS - 1) / (peaks["hbm_gbs"] * 1e9) * 1e3,
                "prefill_gflop_per_crop": 53.26 + 19.0, "prefill_tensor_ms_at_peak": (53.26 + 19.0) * B_PER_GPU / (peaks["tf_sustained"] * 1e3) * 1e3}
@@ -537,11 +549,14 @@ def main():
         if not args.no_cpu_baseline:
             threads = host_threads()
             log(f"cpu_baseline: oracle port on {threads} threads")
-            one = cpu_oracle_sample(CPU_CROPS, CPU_STEPS, threads)
-            t_run, t_full = one()
-            log(f"cpu_baseline: ran {t_run:.1f}s, full-length estimate {t_full:.1f}s")
-            cpu = {"value": CPU_CROPS / t_full, "unit": "crops/s", "cores": threads, "kind": "port",
-                   "sample": cpu_sample_text(CPU_CROPS, CPU_STEPS) + ", single timed run"}
+            try:
+                one = cpu_oracle_sample(CPU_CROPS, CPU_STEPS, threads)
+                t_run, t_full = one()
+                log(f"cpu_baseline: ran {t_run:.1f}s, full-length estimate {t_full:.1f}s")
+                cpu = {"value": CPU_CROPS / t_full, "unit": "crops/s", "cores": threads, "kind": "port",
+                       "sample": cpu_sample_text(CPU_CROPS, CPU_STEPS) + ", single timed run"}
+            except Exception as e:      # noqa: BLE001
+                cpu = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
