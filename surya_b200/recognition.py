@@ -610,17 +610,25 @@ class RecognitionRunner:
         scratch = eng.alloc_slots(1)[0]      # idle rows decode into a scratch slot (the reference decodes every row too)
         row_prompt: List[Optional[int]] = [None] * Bsz
         row_slot = [scratch] * Bsz
-        ids_io = torch.full((Bsz,), cfg.pad_token_id, dtype=torch.int64, device=dev)
-        pos_host = torch.zeros(Bsz, dtype=torch.int32).pin_memory()
-        slot_host = torch.zeros(Bsz, dtype=torch.int32).pin_memory()
-        pos_io = torch.zeros(Bsz, dtype=torch.int32, device=dev)
-        slot_t = torch.zeros(Bsz, dtype=torch.int32, device=dev)
-        # persistent history buffers: same pointers every call -> the captured decode graph is reused
+        # persistent per-runner buffers: same device pointers every call (the captured decode graph is reused) and no
+        # cudaHostAlloc / cudaMalloc on the per-batch path
         T = max(1, self.max_tokens)
-        hist = {"tok": torch.empty((T, Bsz), dtype=torch.int64, device=dev),
-                "score": torch.empty((T, Bsz), dtype=torch.float32, device=dev),
-                "bbox": torch.empty((T, Bsz, 6), dtype=torch.int64, device=dev),
-                "done": torch.empty((T, Bsz), dtype=torch.uint8, device=dev)}
+        bufs = getattr(self, "_bufs", None)
+        if bufs is None or bufs["key"] != (Bsz, T):
+            bufs = {"key": (Bsz, T),
+                    "ids_io": torch.empty((Bsz,), dtype=torch.int64, device=dev),
+                    "pos_host": torch.zeros(Bsz, dtype=torch.int32).pin_memory(),
+                    "slot_host": torch.zeros(Bsz, dtype=torch.int32).pin_memory(),
+                    "pos_io": torch.zeros(Bsz, dtype=torch.int32, device=dev),
+                    "slot_t": torch.zeros(Bsz, dtype=torch.int32, device=dev),
+                    "hist": {"tok": torch.empty((T, Bsz), dtype=torch.int64, device=dev),
+                             "score": torch.empty((T, Bsz), dtype=torch.float32, device=dev),
+                             "bbox": torch.empty((T, Bsz, 6), dtype=torch.int64, device=dev),
+                             "done": torch.empty((T, Bsz), dtype=torch.uint8, device=dev)}}
+            self._bufs = bufs
+        ids_io, pos_host, slot_host = bufs["ids_io"], bufs["pos_host"], bufs["slot_host"]
+        pos_io, slot_t, hist = bufs["pos_io"], bufs["slot_t"], bufs["hist"]
+        ids_io.fill_(cfg.pad_token_id)
 
         def finish(row):
             eng.release_slots([row_slot[row]])

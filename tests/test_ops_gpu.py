@@ -364,3 +364,37 @@ def test_gemm_splitk_cluster(built_lib, dtype, M, N, K, pk, bn, epi):
     ref = (y.float() + res.float()).to(dtype) if res is not None else y
     scale = torch.maximum(lin.float().abs(), res.float().abs()) if res is not None else None
     _close(out, ref, dtype, ulps=3.0, what=f"splitk {M}x{N}x{K} pk={pk} bn={bn} {epi}", scale=scale)
+
+
+# ------------------------------------------------------------------------------------------------ error behaviour
+def test_errors_are_loud(built_lib):
+    """Bad arguments come back as a negative code + message through the C ABI (raised as SuryaB200Error), never as a silent
+    fallback: misaligned TMA pitch, odd SwiGLU width, unsupported head_dim / GQA group, unsupported depthwise kernel size."""
+    from surya_b200 import _lib, ops
+
+    dt = torch.bfloat16
+    a = torch.randn(64, 100, device="cuda").to(dt)          # row pitch 200 B: not a multiple of 16
+    w = torch.randn(32, 100, device="cuda").to(dt)
+    with pytest.raises(_lib.SuryaB200Error, match="16B"):
+        ops.gemm(a, w)
+    a = torch.randn(64, 128, device="cuda").to(dt)
+    w = torch.randn(33, 128, device="cuda").to(dt)
+    with pytest.raises(_lib.SuryaB200Error, match="even N"):
+        ops.gemm(a, w, act="silu", swiglu=True)
+    B, nh, nkv, hd = 2, 6, 2, 72
+    qkv = torch.randn(B, (nh + 2 * nkv) * hd, device="cuda").to(dt)
+    kc = torch.zeros(B, nkv, 16, hd, device="cuda", dtype=dt)
+    slot = torch.arange(B, dtype=torch.int32, device="cuda")
+    pos = torch.zeros(B, dtype=torch.int32, device="cuda")
+    inv = torch.ones(hd // 2, device="cuda")
+    with pytest.raises(_lib.SuryaB200Error, match="head_dim"):
+        ops.decode_attn(qkv, kc, kc.clone(), slot, pos, inv, nh, nkv, hd, 1.0)
+    x = torch.randn(1, 8, 8, 16, device="cuda").half()
+    with pytest.raises(_lib.SuryaB200Error, match="kernel size"):
+        ops.dwconv_nhwc(x, torch.randn(49, 16, device="cuda").half(), None, 7, 1, 3, "none")
+    # and the library keeps working after an error
+    a = torch.randn(64, 128, device="cuda").to(dt)
+    w = torch.randn(32, 128, device="cuda").to(dt)
+    out = ops.gemm(a, w)
+    torch.cuda.synchronize()
+    _close(out, (a.float() @ w.float().t()).to(dt), dt, what="gemm after errors")
