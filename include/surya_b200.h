@@ -276,6 +276,55 @@ int sb_box_next_token(const float* bbox, const float* const* heads, const int* h
                       const int* hist_base, int hist_T, long long* hist_tok, float* hist_bbox, float* const* hist_heads,
                       unsigned char* hist_done, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ layout / table_rec engine
+ * Donut-Swin encoder + ADETR box decoder with the layer loops, workspaces, K/V caches and the greedy loop in C++
+ * (DonutSwinLayoutModel / DonutSwinModel.forward, surya/layout/model/encoder.py:33-81, surya/table_rec/model/encoder.py:35-87;
+ * SuryaLayoutDecoder / SuryaTableRecDecoder.forward, surya/layout/model/decoder.py:95-126, surya/table_rec/model/decoder.py:121-155;
+ * the predictors' step loops, surya/layout/__init__.py:106-137, surya/table_rec/__init__.py:33-131).
+ * Weight table (device pointers; 16-bit tensors in the engine dtype unless marked f32):
+ *   [SB_LW_PE_W] patch-embed weight [embed_dim, Kp] (K = in_ch*patch^2 zero-padded to a multiple of 64), [SB_LW_PE_B] bias f32,
+ *   [SB_LW_PE_LN_W/B] embeddings.norm, [SB_LW_ENC_POS] position_embeddings [enc_len, hidden];
+ *   per stage: sin-cos table [H*W, C]; per layer SB_LW_ENC_LAYER tensors in SB_LWE_* order (fused qkv [3C, C] + f32 bias,
+ *   relative_position_bias_table [225, nh], ...); per non-final stage: downsample.norm w, b, reduction [2C, 4C];
+ *   decoder: embedding tables (layout 15: w,h,cx,cy,xskew,yskew,x1..y4,label; table 13: w,h,cx,cy,xskew,yskew,x1,y1,x3,y3,
+ *   category,merge,colspan); per layer SB_LW_DEC_LAYER tensors in SB_LWD_* order (cross K|V fused [2*n_kv*64, enc_hidden],
+ *   self q|k|v fused, gate/up rows interleaved); tail in SB_LWX_* order (inv_freq f32);
+ *   heads: layout bbox_w, bbox_b, class_w; table bbox, category, merges, colspan, is_header. */
+enum { SB_LW_PE_W = 0, SB_LW_PE_B, SB_LW_PE_LN_W, SB_LW_PE_LN_B, SB_LW_ENC_POS, SB_LW_ENC_FIXED };
+enum { SB_LWE_LN1_W = 0, SB_LWE_LN1_B, SB_LWE_QKV_W, SB_LWE_QKV_B, SB_LWE_RPB, SB_LWE_O_W, SB_LWE_O_B, SB_LWE_LN2_W, SB_LWE_LN2_B,
+       SB_LWE_FC1_W, SB_LWE_FC1_B, SB_LWE_FC2_W, SB_LWE_FC2_B, SB_LW_ENC_LAYER };
+enum { SB_LW_ENC_MERGE = 3 };
+enum { SB_LWD_CROSS_NORM = 0, SB_LWD_SELF_NORM, SB_LWD_MLP_NORM, SB_LWD_CQ_W, SB_LWD_CKV_W, SB_LWD_CO_W, SB_LWD_CO_B, SB_LWD_SQKV_W,
+       SB_LWD_SO_W, SB_LWD_SO_B, SB_LWD_GU_W, SB_LWD_DOWN_W, SB_LW_DEC_LAYER };
+enum { SB_LWX_FINAL_NORM = 0, SB_LWX_OUT_LN_W, SB_LWX_OUT_LN_B, SB_LWX_INV_FREQ, SB_LW_DEC_TAIL };
+
+typedef struct sb_layout_config {
+  int dtype;                                   /* SB_DT_* */
+  int img_h, img_w, patch, in_ch, embed_dim, n_stages, depths[4], heads[4], window;
+  float enc_ln_eps;
+  int kind;                                    /* 0 = layout (BboxEmbedding, double residual flow), 1 = table_rec (LabelEmbedding) */
+  int dec_layers, hidden, inter, enc_hidden, n_heads, n_kv, head_dim;
+  float rms_eps, dec_ln_eps;
+  int double_residual, bbox_size, vocab, box_w, prop_w;
+  int n_out_heads, head_n[4];                  /* layout: {label_count}; table: {category, merges, 1 (colspan), is_header} */
+  int eos, pad;
+  int max_batch, s_max;
+} sb_layout_config;
+typedef struct sb_layout_engine sb_layout_engine;
+
+int sb_layout_create(const sb_layout_config* cfg, const void* const* weights, int n_weights, sb_layout_engine** out);
+void sb_layout_destroy(sb_layout_engine* e);
+size_t sb_layout_workspace_bytes(const sb_layout_engine* e);
+/* pixels NCHW [batch, in_ch, img_h, img_w] (engine dtype, or float32 when pixels_f32) -> enc_out [batch, Lk, hidden]. */
+int sb_layout_encode(sb_layout_engine* e, const void* pixels, int pixels_f32, int batch, void* enc_out, void* stream);
+/* One whole greedy pass on the device: cross K/V of `enc`, prompt [batch, q_len, 6 + n_out_heads] int64 fed position by
+ * position, then n_steps tokens (token formation, position advance and history append in sb_box_next_token's kernel; steps
+ * replayed as CUDA graphs of 8).  Histories (device): tok [n_steps, batch, ncol] i64, bbox [n_steps, batch, 6] f32,
+ * heads[k] [n_steps, batch, head_n[k]] f32, done [n_steps, batch] u8 (may be NULL for layout). */
+int sb_layout_decode(sb_layout_engine* e, const void* enc, int batch, const long long* prompt, int q_len, int n_steps,
+                     long long* hist_tok, float* hist_bbox, float* const* hist_heads, unsigned char* hist_done, int use_graph,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@ No PyTorch math on the forward path (torch = memory + streams), no import of ora
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from typing import Dict, List, Optional
 
@@ -21,6 +22,24 @@ import torch
 from . import _lib, ops
 from .config import LayoutConfig
 from .synth import LAYOUT_EMBED_TABLES, TABLE_HEADS
+
+
+class _LayoutCfgC(ctypes.Structure):
+    _fields_ = [
+        ("dtype", ctypes.c_int),
+        ("img_h", ctypes.c_int), ("img_w", ctypes.c_int), ("patch", ctypes.c_int), ("in_ch", ctypes.c_int),
+        ("embed_dim", ctypes.c_int), ("n_stages", ctypes.c_int), ("depths", ctypes.c_int * 4), ("heads", ctypes.c_int * 4),
+        ("window", ctypes.c_int), ("enc_ln_eps", ctypes.c_float),
+        ("kind", ctypes.c_int),
+        ("dec_layers", ctypes.c_int), ("hidden", ctypes.c_int), ("inter", ctypes.c_int), ("enc_hidden", ctypes.c_int),
+        ("n_heads", ctypes.c_int), ("n_kv", ctypes.c_int), ("head_dim", ctypes.c_int),
+        ("rms_eps", ctypes.c_float), ("dec_ln_eps", ctypes.c_float),
+        ("double_residual", ctypes.c_int), ("bbox_size", ctypes.c_int), ("vocab", ctypes.c_int), ("box_w", ctypes.c_int),
+        ("prop_w", ctypes.c_int),
+        ("n_out_heads", ctypes.c_int), ("head_n", ctypes.c_int * 4),
+        ("eos", ctypes.c_int), ("pad", ctypes.c_int),
+        ("max_batch", ctypes.c_int), ("s_max", ctypes.c_int),
+    ]
 
 
 def _sincos_table(width: int, height: int, dim: int) -> torch.Tensor:
@@ -39,8 +58,16 @@ class LayoutEngine:
     GRAPH_GROUP = 8      # decode steps per CUDA-graph replay in run_loop
 
     def __init__(self, cfg: LayoutConfig, sd_enc: Dict[str, torch.Tensor], sd_dec: Dict[str, torch.Tensor],
-                 dtype: torch.dtype = torch.float16, device: str | torch.device = "cuda", max_batch: int = 16):
-        _lib.load()
+                 dtype: torch.dtype = torch.float16, device: str | torch.device = "cuda", max_batch: int = 16,
+                 impl: str = "native"):
+        """impl = "native": layer loops, workspaces and the decode loop run inside libsurya_b200.so (sb_layout_*);
+        impl = "python": the same kernels launched op by op from this module (kept as the readable statement of the op
+        sequence and as a cross-check — results are bit-identical)."""
+        self.lib = _lib.load()
+        if impl not in ("native", "python"):
+            raise ValueError(impl)
+        self.impl = impl
+        self._h = None
         self.cfg, self.dtype, self.device, self.max_batch = cfg, dtype, torch.device(device), max_batch
         e, d = cfg.encoder, cfg.decoder
         dev = self.device
@@ -116,17 +143,102 @@ class LayoutEngine:
             self.bbox_w, self.bbox_b = T(sd_dec["bbox_head.weight"]), T(sd_dec["bbox_head.bias"])
         self.inv_freq = (1.0 / (d.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).to(dev)
         self.s_max = d.max_boxes + (72 if d.kind == "table" else 8)     # table prompts carry the query + column boxes
+        if impl == "native":
+            self._create_native()
         self._cache_batch = 0
         self.cross_kv: List[Optional[torch.Tensor]] = [None] * d.num_hidden_layers
         self.kcache: List[torch.Tensor] = []
         self.vcache: List[torch.Tensor] = []
         self.n_enc = 0
 
+    # ---------------------------------------------------------------------------------------------- native engine
+    def _weight_table(self) -> List[torch.Tensor]:
+        """Flat device-tensor list in the SB_LW_* order documented in include/surya_b200.h."""
+        d = self.cfg.decoder
+        w = [self.pe_w, self.pe_b, self.pe_ln[0], self.pe_ln[1], self.enc_pos]
+        for st in self.stages:
+            w.append(st["pos"])
+            for L in st["layers"]:
+                w += [L["ln1"][0], L["ln1"][1], L["qkv_w"], L["qkv_b"], L["rpb"], L["o_w"], L["o_b"], L["ln2"][0], L["ln2"][1],
+                      L["fc1_w"], L["fc1_b"], L["fc2_w"], L["fc2_b"]]
+            if "merge" in st:
+                w += [st["merge"]["ln"][0], st["merge"]["ln"][1], st["merge"]["w"]]
+        w += list(self.tables)
+        for L in self.layers:
+            w += [L["cross_norm"], L["self_norm"], L["mlp_norm"], L["cq_w"], L["ckv_w"], L["co_w"], L["co_b"], L["sqkv_w"],
+                  L["so_w"], L["so_b"], L["gu_w"], L["down_w"]]
+        w += [self.final_norm, self.out_ln[0], self.out_ln[1], self.inv_freq]
+        if self.kind == "table":
+            w += [self.head_w[k] for k in TABLE_HEADS]
+        else:
+            w += [self.bbox_w, self.bbox_b, self.cls_w]
+        return w
+
+    def _create_native(self):
+        e, d = self.cfg.encoder, self.cfg.decoder
+        c = _LayoutCfgC()
+        c.dtype = ops.dt_code(self.dtype)
+        c.img_h, c.img_w, c.patch, c.in_ch = e.image_size[0], e.image_size[1], e.patch_size, e.num_channels
+        c.embed_dim, c.n_stages, c.window, c.enc_ln_eps = e.embed_dim, len(e.depths), e.window_size, e.layer_norm_eps
+        for i, (dep, nh) in enumerate(zip(e.depths, e.num_heads)):
+            c.depths[i], c.heads[i] = dep, nh
+        c.kind = 1 if d.kind == "table" else 0
+        c.dec_layers, c.hidden, c.inter, c.enc_hidden = d.num_hidden_layers, d.hidden_size, d.intermediate_size, d.encoder_hidden_size
+        c.n_heads, c.n_kv, c.head_dim = d.num_attention_heads, d.num_key_value_heads, d.head_dim
+        c.rms_eps, c.dec_ln_eps = d.rms_norm_eps, d.layer_norm_eps
+        c.double_residual, c.bbox_size, c.vocab = int(d.double_residual_flow), d.bbox_size, d.vocab_size
+        c.box_w, c.prop_w = d.box_embed_size, d.property_embed_size
+        head_n = [d.category_count, d.merge_count, 1, d.header_count] if d.kind == "table" else [d.label_count]
+        c.n_out_heads = len(head_n)
+        for i, n in enumerate(head_n):
+            c.head_n[i] = n
+        c.eos, c.pad = d.eos_token_id, d.pad_token_id
+        c.max_batch, c.s_max = self.max_batch, self.s_max
+        self._wt = self._weight_table()          # keeps the device tensors alive
+        arr = (ctypes.c_void_p * len(self._wt))(*[t.data_ptr() for t in self._wt])
+        self._h = ctypes.c_void_p()
+        self.lib.sb_layout_workspace_bytes.restype = ctypes.c_size_t
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sb_layout_create(ctypes.byref(c), arr, ctypes.c_int(len(self._wt)), ctypes.byref(self._h)),
+                       "sb_layout_create")
+        self._head_n = head_n
+
+    def close(self):
+        if self._h:
+            self.lib.sb_layout_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # noqa: BLE001 - interpreter shutdown
+            pass
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.sb_layout_workspace_bytes(self._h)) if self._h else 0
+
     # ---------------------------------------------------------------------------------------------- encoder
     def encode(self, pixel_values: torch.Tensor) -> torch.Tensor:
         """DonutSwinLayoutModel.forward (surya/layout/model/encoder.py:33-81): NCHW pixels -> [B, L, hidden]."""
         e = self.cfg.encoder
         B, _, Hi, Wi = pixel_values.shape
+        if self.impl == "native" and B > 0:
+            if (Hi, Wi) != tuple(e.image_size):
+                raise _lib.SuryaB200Error(f"layout encoder expects {e.image_size} inputs, got {(Hi, Wi)}")
+            if not pixel_values.is_cuda:
+                pixel_values = pixel_values.to(self.device, non_blocking=True)
+            if pixel_values.dtype not in (torch.float32, self.dtype):
+                raise _lib.SuryaB200Error("pixel_values must be float32 or the engine dtype")
+            pixel_values = pixel_values.contiguous()
+            gh, gw = e.grid
+            Lk = (gh >> (len(e.depths) - 1)) * (gw >> (len(e.depths) - 1))
+            out = torch.empty((B, Lk, e.hidden_size), dtype=self.dtype, device=self.device)
+            for b0 in range(0, B, self.max_batch):
+                b1 = min(B, b0 + self.max_batch)
+                _lib.check(self.lib.sb_layout_encode(self._h, _lib.ptr(pixel_values[b0:b1]), ctypes.c_int(1 if pixel_values.dtype == torch.float32 else 0),
+                                                     ctypes.c_int(b1 - b0), _lib.ptr(out[b0:b1]), _lib.stream_ptr()), "sb_layout_encode")
+            return out
         if B == 0:
             raise _lib.SuryaB200Error("empty batch: the predictors return before calling the model (layout/__init__.py:193-195)")
         if (Hi, Wi) != tuple(e.image_size):
@@ -274,6 +386,26 @@ class LayoutEngine:
         q = prompt.shape[1]
         if q - 1 + n_steps > self.s_max:
             raise _lib.SuryaB200Error("prompt + steps exceed the allocated self-attention cache")
+        if self.impl == "native":
+            if B > self.max_batch:
+                raise _lib.SuryaB200Error(f"batch {B} exceeds the engine's max_batch {self.max_batch}")
+            hk = (B, n_steps)
+            hist = getattr(self, "_nhist", None)
+            if hist is None or hist["key"] != hk:       # persistent: same pointers -> the step graphs are reused
+                dev, ncol = self.device, d.token_width
+                hist = {"key": hk, "tok": torch.zeros((n_steps, B, ncol), dtype=torch.int64, device=dev),
+                        "bbox": torch.zeros((n_steps, B, 6), dtype=torch.float32, device=dev),
+                        "heads": [torch.zeros((n_steps, B, n), dtype=torch.float32, device=dev) for n in self._head_n],
+                        "done": torch.zeros((n_steps, B), dtype=torch.uint8, device=dev)}
+                self._nhist = hist
+            prompt_d = prompt.to(self.device, torch.int64).contiguous()
+            enc_c = enc.contiguous()
+            hp = (ctypes.c_void_p * 4)(*([t.data_ptr() for t in hist["heads"]] + [None] * (4 - len(hist["heads"]))))
+            _lib.check(self.lib.sb_layout_decode(self._h, _lib.ptr(enc_c), ctypes.c_int(B), _lib.ptr(prompt_d), ctypes.c_int(q),
+                                                 ctypes.c_int(n_steps), _lib.ptr(hist["tok"]), _lib.ptr(hist["bbox"]), hp,
+                                                 _lib.ptr(hist["done"]), ctypes.c_int(1 if use_graph else 0), _lib.stream_ptr()),
+                       "sb_layout_decode")
+            return hist["tok"], hist["bbox"], list(hist["heads"]), hist["done"]
         st = self._loop_state(B, Lk, n_steps)
         st["enc"].copy_(enc)
         enc2d = st["enc"].view(B * Lk, -1)
