@@ -49,7 +49,7 @@ struct sb_layout_engine {
   float* out_bbox = nullptr;           // [B, 6]
   float* out_head[4] = {nullptr, nullptr, nullptr, nullptr};
   unsigned char* done = nullptr;
-  int batch = 0, Lk = 0;
+  int Lk = 0;
   // graphs
   cudaGraphExec_t g_group = nullptr, g_one = nullptr;
   const void* graph_key[8] = {nullptr};
@@ -59,7 +59,6 @@ struct sb_layout_engine {
 
   int ncol() const { return 6 + c.n_out_heads; }
   // ---- weight table (see include/surya_b200.h)
-  int enc_layers_before(int stage) const { int n = 0; for (int s = 0; s < stage; ++s) n += c.depths[s]; return n; }
   const void* WF(int i) const { return w[i]; }
   int stage_base(int s) const {      // index of the stage's position table
     int idx = SB_LW_ENC_FIXED;
