@@ -17,6 +17,66 @@
 namespace sb {
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
+// A row is held in registers by LPR = min(32, C/8) lanes (one global read, two-pass statistics from registers); for narrow rows
+// (C = 128, 256) a warp normalises 32/LPR rows at once.  Rows wider than 8 * 32 * LN_MAXV elements take the streaming kernel.
+constexpr int LN_MAXV = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(128) layernorm_reg_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                            const T* __restrict__ b, T* __restrict__ y, int rows, int C, float eps,
+                                                            int lpr) {
+  const int lane = threadIdx.x & 31;
+  const int rows_per_warp = 32 / lpr;
+  const int sub = lane / lpr, sl = lane % lpr;
+  const long long warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long row = warp_id * rows_per_warp + sub;
+  const bool ok = row < rows;
+  const T* xr = x + (ok ? row : 0) * C;
+  uint4 v[LN_MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int it = 0; it < LN_MAXV; ++it) {
+    const int i = (it * lpr + sl) * 8;
+    v[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (ok && i < C) {
+      v[it] = *reinterpret_cast<const uint4*>(xr + i);
+      const T* e = reinterpret_cast<const T*>(&v[it]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += to_f<T>(e[j]);
+    }
+  }
+  for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int it = 0; it < LN_MAXV; ++it) {
+    const int i = (it * lpr + sl) * 8;
+    if (ok && i < C) {
+      const T* e = reinterpret_cast<const T*>(&v[it]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = to_f<T>(e[j]) - mean; q += d * d; }
+    }
+  }
+  for (int o = lpr >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+  if (!ok) return;
+  T* yr = y + row * C;
+#pragma unroll
+  for (int it = 0; it < LN_MAXV; ++it) {
+    const int i = (it * lpr + sl) * 8;
+    if (i < C) {
+      const uint4 wu = *reinterpret_cast<const uint4*>(w + i);
+      const uint4 bu = *reinterpret_cast<const uint4*>(b + i);
+      const T *e = reinterpret_cast<const T*>(&v[it]), *we = reinterpret_cast<const T*>(&wu), *be = reinterpret_cast<const T*>(&bu);
+      uint4 o;
+      T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) oe[j] = from_f<T>((to_f<T>(e[j]) - mean) * rstd * to_f<T>(we[j]) + to_f<T>(be[j]));
+      *reinterpret_cast<uint4*>(yr + i) = o;
+    }
+  }
+}
+
 template <typename T>
 __global__ void layernorm_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ b,
                                  T* __restrict__ y, int rows, int C, float eps) {
@@ -57,6 +117,17 @@ __global__ void layernorm_kernel(const T* __restrict__ x, const T* __restrict__ 
 int layernorm(int dtype, const void* x, const void* w, const void* b, void* y, int rows, int C, float eps, cudaStream_t st) {
   if (rows <= 0) return 0;
   if (C % 8) { set_error("layernorm: C must be a multiple of 8"); return -1; }
+  const int vecs = C / 8;
+  int lpr = 32;
+  while (lpr > 1 && (lpr >> 1) >= vecs) lpr >>= 1;       // smallest power of two >= vecs, capped at 32
+  if (vecs <= lpr * LN_MAXV && (vecs % lpr == 0 || lpr == 32)) {
+    const int rows_per_warp = 32 / lpr;
+    const long long warps = (static_cast<long long>(rows) + rows_per_warp - 1) / rows_per_warp;
+    dim3 grid(static_cast<unsigned>((warps + 3) / 4)), block(128);
+    if (dtype == DT_F16) layernorm_reg_kernel<__half><<<grid, block, 0, st>>>((const __half*)x, (const __half*)w, (const __half*)b, (__half*)y, rows, C, eps, lpr);
+    else layernorm_reg_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, rows, C, eps, lpr);
+    return launch_ok();
+  }
   dim3 grid((rows + 3) / 4), block(128);
   if (dtype == DT_F16) layernorm_kernel<__half><<<grid, block, 0, st>>>((const __half*)x, (const __half*)w, (const __half*)b, (__half*)y, rows, C, eps);
   else layernorm_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, rows, C, eps);
@@ -66,37 +137,42 @@ int layernorm(int dtype, const void* x, const void* w, const void* b, void* y, i
 // ------------------------------------------------------------------------------------------------ patch-embed im2col
 // in NCHW [B, Cin, H, W]; out [B*gh*gw, Kp]: column = c*P*P + ky*P + kx (Conv2d weight flatten order), zero padded to Kp.
 template <typename T, typename InT>
-__global__ void patch_gather_kernel(const InT* __restrict__ in, T* __restrict__ out, int B, int Cin, int H, int W, int P, int Kp) {
-  const int gh = H / P, gw = W / P;
-  const long long total = static_cast<long long>(B) * gh * gw * Kp;
-  const int K = Cin * P * P;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int col = idx % Kp;
-    const long long tok = idx / Kp;
+__global__ void __launch_bounds__(256) patch_gather_kernel(const InT* __restrict__ in, T* __restrict__ out, int Cin, int H, int W,
+                                                          int P, int Kp) {
+  // one thread = 8 consecutive output columns of one patch (16-byte store); (patch row, image) come from the grid
+  const int gw = W / P, gh = H / P;
+  const int groups = Kp >> 3;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= gw * groups) return;
+  const int g8 = t % groups, gx = t / groups;
+  const int gy = blockIdx.y, b = blockIdx.z;
+  const int K = Cin * P * P, PP = P * P;
+  uint4 pack;
+  T* pe = reinterpret_cast<T*>(&pack);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = g8 * 8 + j;
     float v = 0.f;
     if (col < K) {
-      const int c = col / (P * P), ky = (col / P) % P, kx = col % P;
-      const int gx = tok % gw, gy = (tok / gw) % gh;
-      const int b = tok / (static_cast<long long>(gw) * gh);
+      const int c = col / PP, r = col - c * PP;
+      const int ky = r / P, kx = r - ky * P;
       const InT* p = in + ((static_cast<size_t>(b) * Cin + c) * H + gy * P + ky) * W + gx * P + kx;
       if constexpr (sizeof(InT) == 4) v = static_cast<float>(*p); else v = to_f<InT>(*p);
     }
-    out[idx] = from_f<T>(v);
+    pe[j] = from_f<T>(v);
   }
+  *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * gh + gy) * gw + gx) * Kp + g8 * 8) = pack;
 }
 
 int patch_gather(int dtype, const void* in, int in_f32, void* out, int B, int Cin, int H, int W, int P, int Kp, cudaStream_t st) {
-  const long long total = static_cast<long long>(B) * (H / P) * (W / P) * Kp;
-  int grid = static_cast<int>((total + 255) / 256);
-  if (grid > num_sms() * 32) grid = num_sms() * 32;
-  if (dtype == DT_F16) {
-    if (in_f32) patch_gather_kernel<__half, float><<<grid, 256, 0, st>>>((const float*)in, (__half*)out, B, Cin, H, W, P, Kp);
-    else patch_gather_kernel<__half, __half><<<grid, 256, 0, st>>>((const __half*)in, (__half*)out, B, Cin, H, W, P, Kp);
-  } else {
-    if (in_f32) patch_gather_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const float*)in, (__nv_bfloat16*)out, B, Cin, H, W, P, Kp);
-    else patch_gather_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, Cin, H, W, P, Kp);
-  }
+  if (B <= 0) return 0;
+  if (H % P || W % P || Kp % 8 || Kp < Cin * P * P) { set_error("patch_gather: H, W multiples of P and Kp >= Cin*P*P, Kp %% 8 == 0"); return -1; }
+  if (B > 65535 || H / P > 65535) { set_error("patch_gather: batch / rows too large for the grid"); return -1; }
+  dim3 grid(((W / P) * (Kp / 8) + 255) / 256, H / P, B);
+#define PG(T_, I_) patch_gather_kernel<T_, I_><<<grid, 256, 0, st>>>((const I_*)in, (T_*)out, Cin, H, W, P, Kp)
+  if (dtype == DT_F16) { if (in_f32) PG(__half, float); else PG(__half, __half); }
+  else { if (in_f32) PG(__nv_bfloat16, float); else PG(__nv_bfloat16, __nv_bfloat16); }
+#undef PG
   return launch_ok();
 }
 

@@ -50,7 +50,23 @@ def det(batch: int = 4, size: int = 1024):
     torch.cuda.synchronize()
 
 
+def layout(batch: int = 16):
+    from surya_b200.config import layout_default
+    from surya_b200.layout import LayoutEngine, layout_greedy
+    from surya_b200.synth import adetr_layout_state_dict, layout_synthetic_pages, swin_state_dict
+
+    cfg = layout_default()
+    eng = LayoutEngine(cfg, swin_state_dict(cfg.encoder, 0), adetr_layout_state_dict(cfg.decoder, 0), dtype=torch.float16,
+                       max_batch=batch)
+    x = layout_synthetic_pages(batch, cfg.encoder.image_size, seed=3).half().cuda()
+    layout_greedy(eng, x, 3, use_graph=False)      # encoder + cross K/V + 3 eager decode steps
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
+    if "--layout" in sys.argv:
+        layout()
+        sys.exit(0)
     if "--det" in sys.argv:
         b = int(sys.argv[sys.argv.index("--batch") + 1]) if "--batch" in sys.argv else 4
         det(batch=b)
