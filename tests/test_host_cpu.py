@@ -267,3 +267,37 @@ def test_table_oracle_pinned_to_reference_golden():
     for k, v in g["heads"].items():
         assert (heads[k] - v).abs().max().item() < 1e-4, k
     assert torch.equal(tok, g["tokens"])
+
+
+def test_layout_weight_table_matches_the_c_abi_layout():
+    """LayoutEngine._weight_table order / count vs the SB_LW_* layout in include/surya_b200.h (what sb_layout_create checks)."""
+    import re
+
+    from surya_b200.config import layout_tiny, table_tiny
+    from surya_b200.layout import LayoutEngine
+    from surya_b200.synth import adetr_layout_state_dict, adetr_table_state_dict, swin_state_dict
+
+    hdr = (ROOT / "include" / "surya_b200.h").read_text()
+    def enum_size(last):      # value of the trailing enumerator = number of entries before it
+        body = re.search(r"enum \{([^}]*\b%s\b)[^}]*\}" % last, hdr).group(1)
+        return len([x for x in body.split(",") if x.strip()]) - 1
+
+    n_fixed, n_layer, n_dec, n_tail = enum_size("SB_LW_ENC_FIXED"), enum_size("SB_LW_ENC_LAYER"), enum_size("SB_LW_DEC_LAYER"), enum_size("SB_LW_DEC_TAIL")
+    assert (n_fixed, n_layer, n_dec, n_tail) == (5, 13, 12, 4)
+    for cfg, sdd, tables, heads in ((layout_tiny(), adetr_layout_state_dict, 15, 3), (table_tiny(), adetr_table_state_dict, 13, 5)):
+        eng = LayoutEngine.__new__(LayoutEngine)          # pack on the CPU without creating the CUDA engine
+        import surya_b200.layout as LM
+        orig = LM._lib.load
+        LM._lib.load = lambda *a, **k: None
+        try:
+            LayoutEngine.__init__(eng, cfg, swin_state_dict(cfg.encoder, 0), sdd(cfg.decoder, 0), device="cpu", impl="python")
+        finally:
+            LM._lib.load = orig
+        w = eng._weight_table()
+        e, d = cfg.encoder, cfg.decoder
+        want = n_fixed + sum(1 + dep * n_layer for dep in e.depths) + 3 * (len(e.depths) - 1) + tables + d.num_hidden_layers * n_dec + n_tail + heads
+        assert len(w) == want
+        assert w[0].shape == (e.embed_dim, 64) and w[4].shape == (e.encoder_length, e.hidden_size)
+        assert w[5].shape == (e.grid[0] * e.grid[1], e.embed_dim)                      # stage-0 sin-cos table
+        assert w[5 + 1 + 2].shape == (3 * e.embed_dim, e.embed_dim)                     # fused qkv of the first layer
+        assert w[-heads].shape[0] == 6                                                  # bbox head first
