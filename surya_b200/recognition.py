@@ -642,8 +642,11 @@ class RecognitionRunner:
                     take = [queue.popleft() for _ in range(min(len(empty), len(queue)))]
                     rows = empty[: len(take)]
                     new_slots = eng.alloc_slots(len(take))
+                    tl = tiles_for(take)
+                    if not tl.is_cuda:         # start the (pinned, asynchronous) upload first; the index plan is built meanwhile
+                        tl = tl.to(dev, non_blocking=True)
                     plan = build_prefill_plan(cfg, np.array([grids[i] for i in take]), [seqs[i] for i in take], new_slots)
-                    out = eng.prefill(tiles_for(take), plan)
+                    out = eng.prefill(tl, plan)
                     ids_io[torch.tensor(rows, dtype=torch.int64, device=dev)] = out["next_ids"]
                     tok_h, sc_h, bb_h = out["tok"].cpu().numpy(), out["score"].cpu().numpy(), out["bbox"].cpu().numpy()
                     for j, (r, p) in enumerate(zip(rows, take)):
