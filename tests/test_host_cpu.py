@@ -301,3 +301,36 @@ def test_layout_weight_table_matches_the_c_abi_layout():
         assert w[5].shape == (e.grid[0] * e.grid[1], e.embed_dim)                      # stage-0 sin-cos table
         assert w[5 + 1 + 2].shape == (3 * e.embed_dim, e.embed_dim)                     # fused qkv of the first layer
         assert w[-heads].shape[0] == 6                                                  # bbox head first
+
+
+def test_prefill_plan_random_grids_property():
+    """Randomised ragged batches: window permutation is a permutation, windows tile the patch range, image segments follow the
+    grids, and every image token reads a distinct merged-feature row — checked against the oracle's index math."""
+    from oracle import rec_oracle as O
+    from surya_b200.config import tiny_rec
+    from surya_b200.recognition import build_prefill_plan, prompt_tokens
+
+    cfg = tiny_rec()
+    e = cfg.vision_encoder
+    rng = np.random.default_rng(7)
+    for _ in range(25):
+        n = int(rng.integers(1, 6))
+        grids = [(1, int(2 * rng.integers(1, 10)), int(2 * rng.integers(1, 38))) for _ in range(n)]
+        g = np.array(grids, dtype=np.int64)
+        seqs = [prompt_tokens(cfg, int(h * w) // 4) for _, h, w in grids]
+        slots = list(rng.permutation(16)[:n])
+        plan = build_prefill_plan(cfg, g, seqs, slots=[int(s) for s in slots])
+        ints = plan.ints.numpy()
+        arr = lambda name: ints[plan.off[name][0]: plan.off[name][0] + plan.off[name][1]]
+        total = int((g[:, 1] * g[:, 2]).sum())
+        perm = arr("patch_perm")
+        assert sorted(perm.tolist()) == list(range(total))
+        widx, cu_win = O.vision_window_index(g, e.window_size, e.spatial_merge_size, e.patch_size)
+        assert np.array_equal(perm, np.arange(total).reshape(total // 4, 4)[widx].reshape(-1))
+        assert np.array_equal(np.concatenate([arr("win_start"), [total]]), cu_win) and (arr("win_len") > 0).all()
+        assert int(arr("win_len").sum()) == total and int(arr("img_len").sum()) == total
+        ids = np.concatenate(seqs)
+        fr = arr("feat_row")[ids == cfg.image_token_id]
+        assert sorted(fr.tolist()) == list(range(total // 4))
+        lens = np.array([len(s) for s in seqs])
+        assert np.array_equal(arr("tok_slot"), np.repeat(np.array(slots, dtype=np.int64), lens))
