@@ -566,16 +566,32 @@ class RecognitionRunner:
     def __init__(self, engine: RecEngine, batch_size: int = 256, max_tokens: int = 128, poll: int = 8):
         self.engine, self.batch_size, self.max_tokens, self.poll = engine, batch_size, max_tokens, max(1, poll)
 
-    def preprocess(self, crops: Sequence[np.ndarray], math_mode: bool = True):
+    def preprocess(self, crops: Sequence[np.ndarray], math_mode: bool = True, workers: Optional[int] = None):
+        """Host side of SuryaOCRProcessor for one crop each (scale_to_fit -> resize to x28 -> normalise -> merge-block-major
+        tiles, processor/__init__.py:140-230) — the OpenCV resizes release the GIL, so crops are processed by a small thread
+        pool; results are in input order and identical to the serial loop."""
         cfg = self.engine.cfg
-        tiles, grids, seqs = [], [], []
-        for crop in crops:
+
+        def one(crop):
             img = scale_to_fit(np.asarray(crop, dtype=np.float32), (1024, 256))
             t, g = tile_image(img, cfg.vision_encoder.patch_size, cfg.merge_size)
-            tiles.append(t)
-            grids.append(g)
-            seqs.append(prompt_tokens(cfg, t.shape[0] // cfg.merge_size ** 2, math_mode))
-        return tiles, grids, seqs
+            return t, g, prompt_tokens(cfg, t.shape[0] // cfg.merge_size ** 2, math_mode)
+
+        n = len(crops)
+        if workers is None:
+            import os
+            try:
+                avail = len(os.sched_getaffinity(0))
+            except AttributeError:
+                avail = os.cpu_count() or 1
+            workers = max(1, min(16, avail, n // 8))
+        if workers <= 1 or n < 16:
+            res = [one(c) for c in crops]
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=workers) as ex:
+                res = list(ex.map(one, crops))
+        return [r[0] for r in res], [r[1] for r in res], [r[2] for r in res]
 
     def run_preprocessed(self, tiles, grids, seqs, fixed_steps: bool = False):
         """tiles: per-crop list of [P_i, patch_dim] arrays, or ONE packed [sum P_i, patch_dim] array / torch tensor in crop

@@ -334,3 +334,19 @@ def test_prefill_plan_random_grids_property():
         assert sorted(fr.tolist()) == list(range(total // 4))
         lens = np.array([len(s) for s in seqs])
         assert np.array_equal(arr("tok_slot"), np.repeat(np.array(slots, dtype=np.int64), lens))
+
+
+def test_pooled_preprocess_equals_serial():
+    from surya_b200 import recognition as R
+    from surya_b200.config import tiny_rec
+    from surya_b200.synth import rec_synthetic_crops
+
+    class _E:
+        cfg = tiny_rec()
+
+    r = R.RecognitionRunner.__new__(R.RecognitionRunner)
+    r.engine = _E()
+    crops = list(rec_synthetic_crops(24, 48, 512, seed=1)) + list(rec_synthetic_crops(8, 40, 300, seed=2))
+    a, b = r.preprocess(crops, workers=1), r.preprocess(crops, workers=4)
+    assert a[1] == b[1]
+    assert all(np.array_equal(x, y) for x, y in zip(a[0], b[0])) and all(np.array_equal(x, y) for x, y in zip(a[2], b[2]))
