@@ -1,6 +1,6 @@
 // surya_b200 — layout / table_rec engine: Donut-Swin encoder + ADETR box decoder behind the C ABI (sb_layout_*).
 //
-// Same kernels and the same op order as the Python-driven path in surya_b200/layout.py (which stays as the readable
+// Same kernels and the same op order as the op-by-op path in surya_b200/layout.py (impl="ops": one C-ABI call per kernel; it stays as the readable
 // statement of the sequence and as a cross-check: tests require bit-identical results); here the layer loops, the
 // workspaces, the K/V caches and the greedy decode loop (one CUDA graph per 8 steps) live in C++ so that nothing on the
 // forward path depends on the host between the first and the last kernel.

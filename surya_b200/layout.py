@@ -61,10 +61,11 @@ class LayoutEngine:
                  dtype: torch.dtype = torch.float16, device: str | torch.device = "cuda", max_batch: int = 16,
                  impl: str = "native"):
         """impl = "native": layer loops, workspaces and the decode loop run inside libsurya_b200.so (sb_layout_*);
-        impl = "python": the same kernels launched op by op from this module (kept as the readable statement of the op
-        sequence and as a cross-check — results are bit-identical)."""
+        impl = "ops": the same CUDA kernels launched one C-ABI call at a time from this module (kept as the readable statement of
+        the op sequence and as a cross-check — results are bit-identical).  Both need the library and a GPU; neither does any
+        math in PyTorch."""
         self.lib = _lib.load()
-        if impl not in ("native", "python"):
+        if impl not in ("native", "ops"):
             raise ValueError(impl)
         self.impl = impl
         self._h = None

@@ -290,7 +290,7 @@ def test_layout_weight_table_matches_the_c_abi_layout():
         orig = LM._lib.load
         LM._lib.load = lambda *a, **k: None
         try:
-            LayoutEngine.__init__(eng, cfg, swin_state_dict(cfg.encoder, 0), sdd(cfg.decoder, 0), device="cpu", impl="python")
+            LayoutEngine.__init__(eng, cfg, swin_state_dict(cfg.encoder, 0), sdd(cfg.decoder, 0), device="cpu", impl="ops")
         finally:
             LM._lib.load = orig
         w = eng._weight_table()

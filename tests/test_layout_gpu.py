@@ -426,7 +426,7 @@ def test_native_engine_equals_op_by_op_path(built_lib, kind):
         cfg, g, sde, sdd, x, prompt = _table_tiny()
         prompt = prompt.cuda()
     nat = LayoutEngine(cfg, sde, sdd, dtype=torch.float16, impl="native", max_batch=4)
-    ref = LayoutEngine(cfg, sde, sdd, dtype=torch.float16, impl="python")
+    ref = LayoutEngine(cfg, sde, sdd, dtype=torch.float16, impl="ops")
     assert nat.workspace_bytes > 0
     x = x.cuda()
     enc_n, enc_p = nat.encode(x), ref.encode(x)
