@@ -84,3 +84,40 @@ def sharded_recognition(run_local: Callable[[List[int]], Tuple[List[List[int]], 
             scores[idx] = gathered[2][r][j, :L].tolist()
             bboxes[idx] = gathered[3][r][j].numpy()
     return tokens, scores, bboxes
+
+
+def page_slices(n_pages: int, n_ranks: int) -> List[Tuple[int, int]]:
+    """Contiguous page ranges per rank (detection / layout / table_rec: pages are equal-cost units),
+    sizes differing by at most one."""
+    base, extra = divmod(n_pages, n_ranks)
+    out, lo = [], 0
+    for r in range(n_ranks):
+        hi = lo + base + (1 if r < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def sharded_pages(run_local: Callable[[int, int], torch.Tensor], n_pages: int, device=None) -> torch.Tensor:
+    """Run `run_local(lo, hi)` -> tensor [hi - lo, ...] on this rank's page range and all-gather the per-page results of ALL
+    ranks in page order (detection heatmaps [n, 2, H/4, W/4], layout / table token histories [n, steps, cols], ...).
+    Shares are padded to the largest share so the collective has a fixed shape."""
+    rank, n_ranks = world()
+    slices = page_slices(n_pages, n_ranks)
+    lo, hi = slices[rank]
+    mine = run_local(lo, hi) if hi > lo else None
+    if n_ranks == 1:
+        return mine
+    # every rank needs the trailing shape / dtype even if its share is empty
+    meta = [None] * n_ranks
+    dist.all_gather_object(meta, None if mine is None else (tuple(mine.shape[1:]), str(mine.dtype).split(".")[-1]))
+    shape, dname = next(m for m in meta if m is not None)
+    dtype = getattr(torch, dname)
+    cap = max(h - l for l, h in slices)
+    dev = device if device is not None else (mine.device if mine is not None else "cpu")
+    buf = torch.zeros((cap,) + tuple(shape), dtype=dtype, device=dev)
+    if mine is not None:
+        buf[: hi - lo] = mine.to(dev)
+    outs = [torch.empty_like(buf) for _ in range(n_ranks)]
+    dist.all_gather(outs, buf)
+    return torch.cat([o[: h - l] for o, (l, h) in zip(outs, slices)], 0)

@@ -72,3 +72,37 @@ def test_sharded_gather_world2_matches_single_process():
         assert toks == ref[0]
         assert all(np.allclose(a, b) for a, b in zip(scs, ref[1]))
         assert boxsum == ref[2].sum()
+
+
+def _pages_worker(rank, world, port, n_pages, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from surya_b200.shard import sharded_pages
+
+    def run(lo, hi):
+        return torch.arange(lo, hi, dtype=torch.float32)[:, None, None] * torch.ones(1, 2, 3)
+
+    out = sharded_pages(run, n_pages)
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_page_slices_and_sharded_pages_world2():
+    from surya_b200.shard import page_slices, sharded_pages
+
+    assert page_slices(32, 8) == [(4 * r, 4 * r + 4) for r in range(8)]
+    assert page_slices(5, 2) == [(0, 3), (3, 5)] and page_slices(1, 2) == [(0, 1), (1, 1)]
+    ref = sharded_pages(lambda lo, hi: torch.arange(lo, hi, dtype=torch.float32)[:, None, None] * torch.ones(1, 2, 3), 5)
+    for n_pages in (5, 1):
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_pages_worker, args=(r, 2, port, n_pages, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=120) for _ in range(2)]
+        for p in procs:
+            p.join(timeout=60)
+        for _, out in res:
+            assert out.shape == (n_pages, 2, 3)
+            assert torch.equal(out, ref[:n_pages])
