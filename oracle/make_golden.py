@@ -155,6 +155,49 @@ def make_table_golden():
     print(f"[golden] table_tiny: tokens[0,:2]={g['tokens'][0, :2].tolist()}")
 
 
+def make_layout_variants_golden():
+    """Extra pins for the oracle only (CPU test): a NON-SQUARE Swin input (256x384: exercises the (W, H) order of the
+    sin-cos tables, window partition of unequal sides and the shift masks) and a table_rec CELL-pass prompt (query + 4 column
+    boxes, q_len = 7 prefill; table_rec/__init__.py:206-222, processor.py:78-82)."""
+    from oracle import layout_oracle as L
+    from surya_b200.config import AdetrConfig, LayoutConfig, SwinConfig, table_decoder
+    from surya_b200.synth import adetr_table_state_dict, layout_synthetic_pages, swin_state_dict, table_query_tokens
+
+    enc_cfg = SwinConfig(image_size=(256, 384), depths=(2, 2, 2, 2), encoder_length=96)
+    cfg = LayoutConfig(encoder=enc_cfg, decoder=table_decoder(2))
+    sde, sdd = swin_state_dict(enc_cfg, 3), adetr_table_state_dict(cfg.decoder, 3)
+    enc, dec = ref_shim.build_reference_table_models(cfg, sde, sdd)
+    x = layout_synthetic_pages(2, enc_cfg.image_size, seed=21)
+    d = cfg.decoder
+    q = table_query_tokens(d, 2)
+    rng = np.random.default_rng(5)
+    cols = []
+    for _ in range(4):
+        b = rng.integers(0, 1025, size=6).tolist()
+        cols.append(b + [2 + d.special_token_count, d.special_token_count, 0, d.special_token_count])
+    ids = torch.cat([q, torch.tensor(cols, dtype=torch.long).unsqueeze(0).repeat(2, 1, 1)], dim=1)     # [2, 7, 10]
+    steps = 5
+    with torch.inference_mode():
+        ref_enc = enc(pixel_values=x).last_hidden_state
+        dec.model._setup_cache(dec.config, 2, "cpu", torch.float32)
+        pos = torch.ones_like(ids[0, :, 0], dtype=torch.int64).cumsum(0) - 1
+        cur, toks, heads = ids, [], []
+        for s in range(steps):
+            out = dec(input_ids=cur, encoder_hidden_states=ref_enc, cache_position=pos, use_cache=True, prefill=(s == 0))
+            pos = pos[-1:] + 1
+            logits = out["box_property_logits"]
+            tok, _ = L.table_next_tokens(logits, d)
+            cur = tok.unsqueeze(1)
+            toks.append(tok)
+            heads.append({k: v[:, -1].float().clone() for k, v in logits.items()})
+    g = {"encoder": ref_enc.float().clone(), "prompt": ids, "tokens": torch.stack(toks, 1),
+         "heads": {k: torch.stack([h[k] for h in heads], 1) for k in heads[0]},
+         "meta": {"kind": "table_nonsquare_cellpass", "steps": steps, "seed": 3, "page_seed": 21, "image_size": [256, 384],
+                  "torch": str(torch.__version__), "reference": "VikParuchuri/surya@80e9a7e (v0.14.6), fp32 CPU"}}
+    torch.save(g, GOLDEN / "table_nonsquare_cellpass.pt")
+    print(f"[golden] table_nonsquare_cellpass: enc {tuple(ref_enc.shape)} tokens[0,0]={g['tokens'][0, 0].tolist()}")
+
+
 def make_det_golden():
     """Reference EfficientViT segmentation logits for one seeded 512x512 page (surya/detection/__init__.py:94-104)."""
     from surya_b200.config import det_default
@@ -182,6 +225,7 @@ def main():
         make_layout_golden()
     if "table" in which:
         make_table_golden()
+        make_layout_variants_golden()
     if "det" in which:
         make_det_golden()
     if "rec" not in which:

@@ -446,3 +446,29 @@ def test_native_engine_equals_op_by_op_path(built_lib, kind):
 def _flatten(res):
     tok, bbox, heads, done = res
     return [tok, bbox] + list(heads) + [done]
+
+
+def test_nonsquare_encoder_and_cellpass_prompt_vs_reference_golden(built_lib):
+    """256x384 input (non-square Swin grid) and a 7-token table_rec cell-pass prompt, both against the second reference
+    fixture: encoder states, then the heads of the first generated position after the multi-token prompt."""
+    from surya_b200.config import LayoutConfig, SwinConfig, table_decoder
+    from surya_b200.layout import LayoutEngine
+    from surya_b200.synth import adetr_table_state_dict, layout_synthetic_pages, swin_state_dict
+
+    g = torch.load(GOLDEN / "table_nonsquare_cellpass.pt")
+    enc_cfg = SwinConfig(image_size=tuple(g["meta"]["image_size"]), depths=(2, 2, 2, 2), encoder_length=96)
+    cfg = LayoutConfig(encoder=enc_cfg, decoder=table_decoder(2))
+    sde, sdd = swin_state_dict(enc_cfg, g["meta"]["seed"]), adetr_table_state_dict(cfg.decoder, g["meta"]["seed"])
+    x = layout_synthetic_pages(2, enc_cfg.image_size, seed=g["meta"]["page_seed"])
+    for impl in ("native", "ops"):
+        eng = LayoutEngine(cfg, sde, sdd, dtype=torch.float16, impl=impl, max_batch=2)
+        enc = eng.encode(x.cuda())
+        ref = g["encoder"]
+        rel = ((enc.float().cpu() - ref).norm() / ref.norm()).item()
+        assert enc.shape == ref.shape and rel < 5e-3, (impl, rel)
+        tok, bbox, heads, done = eng.run_loop(ref.to(torch.float16).cuda(), g["prompt"].cuda(), 1, use_graph=False)
+        got = {"bbox": bbox[0], "category": heads[0][0], "merges": heads[1][0], "colspan": heads[2][0], "is_header": heads[3][0]}
+        for k, v in got.items():
+            err = (v.cpu() - g["heads"][k][:, 0]).abs().max().item()
+            assert err < 1e-2 * max(1.0, g["heads"][k].abs().max().item()), (impl, k, err)
+        eng.close()
