@@ -156,14 +156,14 @@ def make_table_golden():
 
 
 def make_layout_variants_golden():
-    """Extra pins for the oracle only (CPU test): a NON-SQUARE Swin input (256x384: exercises the (W, H) order of the
+    """Extra pins for the oracle only (CPU test): a NON-SQUARE Swin input (256x512: exercises the (W, H) order of the
     sin-cos tables, window partition of unequal sides and the shift masks) and a table_rec CELL-pass prompt (query + 4 column
     boxes, q_len = 7 prefill; table_rec/__init__.py:206-222, processor.py:78-82)."""
     from oracle import layout_oracle as L
     from surya_b200.config import AdetrConfig, LayoutConfig, SwinConfig, table_decoder
     from surya_b200.synth import adetr_table_state_dict, layout_synthetic_pages, swin_state_dict, table_query_tokens
 
-    enc_cfg = SwinConfig(image_size=(256, 384), depths=(2, 2, 2, 2), encoder_length=96)
+    enc_cfg = SwinConfig(image_size=(256, 512), depths=(2, 2, 2, 2), encoder_length=128)
     cfg = LayoutConfig(encoder=enc_cfg, decoder=table_decoder(2))
     sde, sdd = swin_state_dict(enc_cfg, 3), adetr_table_state_dict(cfg.decoder, 3)
     enc, dec = ref_shim.build_reference_table_models(cfg, sde, sdd)
@@ -192,7 +192,7 @@ def make_layout_variants_golden():
             heads.append({k: v[:, -1].float().clone() for k, v in logits.items()})
     g = {"encoder": ref_enc.float().clone(), "prompt": ids, "tokens": torch.stack(toks, 1),
          "heads": {k: torch.stack([h[k] for h in heads], 1) for k in heads[0]},
-         "meta": {"kind": "table_nonsquare_cellpass", "steps": steps, "seed": 3, "page_seed": 21, "image_size": [256, 384],
+         "meta": {"kind": "table_nonsquare_cellpass", "steps": steps, "seed": 3, "page_seed": 21, "image_size": [256, 512],
                   "torch": str(torch.__version__), "reference": "VikParuchuri/surya@80e9a7e (v0.14.6), fp32 CPU"}}
     torch.save(g, GOLDEN / "table_nonsquare_cellpass.pt")
     print(f"[golden] table_nonsquare_cellpass: enc {tuple(ref_enc.shape)} tokens[0,0]={g['tokens'][0, 0].tolist()}")

@@ -353,19 +353,19 @@ def test_pooled_preprocess_equals_serial():
 
 
 def test_oracle_pinned_nonsquare_swin_and_cellpass_prompt():
-    """Second table_rec fixture from the reference: 256x384 input (non-square windows / sin-cos order / shift masks) and a
+    """Second table_rec fixture from the reference: 256x512 input (non-square windows / sin-cos order / shift masks) and a
     7-token cell-pass prompt (query + 4 column boxes) prefilled in one call."""
     from oracle import layout_oracle as L
     from surya_b200.config import LayoutConfig, SwinConfig, table_decoder
     from surya_b200.synth import adetr_table_state_dict, layout_synthetic_pages, swin_state_dict
 
     g = torch.load(GOLDEN / "table_nonsquare_cellpass.pt")
-    enc_cfg = SwinConfig(image_size=tuple(g["meta"]["image_size"]), depths=(2, 2, 2, 2), encoder_length=96)
+    enc_cfg = SwinConfig(image_size=tuple(g["meta"]["image_size"]), depths=(2, 2, 2, 2), encoder_length=128)
     cfg = LayoutConfig(encoder=enc_cfg, decoder=table_decoder(2))
     sde, sdd = swin_state_dict(enc_cfg, g["meta"]["seed"]), adetr_table_state_dict(cfg.decoder, g["meta"]["seed"])
     x = layout_synthetic_pages(2, enc_cfg.image_size, seed=g["meta"]["page_seed"])
     tok, done, enc, heads = L.table_greedy(sde, sdd, cfg, x, g["prompt"], g["meta"]["steps"])
-    assert enc.shape == g["encoder"].shape == (2, 96, 1024)
+    assert enc.shape == g["encoder"].shape == (2, 128, 1024)
     assert (enc - g["encoder"]).abs().max().item() < 1e-5
     for k, v in g["heads"].items():
         assert (heads[k] - v).abs().max().item() < 1e-4, k

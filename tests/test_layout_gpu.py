@@ -449,14 +449,14 @@ def _flatten(res):
 
 
 def test_nonsquare_encoder_and_cellpass_prompt_vs_reference_golden(built_lib):
-    """256x384 input (non-square Swin grid) and a 7-token table_rec cell-pass prompt, both against the second reference
+    """256x512 input (non-square Swin grid) and a 7-token table_rec cell-pass prompt, both against the second reference
     fixture: encoder states, then the heads of the first generated position after the multi-token prompt."""
     from surya_b200.config import LayoutConfig, SwinConfig, table_decoder
     from surya_b200.layout import LayoutEngine
     from surya_b200.synth import adetr_table_state_dict, layout_synthetic_pages, swin_state_dict
 
     g = torch.load(GOLDEN / "table_nonsquare_cellpass.pt")
-    enc_cfg = SwinConfig(image_size=tuple(g["meta"]["image_size"]), depths=(2, 2, 2, 2), encoder_length=96)
+    enc_cfg = SwinConfig(image_size=tuple(g["meta"]["image_size"]), depths=(2, 2, 2, 2), encoder_length=128)
     cfg = LayoutConfig(encoder=enc_cfg, decoder=table_decoder(2))
     sde, sdd = swin_state_dict(enc_cfg, g["meta"]["seed"]), adetr_table_state_dict(cfg.decoder, g["meta"]["seed"])
     x = layout_synthetic_pages(2, enc_cfg.image_size, seed=g["meta"]["page_seed"])
