@@ -370,3 +370,24 @@ def test_oracle_pinned_nonsquare_swin_and_cellpass_prompt():
     for k, v in g["heads"].items():
         assert (heads[k] - v).abs().max().item() < 1e-4, k
     assert torch.equal(tok, g["tokens"])
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The bench lines committed under profiles/ carry every key the driver's contract names (schema guard for bench.py)."""
+    import json
+
+    for name in ("r01_final_bench_n1.json", "r01_final_bench_n2.json", "r01_final_bench_n4.json"):
+        d = json.loads((ROOT / "profiles" / name).read_text())
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                  "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+            assert k in d, (name, k)
+        assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
+        assert "workload" in d["config"] and d["steps"] >= 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+        assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+        assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+        assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
+        if d["n_gpus"] == 1:
+            assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "port"
+            assert d["roofline"]["traffic"] is not None
