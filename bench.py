@@ -435,6 +435,7 @@ def main():
     plan.ids = plan.ids.to(dev)
     slot_t = torch.tensor(slots, dtype=torch.int32, device=dev)
     lens = torch.tensor([len(s) for s in seqs], dtype=torch.int32, device=dev)
+    max_len = max(len(s) for s in seqs)
     ids_io = torch.empty(B_PER_GPU, dtype=torch.int64, device=dev)
     pos_io = torch.empty(B_PER_GPU, dtype=torch.int32, device=dev)
     hist = {"tok": torch.empty((MAX_TOKENS - 1, B_PER_GPU), dtype=torch.int64, device=dev),
@@ -447,7 +448,7 @@ def main():
         out = eng.prefill(tiles_dev, plan)
         ids_io.copy_(out["next_ids"])
         pos_io.copy_(lens)
-        eng.decode_steps(ids_io, slot_t, pos_io, MAX_TOKENS - 1, hist=hist)
+        eng.decode_steps(ids_io, slot_t, pos_io, MAX_TOKENS - 1, hist=hist, max_pos=max_len)
         if world > 1:
             dist.all_gather(gather_buf, hist["tok"])
         return out
@@ -492,7 +493,7 @@ def main():
 
     def decode_only():
         pos_io.copy_(lens)
-        eng.decode_steps(ids_io, slot_t, pos_io, MAX_TOKENS - 1, hist=hist)
+        eng.decode_steps(ids_io, slot_t, pos_io, MAX_TOKENS - 1, hist=hist, max_pos=max_len)
 
     log(f"resident: {ms_step:.2f} ms/step -> {value:.1f} crops/s; phase split")
     ms_prefill = timed(prefill_only, 3) / 3

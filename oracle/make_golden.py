@@ -217,10 +217,41 @@ def make_det_golden():
     print(f"[golden] det_default: logits {tuple(logits.shape)} max={logits.max():.4f}")
 
 
+def trace_crops():
+    """Seeded crops of mixed widths for the predictor-trace golden: prompts of different lengths (left padding, merge offsets of
+    both signs) through 3 batch rows."""
+    widths = [512, 300, 700, 256, 900, 380, 620]
+    return [rec_synthetic_crops(1, 48, w, seed=200 + i)[0] for i, w in enumerate(widths)]
+
+
+def make_predictor_trace_golden():
+    """The reference's UNMODIFIED RecognitionPredictor.prediction_loop (prefill / decode / merge / maybe_trim_cache_padding,
+    surya/recognition/__init__.py:326-607) run over B200SuryaModel + SlotCache with the CPU oracle as the engine
+    (oracle/ref_predictors.py); every model call and cache operation is logged so the GPU test can replay the exact sequence
+    against the CUDA engine.  fp32, tiny config, 7 crops through 3 rows, max_tokens 10, trim threshold lowered to 2."""
+    from oracle import ref_predictors as RP
+
+    cfg = tiny_rec()
+    sd = rec_state_dict(cfg, seed=0)
+    t0 = time.time()
+    events, tokens, bboxes, scores, eng = RP.record_rec_trace(cfg, sd, trace_crops(), batch_size=3, max_tokens=10,
+                                                              min_trim_length=2)
+    assert len(eng.free_slots) == eng.max_slots, "the predictor run leaked KV slots"
+    g = {"events": events, "tokens": tokens, "scores": scores, "bboxes": bboxes,
+         "meta": {"kind": "rec_predictor_trace", "batch_size": 3, "max_tokens": 10, "min_trim_length": 2, "seed": 0,
+                  "torch": str(torch.__version__), "reference": "VikParuchuri/surya@80e9a7e RecognitionPredictor.prediction_loop, fp32 CPU"}}
+    torch.save(g, GOLDEN / "rec_predictor_trace.pt")
+    kinds = [e["kind"] for e in events]
+    print(f"[golden] rec_predictor_trace: {time.time() - t0:.1f}s {len(events)} events "
+          f"({kinds.count('prefill')} prefill, {kinds.count('decode')} decode, merges "
+          f"{[(e['idxs'], e['offset']) for e in events if e['kind'] == 'merge']}, trims {[e['n'] for e in events if e['kind'] == 'trim']}) "
+          f"tokens[0]={tokens[0]}")
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
-    which = set(sys.argv[1:]) or {"rec", "det", "layout", "table"}
+    which = set(sys.argv[1:]) or {"rec", "det", "layout", "table", "trace"}
     if "layout" in which:
         make_layout_golden()
     if "table" in which:
@@ -228,9 +259,11 @@ def main():
         make_layout_variants_golden()
     if "det" in which:
         make_det_golden()
+    if "trace" in which:
+        make_predictor_trace_golden()
     if "rec" not in which:
         return
-    for kind, cfg, steps in (("tiny", tiny_rec(), 12), ("synrec", syn_rec(), 3)):
+    for kind, cfg, steps in (("tiny", tiny_rec(), 32), ("synrec", syn_rec(), 40)):
         t0 = time.time()
         sd = rec_state_dict(cfg, seed=0)
         batch = O.build_batch(golden_crops(kind), cfg)

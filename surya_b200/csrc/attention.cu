@@ -284,6 +284,13 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const DecodeKParams p)
   const int slot = p.slot[b];
   const int pos = p.pos[b];
   const int n_keys = pos + 1;
+  if (pos < 0 || pos >= p.s_max) {
+    // the cache row is full (host-side callers reject this before launching, recognition.py / layout.py): never write past
+    // the slot — emit zeros so a caller that ignored the bound sees an obviously dead row instead of corrupting a neighbour
+    T* orow0 = reinterpret_cast<T*>(p.out) + static_cast<size_t>(b) * p.ldo + (blockIdx.y * G) * HD;
+    for (int i = threadIdx.x; i < G * HD; i += 128) orow0[i] = from_f<T>(0.f);
+    return;
+  }
   const T* row = reinterpret_cast<const T*>(p.qkv) + static_cast<size_t>(b) * p.ld;
   T* kc = reinterpret_cast<T*>(p.kcache) + (static_cast<size_t>(slot) * p.n_kv_heads + kvh) * p.s_max * HD;
   T* vc = reinterpret_cast<T*>(p.vcache) + (static_cast<size_t>(slot) * p.n_kv_heads + kvh) * p.s_max * HD;

@@ -296,11 +296,12 @@ def detect_heatmaps(engine: DetEngine, pixel_values: torch.Tensor, out_size: Tup
 
 
 def detect_pages_host(engine: DetEngine, pages_host: torch.Tensor, out_host: torch.Tensor | None = None, chunk: int = 8,
-                      out_size: Tuple[int, int] | None = None) -> torch.Tensor:
+                      out_size: Tuple[int, int] | None = None, sync: bool = True) -> torch.Tensor:
     """Host-to-host variant of detect_heatmaps for a whole batch (DetectionPredictor.batch_detection,
     surya/detection/__init__.py:94-132: pixel batch up, fp32 full-resolution heatmaps down): the batch is cut into chunks and
     the upload of chunk i+1, the forward + upsample of chunk i and the download of chunk i-1 run on three streams, so PCIe
-    time hides behind the kernels.  pages_host: pinned NCHW fp16/fp32 [B,3,H,W]; returns pinned fp32 [B, labels, H, W]."""
+    time hides behind the kernels.  pages_host: pinned NCHW fp16/fp32 [B,3,H,W]; returns pinned fp32 [B, labels, H, W], complete
+    on return (sync=False returns after stream-ordering only: the caller must synchronise before touching the buffer)."""
     B, _, H, W = pages_host.shape
     size = out_size or (H, W)
     L = engine.cfg.num_labels
@@ -345,4 +346,10 @@ def detect_pages_host(engine: DetEngine, pages_host: torch.Tensor, out_host: tor
             ev_o[k].record(s_out)
     cur.wait_stream(s_out)
     cur.wait_stream(s_c)
+    if sync:
+        # host-to-host contract: the caller reads out_host (e.g. `.numpy()`, like the reference after `.cpu()`) right away,
+        # so the last download must have landed, not merely be ordered on a stream
+        for ev in ev_o:
+            if ev is not None:
+                ev.synchronize()
     return out_host

@@ -261,7 +261,7 @@ class RecEngine:
     """Owns one sb_rec_engine (weights + KV slots + workspaces) on the current CUDA device."""
 
     def __init__(self, cfg: RecConfig, state_dict: Dict[str, torch.Tensor], dtype: torch.dtype = torch.bfloat16,
-                 device: str | torch.device = "cuda", max_slots: int = 256, s_max: Optional[int] = None,
+                 device: str | torch.device = "cuda", max_slots: int = 257, s_max: Optional[int] = None,
                  max_patches: int = 65536, max_tokens: int = 32768, max_seqs: Optional[int] = None,
                  packed_weights: Optional[List[torch.Tensor]] = None):
         self.lib = _lib.load()
@@ -270,6 +270,7 @@ class RecEngine:
         self.weights = packed_weights if packed_weights is not None else pack_rec_weights(state_dict, cfg, dtype, self.device)
         self.s_max = s_max or cfg.max_sequence_length
         self.max_slots = max_slots
+        self.max_patches, self.max_tokens = max_patches, max_tokens
         mask = 0
         for i in e.fullatt_block_indexes:
             mask |= 1 << i
@@ -350,9 +351,14 @@ class RecEngine:
         out["_keep"] = (tiles, ints, ids)
         return out
 
-    def decode(self, input_ids: torch.Tensor, slot: torch.Tensor, pos: torch.Tensor, want_logits: bool = False):
+    def decode(self, input_ids: torch.Tensor, slot: torch.Tensor, pos: torch.Tensor, want_logits: bool = False,
+               max_pos: Optional[int] = None):
         dev = self.device
         B = input_ids.numel()
+        if max_pos is None:
+            max_pos = int(pos.max().item()) if B else 0
+        if max_pos >= self.s_max:
+            raise _lib.SuryaB200Error(f"decode at position {max_pos} but the engine was built with s_max={self.s_max}")
         out = {
             "tok": torch.empty(B, dtype=torch.int64, device=dev), "score": torch.empty(B, dtype=torch.float32, device=dev),
             "bbox": torch.empty((B, 6), dtype=torch.int64, device=dev),
@@ -371,10 +377,18 @@ class RecEngine:
         check(self.lib.sb_rec_set_decode_chains(self._h, c_int(n)), "sb_rec_set_decode_chains")
 
     def decode_steps(self, ids_io: torch.Tensor, slot: torch.Tensor, pos_io: torch.Tensor, n_steps: int,
-                     hist: Optional[dict] = None, use_graph: bool = True):
-        """n_steps greedy steps on the device; ids_io / pos_io advance in place. Returns step-major histories."""
+                     hist: Optional[dict] = None, use_graph: bool = True, max_pos: Optional[int] = None):
+        """n_steps greedy steps on the device; ids_io / pos_io advance in place. Returns step-major histories.
+        max_pos: the largest value in pos_io as known by the host (callers that built pos_io on the host pass it for free);
+        the last step writes cache row max_pos + n_steps - 1, which must exist."""
         dev = self.device
         B = ids_io.numel()
+        if max_pos is None:
+            max_pos = int(pos_io.max().item()) if B else 0
+        if max_pos + n_steps > self.s_max:
+            raise _lib.SuryaB200Error(
+                f"decode would write KV row {max_pos + n_steps - 1} but the engine was built with s_max={self.s_max} "
+                "(prompt length + max_tokens must not exceed s_max)")
         if hist is None:
             hist = {
                 "tok": torch.empty((n_steps, B), dtype=torch.int64, device=dev),
@@ -398,42 +412,84 @@ class RecEngine:
 
 # ------------------------------------------------------------------------------------------------ model / cache mirrors
 class SlotCache:
-    """ContinuousBatchingCache stand-in (surya/recognition/cache.py:7-105): the KV data lives in engine slots,
-    so merge() re-points batch rows at the new sequences' slots and trim_left() has nothing to move."""
+    """ContinuousBatchingCache stand-in (surya/recognition/cache.py:7-105).  The KV data lives in engine slots (no left
+    padding is ever materialised), so merge() re-points batch rows at the new sequences' slots and trim_left() moves no
+    data.  What the predictor's own bookkeeping relies on is kept exact: the padded sequence length (`get_seq_length`,
+    advanced by every model call like DynamicCache.update does), the offset merge() returns (cache.py:70-77, consumed by
+    surya/recognition/__init__.py:447-457 to left-pad the attention masks) and truthiness (:424).
 
-    def __init__(self, engine: RecEngine):
+    Constructible without arguments because RecognitionPredictor.prefill builds its cache itself with
+    `ContinuousBatchingCache()` (:391-395): surya_b200.dropin.install() points that module-level name at this class
+    and B200SuryaModel binds the engine on first use."""
+
+    def __init__(self, engine: Optional[RecEngine] = None):
         self.engine = engine
         self.slots: Optional[torch.Tensor] = None  # int32 [B] on device
         self._host: List[int] = []
+        self._seen_tokens = 0
+
+    def bind(self, engine: RecEngine) -> "SlotCache":
+        if self.engine is not None and self.engine is not engine:
+            raise _lib.SuryaB200Error("SlotCache is already bound to another engine")
+        self.engine = engine
+        return self
 
     def __bool__(self):
         return self.slots is not None
 
-    def __len__(self):
-        return 0 if self.slots is None else int(self.slots.numel())
+    def __len__(self):   # DynamicCache.__len__ = number of layers holding data (cache.py:64-66 compares the two)
+        return 0 if self.slots is None or self.engine is None else self.engine.cfg.decoder.num_hidden_layers
 
-    def assign(self, slots: Sequence[int]):
+    def get_seq_length(self, layer_idx: int = 0) -> int:
+        return self._seen_tokens
+
+    @property
+    def batch_size(self) -> int:
+        return len(self._host)
+
+    def assign(self, slots: Sequence[int], seq_len: int = 0):
         self._host = [int(s) for s in slots]
         self.slots = torch.tensor(self._host, dtype=torch.int32, device=self.engine.device)
+        self._seen_tokens = int(seq_len)
+
+    def advance(self, n: int = 1):
+        self._seen_tokens += n
 
     def merge(self, new_cache: "SlotCache", merge_idxs: Sequence[int], device=None) -> int:
-        """cache.py:57-105 — rows merge_idxs now hold the new sequences; their previous slots are recycled."""
+        """cache.py:57-105 — rows merge_idxs now hold the new sequences (their previous slots are recycled); returns
+        current_seq_length - new_seq_length exactly like the reference, whose caller pads the masks with it."""
+        if not isinstance(new_cache, SlotCache):
+            raise _lib.SuryaB200Error("SlotCache.merge needs a SlotCache (call surya_b200.dropin.install() before prefill)")
+        merge_idxs = [int(i) for i in merge_idxs]
+        if len(merge_idxs) != len(new_cache._host):
+            raise _lib.SuryaB200Error(f"merge of {len(new_cache._host)} sequences into {len(merge_idxs)} rows")
+        offset = self._seen_tokens - new_cache._seen_tokens
+        if offset < 0:                       # the resident cache is the shorter one: it is (notionally) left-padded
+            self._seen_tokens += -offset
         old = [self._host[i] for i in merge_idxs]
         for i, s in zip(merge_idxs, new_cache._host):
             self._host[i] = s
         self.engine.release_slots(old)
         self.slots = torch.tensor(self._host, dtype=torch.int32, device=self.engine.device)
         new_cache.slots, new_cache._host = None, []
-        return 0  # no padding offset exists in a slot cache
+        return offset
 
-    def trim_left(self, n: int):
-        """cache.py:39-46 — left padding is never materialised, nothing to trim."""
-        return None
+    def trim_left(self, n):
+        """cache.py:39-46 — only the notional padded length changes; left padding is never materialised."""
+        self._seen_tokens -= int(n)
 
     def release(self):
-        if self._host:
+        if self._host and self.engine is not None:
             self.engine.release_slots(self._host)
         self._host, self.slots = [], None
+
+    def __del__(self):
+        # RecognitionPredictor.prediction_loop drops its cache with `del self.kv_cache` (surya/recognition/__init__.py:603-605)
+        # and never calls a release hook: the slots go back to the engine when the cache object dies.
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 class _Cfg:
@@ -444,7 +500,8 @@ class _Cfg:
 
 class B200SuryaModel:
     """Call-compatible with the attributes RecognitionPredictor touches on `self.model`
-    (surya/recognition/__init__.py:112, 296-297, 315, 332-339, 398-409): __call__, .config.bbox_size, .device, .dtype."""
+    (surya/recognition/__init__.py:112, 296-297, 315, 332-339, 398-409): __call__, .config.bbox_size, .device, .dtype.
+    `engine` is a RecEngine (or any object with its prefill / decode / alloc_slots / release_slots surface)."""
 
     def __init__(self, engine: RecEngine):
         self.engine = engine
@@ -466,28 +523,44 @@ class B200SuryaModel:
                  encoder_chunk_size=None, **kwargs):
         if inputs_embeds is not None:
             raise NotImplementedError("inputs_embeds is not part of the predictor call surface")
-        if past_key_values is None:
-            raise _lib.SuryaB200Error("B200SuryaModel needs a SlotCache as past_key_values (use model.new_cache())")
+        if not isinstance(past_key_values, SlotCache):
+            raise _lib.SuryaB200Error(
+                "B200SuryaModel needs a SlotCache as past_key_values: call surya_b200.dropin.install() once so that "
+                "RecognitionPredictor.prefill's `ContinuousBatchingCache()` builds one (or pass model.new_cache())")
+        cache = past_key_values.bind(self.engine)
         eng, cfg = self.engine, self.engine.cfg
         B, S = input_ids.shape
         if S > 1 or image_tiles is not None:      # ---- prefill
+            if cache:
+                raise _lib.SuryaB200Error("prefill into a non-empty cache: the predictor prefills a fresh cache and merges it")
             ids_h = input_ids.detach().cpu().numpy()
             m_h = attention_mask.detach().cpu().numpy().astype(bool)
             seqs = [ids_h[b][m_h[b]] for b in range(B)]
             slots = eng.alloc_slots(B)
-            past_key_values.assign(slots)
-            g = grid_thw.detach().cpu().numpy() if grid_thw is not None else np.zeros((0, 3), np.int64)
-            plan = build_prefill_plan(cfg, g, seqs, slots)
-            out = eng.prefill(image_tiles if image_tiles is not None else torch.empty((0, cfg.vision_encoder.patch_dim), dtype=self.dtype, device=self.device),
-                              plan, want_logits=True)
+            try:
+                g = grid_thw.detach().cpu().numpy() if grid_thw is not None else np.zeros((0, 3), np.int64)
+                plan = build_prefill_plan(cfg, g, seqs, slots)
+                tiles = image_tiles if image_tiles is not None else \
+                    torch.empty((0, cfg.vision_encoder.patch_dim), dtype=self.dtype, device=self.device)
+                out = eng.prefill(tiles, plan, want_logits=True)
+            except Exception:
+                eng.release_slots(slots)
+                raise
+            cache.assign(slots, seq_len=S)
         else:                                     # ---- decode
+            if not cache or cache.batch_size != B:
+                raise _lib.SuryaB200Error(f"decode of {B} rows on a cache holding {cache.batch_size}")
             ids = input_ids.reshape(-1).to(torch.int64).contiguous()
-            pos = position_ids.reshape(-1).to(torch.int32).contiguous()
-            out = eng.decode(ids, past_key_values.slots, pos, want_logits=True)
+            # rows the predictor has already retired keep decoding (it steps the whole batch, :326-352) and their positions
+            # keep growing until a merge replaces them: pin such rows to the last cache row instead of running off the slot.
+            # Live rows never get there as long as s_max >= prompt + max_tokens (RecEngine's default: max_sequence_length).
+            pos = position_ids.reshape(-1).to(torch.int32).clamp_(max=eng.s_max - 1).contiguous()
+            out = eng.decode(ids, cache.slots, pos, want_logits=True, max_pos=0)
+            cache.advance(1)
         return {
             "lm_logits": out["logits"].unsqueeze(1),
             "bbox_logits": out["bbox_sig"].to(self.dtype).unsqueeze(1),
-            "past_key_values": past_key_values,
+            "past_key_values": cache,
         }
 
 
@@ -623,6 +696,9 @@ class RecognitionRunner:
         bboxes = np.zeros((N, self.max_tokens, 6), dtype=np.int64)
         queue = deque(range(N))
         Bsz = self.batch_size
+        if eng.max_slots < Bsz + 1:
+            raise _lib.SuryaB200Error(f"RecognitionRunner(batch_size={Bsz}) needs an engine with max_slots >= {Bsz + 1} "
+                                      f"(one scratch slot for idle rows); this engine has {eng.max_slots}")
         scratch = eng.alloc_slots(1)[0]      # idle rows decode into a scratch slot (the reference decodes every row too)
         row_prompt: List[Optional[int]] = [None] * Bsz
         row_slot = [scratch] * Bsz
@@ -655,14 +731,32 @@ class RecognitionRunner:
             while queue or any(p is not None for p in row_prompt):
                 empty = [r for r in range(Bsz) if row_prompt[r] is None]
                 if queue and len(empty) / Bsz > self.min_prefill_ratio:
-                    take = [queue.popleft() for _ in range(min(len(empty), len(queue)))]
+                    # at most one prompt per empty row (the reference's rule, :356-359), further bounded by what the engine
+                    # can take in ONE prefill: free KV slots, patch rows and token rows of its workspaces (the reference
+                    # bounds the same thing with encoder_chunk_size); the rest of the queue waits for the next prefill
+                    take, n_p, n_t = [], 0, 0
+                    while queue and len(take) < min(len(empty), len(eng.free_slots)):
+                        i = queue[0]
+                        p_i = int(grids[i][0] * grids[i][1] * grids[i][2])
+                        if take and (n_p + p_i > eng.max_patches or n_t + len(seqs[i]) > eng.max_tokens):
+                            break
+                        if p_i > eng.max_patches or len(seqs[i]) > eng.max_tokens or len(seqs[i]) + self.max_tokens > eng.s_max:
+                            raise _lib.SuryaB200Error(
+                                f"crop {i} needs {p_i} patches / {len(seqs[i])} prompt tokens + {self.max_tokens} generated: beyond "
+                                f"the engine's capacity (max_patches={eng.max_patches}, max_tokens={eng.max_tokens}, s_max={eng.s_max})")
+                        take.append(queue.popleft())
+                        n_p, n_t = n_p + p_i, n_t + len(seqs[i])
                     rows = empty[: len(take)]
                     new_slots = eng.alloc_slots(len(take))
-                    tl = tiles_for(take)
-                    if not tl.is_cuda:         # start the (pinned, asynchronous) upload first; the index plan is built meanwhile
-                        tl = tl.to(dev, non_blocking=True)
-                    plan = build_prefill_plan(cfg, np.array([grids[i] for i in take]), [seqs[i] for i in take], new_slots)
-                    out = eng.prefill(tl, plan)
+                    try:
+                        tl = tiles_for(take)
+                        if not tl.is_cuda:     # start the (pinned, asynchronous) upload first; the index plan is built meanwhile
+                            tl = tl.to(dev, non_blocking=True)
+                        plan = build_prefill_plan(cfg, np.array([grids[i] for i in take]), [seqs[i] for i in take], new_slots)
+                        out = eng.prefill(tl, plan)
+                    except Exception:
+                        eng.release_slots(new_slots)
+                        raise
                     ids_io[torch.tensor(rows, dtype=torch.int64, device=dev)] = out["next_ids"]
                     tok_h, sc_h, bb_h = out["tok"].cpu().numpy(), out["score"].cpu().numpy(), out["bbox"].cpu().numpy()
                     for j, (r, p) in enumerate(zip(rows, take)):
@@ -683,7 +777,7 @@ class RecognitionRunner:
                         slot_host[r] = row_slot[r]
                     pos_io.copy_(pos_host, non_blocking=True)
                     slot_t.copy_(slot_host, non_blocking=True)
-                    eng.decode_steps(ids_io, slot_t, pos_io, n, hist=hist)
+                    eng.decode_steps(ids_io, slot_t, pos_io, n, hist=hist, max_pos=int(pos_host.max()))
                     th, sh, bh = hist["tok"][:n].cpu().numpy(), hist["score"][:n].cpu().numpy(), hist["bbox"][:n].cpu().numpy()
                     for r in active:
                         p = row_prompt[r]

@@ -26,6 +26,16 @@ def deal_round_robin(widths: Sequence[int], n_ranks: int) -> List[List[int]]:
     return [order[r::n_ranks] for r in range(n_ranks)]
 
 
+def _collective_device(device=None) -> torch.device:
+    """Device the collectives of the current process group run on: the caller's choice, else the current CUDA device
+    under NCCL and the CPU under gloo (a rank must never fall back to 'cpu' just because its own share is empty)."""
+    if device is not None:
+        return torch.device(device)
+    if dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
 def broadcast_tensors(tensors: List[torch.Tensor] | None, meta_src: int = 0, device=None) -> List[torch.Tensor]:
     """Rank `meta_src` owns the packed weights; every other rank receives shapes then data (one broadcast per tensor)."""
     rank, n = world()
@@ -34,7 +44,7 @@ def broadcast_tensors(tensors: List[torch.Tensor] | None, meta_src: int = 0, dev
     meta = [[(tuple(t.shape), str(t.dtype).split(".")[-1]) for t in tensors]] if rank == meta_src else [None]
     dist.broadcast_object_list(meta, src=meta_src)
     if rank != meta_src:
-        tensors = [torch.empty(s, dtype=getattr(torch, d), device=device) for s, d in meta[0]]
+        tensors = [torch.empty(s, dtype=getattr(torch, d), device=_collective_device(device)) for s, d in meta[0]]
     for t in tensors:
         dist.broadcast(t, src=meta_src)
     return tensors
@@ -103,6 +113,8 @@ def sharded_pages(run_local: Callable[[int, int], torch.Tensor], n_pages: int, d
     ranks in page order (detection heatmaps [n, 2, H/4, W/4], layout / table token histories [n, steps, cols], ...).
     Shares are padded to the largest share so the collective has a fixed shape."""
     rank, n_ranks = world()
+    if n_pages <= 0:
+        return torch.zeros((0,), device=_collective_device(device))
     slices = page_slices(n_pages, n_ranks)
     lo, hi = slices[rank]
     mine = run_local(lo, hi) if hi > lo else None
@@ -114,7 +126,8 @@ def sharded_pages(run_local: Callable[[int, int], torch.Tensor], n_pages: int, d
     shape, dname = next(m for m in meta if m is not None)
     dtype = getattr(torch, dname)
     cap = max(h - l for l, h in slices)
-    dev = device if device is not None else (mine.device if mine is not None else "cpu")
+    # every rank must hand the collective a tensor on the backend's device type, also the ranks whose share is empty
+    dev = _collective_device(device)
     buf = torch.zeros((cap,) + tuple(shape), dtype=dtype, device=dev)
     if mine is not None:
         buf[: hi - lo] = mine.to(dev)

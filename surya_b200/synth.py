@@ -29,11 +29,25 @@ def _norm_w(name, n, seed):
     return 1.0 + 0.1 * torch.randn(n, generator=_gen(name, seed), dtype=torch.float32)
 
 
-def rec_state_dict(cfg: RecConfig, seed: int = 0, std: float = 0.02) -> Dict[str, torch.Tensor]:
-    """fp32 state dict for SuryaModel (names as in surya/common/surya/__init__.py + encoder/ + decoder/)."""
+def rec_state_dict(cfg: RecConfig, seed: int = 0, std: float | None = None) -> Dict[str, torch.Tensor]:
+    """fp32 state dict for SuryaModel (names as in surya/common/surya/__init__.py + encoder/ + decoder/).
+
+    Recipe (round 2): plain N(0, 0.02) weights make an untrained decoder emit ONE token for ever (the 0.02-RMS token embedding
+    drowns in the first attention output, so the final hidden state never turns) — useless as a token-parity input.  Chosen so
+    that greedy decoding walks through the vocabulary (24 distinct ids in 24 steps on SYN-REC, 27-31 of 32 on the tiny config)
+    while logits stay O(1-3):
+      * linear weights N(0, std), std = 0.02 * sqrt(1280 / hidden) per tower (0.02 at SYN-REC width): unit-RMS inputs give
+        ~0.7-RMS outputs at every width;
+      * decoder gate/up projections x4: the token-dependent MLP path outweighs the context-averaging attention path;
+      * token embedding: first half of the channels N(0, 0.3) (the token survives in the residual stream), second half N(0, std);
+        final RMSNorm weight is ZERO on the first half, so the tied lm_head reads only channels where the embedding is small —
+        otherwise logit[tok] = |E_tok| * cos(h, E_tok) dominates and greedy decoding repeats its own input;
+      * lm_head bias -20 on the special ids except EOS (they are never valid outputs)."""
     sd: Dict[str, torch.Tensor] = {}
     e, d = cfg.vision_encoder, cfg.decoder
     H = e.hidden_size
+    std_dec = std if std is not None else 0.02 * (1280.0 / d.hidden_size) ** 0.5
+    std = std if std is not None else 0.02 * (1280.0 / H) ** 0.5
     p = "vision_encoder."
     sd[p + "patch_embed.proj.weight"] = _normal(p + "patch_embed.proj.weight",
                                                 (H, e.in_channels, e.temporal_patch_size, e.patch_size, e.patch_size),
@@ -59,6 +73,7 @@ def rec_state_dict(cfg: RecConfig, seed: int = 0, std: float = 0.02) -> Dict[str
 
     D = d.hidden_size
     hd = d.head_dim
+    std = std_dec
     for i in range(d.num_hidden_layers):
         b = f"decoder.layers.{i}."
         sd[b + "input_layernorm.weight"] = _norm_w(b + "input_layernorm.weight", D, seed)
@@ -69,14 +84,22 @@ def rec_state_dict(cfg: RecConfig, seed: int = 0, std: float = 0.02) -> Dict[str
             sd[b + f"self_attn.{nm}.bias"] = _normal(b + f"self_attn.{nm}.bias", (rows,), std, seed)
         sd[b + "self_attn.o_proj.weight"] = _normal(b + "self_attn.o_proj.weight", (D, d.num_attention_heads * hd),
                                                     std, seed)
-        sd[b + "mlp.gate_proj.weight"] = _normal(b + "mlp.gate_proj.weight", (d.intermediate_size, D), std, seed)
-        sd[b + "mlp.up_proj.weight"] = _normal(b + "mlp.up_proj.weight", (d.intermediate_size, D), std, seed)
+        sd[b + "mlp.gate_proj.weight"] = _normal(b + "mlp.gate_proj.weight", (d.intermediate_size, D), 4 * std, seed)
+        sd[b + "mlp.up_proj.weight"] = _normal(b + "mlp.up_proj.weight", (d.intermediate_size, D), 4 * std, seed)
         sd[b + "mlp.down_proj.weight"] = _normal(b + "mlp.down_proj.weight", (D, d.intermediate_size), std, seed)
     sd["decoder.norm.weight"] = _norm_w("decoder.norm.weight", D, seed)
+    sd["decoder.norm.weight"][: D // 2] = 0.0
 
-    sd["embedder.token_embed.weight"] = _normal("embedder.token_embed.weight", (cfg.vocab_size, D), std, seed)
+    emb = _normal("embedder.token_embed.weight", (cfg.vocab_size, D), 1.0, seed)
+    emb[:, : D // 2] *= 0.3
+    emb[:, D // 2:] *= std
+    sd["embedder.token_embed.weight"] = emb
     sd["lm_head.weight"] = sd["embedder.token_embed.weight"]  # tied (surya/common/surya/__init__.py:111-116)
     sd["lm_head.bias"] = _normal("lm_head.bias", (cfg.vocab_size,), std, seed)
+    # special ids other than EOS are never valid outputs (feeding IMAGE back trips an assert in the reference,
+    # surya/common/surya/__init__.py:227); a trained head suppresses them, the synthetic one does it through the bias
+    sd["lm_head.bias"][2:16] = -20.0
+    sd["lm_head.bias"][0] = -20.0
     sd["bbox_head.weight"] = _normal("bbox_head.weight", (6, D), std, seed)
     sd["bbox_head.bias"] = _normal("bbox_head.bias", (6,), std, seed)
     sd["img_h_embed.weight"] = _normal("img_h_embed.weight", (cfg.image_embed_encoding_size, D), std, seed)

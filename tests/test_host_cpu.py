@@ -60,7 +60,10 @@ def test_oracle_pinned_to_reference_golden_tiny():
     tok, sc, box, logits = O.greedy_decode(sd, cfg, batch, g["meta"]["steps"], torch.float32, return_logits=True)
     assert (logits - g["logits"]).abs().max().item() < 2e-5
     assert torch.equal(tok, g["tokens"])
-    assert torch.equal(box, g["boxes"])
+    # boxes are trunc(sigmoid * bbox_size): identical except where the reference's own value sits within fp32 noise of an integer
+    d = box != g["boxes"]
+    frac = g["bbox"] * cfg.bbox_size
+    assert ((box - g["boxes"]).abs() <= 1).all() and ((frac - frac.round()).abs()[d] < 1e-3).all() and int(d.sum()) <= 2
     assert (sc - g["score"]).abs().max().item() < 1e-6
 
 

@@ -18,6 +18,8 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import rec_oracle as O
+
 pytestmark = pytest.mark.gpu
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -119,7 +121,8 @@ def test_tiny_vs_golden_and_oracle(built_lib, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_synrec_vs_golden(built_lib, dtype):
-    """Declared SYN-REC config (BASELINE config 2 shapes), 2 crops x 3 steps against the reference golden."""
+    """Declared SYN-REC config (BASELINE config 2 shapes), 2 crops x 40 steps (80 distinct token ids) teacher-forced against
+    the golden produced by the reference's own SuryaModel."""
     from oracle import rec_oracle as O
     from surya_b200.config import syn_rec
     from surya_b200.synth import rec_state_dict
@@ -256,8 +259,8 @@ def test_fullsize_properties_synrec(built_lib):
 
     orig = R.RecEngine.decode_steps
 
-    def eager(self, ids_io, slot, pos_io, n_steps, hist=None, use_graph=True):
-        return orig(self, ids_io, slot, pos_io, n_steps, hist, use_graph=False)
+    def eager(self, ids_io, slot, pos_io, n_steps, hist=None, use_graph=True, max_pos=None):
+        return orig(self, ids_io, slot, pos_io, n_steps, hist, use_graph=False, max_pos=max_pos)
 
     R.RecEngine.decode_steps = eager
     try:
@@ -270,6 +273,132 @@ def test_fullsize_properties_synrec(built_lib):
         eng.set_decode_chains(chains)
         tokens_c, scores_c, bboxes_c = runner.run_preprocessed(tiles, grids, seqs, fixed_steps=True)
         assert tokens_c == tokens and scores_c == scores and np.array_equal(bboxes_c, bboxes), f"chains={chains}"
+    eng.close()
+
+
+def test_synrec_fullsize_vs_oracle(built_lib):
+    """BASELINE config 2 at full length against the CPU oracle: SYN-REC, bf16, 8 distinct 48x512 crops,
+    128 greedy tokens.  (a) teacher-forced with the oracle's tokens: every step's logits inside the bf16 envelope, token ids
+    equal wherever the oracle's top-2 margin exceeds 4x that envelope, boxes within 12/1024;  (b) free-running through the
+    device-side decode loop at B = 256 (the 8 crops replicated 32x): each row follows the oracle until a step whose oracle
+    margin is a near-tie, and replicas are bit-identical.  Flip statistics are written to gpurun_out/rec_parity.json."""
+    from oracle import rec_oracle as O
+    from surya_b200.config import syn_rec
+    from surya_b200.recognition import RecognitionRunner
+    from surya_b200.synth import rec_state_dict, rec_synthetic_crops
+
+    dtype, steps = torch.bfloat16, 128
+    cfg = syn_rec()
+    sd = rec_state_dict(cfg, seed=0)
+    base = list(rec_synthetic_crops(8, 48, 512, seed=1234))
+    batch = O.build_batch(base, cfg)
+    torch.set_num_threads(max(1, min(64, len(os.sched_getaffinity(0)))))
+    otok, osc, obox, ologits = O.greedy_decode(sd, cfg, batch, steps, torch.float32, return_logits=True)
+    top2 = ologits.topk(2, -1).values
+    margin = top2[..., 0] - top2[..., 1]
+    eng = _engine(cfg, sd, dtype, max_slots=260, s_max=256, max_patches=256 * 160, max_tokens=256 * 46)
+    # (a) teacher forced
+    logits, tok, boxes, scores = _teacher_forced(eng, cfg, batch, otok, steps)
+    err = (logits - ologits).abs().max().item()
+    flips = _check_tokens(tok, otok, margin, TOL_GOLD[dtype], "synrec fullsize / oracle")
+    box_err = (boxes - obox).abs().max().item()
+    score_err = (scores - osc).abs().max().item()
+    assert err <= TOL_GOLD[dtype], f"teacher-forced logits vs fp32 oracle: {err}"
+    assert box_err <= 12 and score_err <= 2e-2
+    assert len(set(otok[0].tolist())) >= 64, "the synthetic model is supposed to walk through the vocabulary"
+    # (b) free running, B = 256
+    crops = [base[i % 8] for i in range(256)]
+    runner = RecognitionRunner(eng, batch_size=256, max_tokens=steps)
+    tokens, rscores, bboxes = runner.run(crops, fixed_steps=True)
+    first_div = []
+    for i in range(8):
+        ref = otok[i].tolist()
+        k = next((j for j in range(steps) if tokens[i][j] != ref[j]), None)
+        first_div.append(k)
+        if k is not None:
+            assert margin[i, k].item() <= 4 * TOL_GOLD[dtype], f"row {i} leaves the oracle at step {k} (margin {margin[i, k].item():.4f})"
+    for i in range(8, 256):
+        assert tokens[i] == tokens[i % 8] and np.array_equal(bboxes[i], bboxes[i % 8])
+    _report("synrec_fullsize_bf16", {"crops": 8, "steps": steps, "max_abs_err_logits_teacher_forced": err,
+                                     "teacher_forced_token_flips_on_near_ties": flips, "of_tokens": 8 * steps,
+                                     "max_box_err": box_err, "max_score_err": score_err,
+                                     "free_running_first_divergence_step": first_div,
+                                     "oracle_margin_median": margin.median().item(), "oracle_margin_min": margin.min().item(),
+                                     "distinct_tokens_row0": len(set(otok[0].tolist()))})
+    eng.close()
+
+
+def test_predictor_trace_replay_gpu(built_lib):
+    """The call sequence of the reference's unmodified RecognitionPredictor.prediction_loop (recorded in the build container,
+    tests/golden/rec_predictor_trace.pt: left-padded prefills, `ContinuousBatchingCache()` per prefill, merges with offsets of
+    both signs, maybe_trim_cache_padding, retired rows that keep decoding) replayed call by call against B200SuryaModel +
+    SlotCache on the CUDA engine.  Tokens must equal the recorded (fp32) ones except on recorded near-ties."""
+    from oracle import ref_predictors as RP
+    from oracle.make_golden import trace_crops
+    from surya_b200.config import tiny_rec
+    from surya_b200.recognition import B200SuryaModel
+    from surya_b200.synth import rec_state_dict
+
+    dtype = torch.float16
+    cfg = tiny_rec()
+    sd = rec_state_dict(cfg, seed=0)
+    g = torch.load(GOLDEN / "rec_predictor_trace.pt")
+    eng = _engine(cfg, sd, dtype, max_slots=16, s_max=256, max_patches=4096, max_tokens=1024)
+    model = B200SuryaModel(eng)
+    stats = {"calls": 0, "rows": 0, "flips": 0, "bbox_err": 0.0}
+
+    def tile_fn(crop):
+        img = O.scale_to_fit(np.asarray(crop, dtype=np.float32), (1024, 256))
+        return O.process_and_tile(img, cfg.vision_encoder.patch_size, cfg.merge_size)[0]
+
+    def check(i, ev, out):
+        tok = out["lm_logits"][:, -1].float().argmax(-1).cpu()
+        diff = tok != ev["tok"]
+        bad = diff & (ev["margin"] > 4 * TOL_GOLD[dtype])
+        assert not bad.any(), f"event {i} ({ev['kind']}): {tok[bad].tolist()} vs recorded {ev['tok'][bad].tolist()}"
+        stats["calls"] += 1
+        stats["rows"] += tok.numel()
+        stats["flips"] += int(diff.sum())
+        stats["bbox_err"] = max(stats["bbox_err"], (out["bbox_logits"][:, -1].float().cpu() - ev["bbox"]).abs().max().item())
+
+    free0 = len(eng.free_slots)
+    RP.replay_rec_trace(model, g, trace_crops(), tile_fn, check)
+    assert len(eng.free_slots) == free0, "replay leaked KV slots"
+    assert stats["bbox_err"] < 5e-3
+    _report("predictor_trace_replay_fp16", stats)
+    eng.close()
+
+
+def test_capacity_and_bounds_are_loud(built_lib):
+    """decode past s_max must raise (never write into a neighbour's KV rows), the runner must chunk prefills by
+    engine capacity and give slots back when a prefill fails."""
+    from surya_b200 import _lib
+    from surya_b200.config import tiny_rec
+    from surya_b200.recognition import RecognitionRunner
+    from surya_b200.synth import rec_state_dict, rec_synthetic_crops
+
+    cfg = tiny_rec()
+    sd = rec_state_dict(cfg, seed=0)
+    eng = _engine(cfg, sd, torch.float16, max_slots=5, s_max=64, max_patches=400, max_tokens=200)
+    crops = list(rec_synthetic_crops(6, 48, 512, seed=3))            # 160 patches, 46 prompt tokens each
+    with pytest.raises(_lib.SuryaB200Error):                         # 46 + 32 > s_max
+        RecognitionRunner(eng, batch_size=4, max_tokens=32).run(crops[:1])
+    assert len(eng.free_slots) == 5
+    with pytest.raises(_lib.SuryaB200Error):                         # runner needs batch_size + 1 slots
+        RecognitionRunner(eng, batch_size=5, max_tokens=4).run(crops[:1])
+    # max_patches = 400 admits two crops per prefill: six crops through four rows still all decode, identically to solo runs
+    runner = RecognitionRunner(eng, batch_size=4, max_tokens=6)
+    tok, sc, bb = runner.run(crops, fixed_steps=True)
+    for i in (0, 5):
+        t1, s1, b1 = runner.run([crops[i]], fixed_steps=True)
+        assert tok[i] == t1[0] and np.array_equal(bb[i], b1[0])
+    assert len(eng.free_slots) == 5
+    # raw decode at a full slot
+    slot = torch.tensor(eng.alloc_slots(1), dtype=torch.int32, device="cuda")
+    with pytest.raises(_lib.SuryaB200Error):
+        eng.decode(torch.zeros(1, dtype=torch.int64, device="cuda"), slot, torch.tensor([64], dtype=torch.int32, device="cuda"))
+    with pytest.raises(_lib.SuryaB200Error):
+        eng.decode_steps(torch.zeros(1, dtype=torch.int64, device="cuda"), slot, torch.tensor([60], dtype=torch.int32, device="cuda"), 8)
     eng.close()
 
 
