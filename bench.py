@@ -200,12 +200,12 @@ def decode_gemm_roofline(eng, peaks, reps=20):
         flops += 2 * a.shape[0] * w.shape[0] * w.shape[1]
 
     for l in range(d.num_hidden_layers):
-        w = eng.weights[base + 7 * l: base + 7 * (l + 1)]
-        add(x, w[1], qkv, bias=w[2])
-        add(ao, w[3], x, residual=x)
-        add(x, w[5], act, act="silu", swiglu=True)
-        add(act, w[6], x, residual=x, splitk=True)      # the engine's decode step lets the down projection use split-K
-    add(x, eng.weights[8], logits, bias=eng.weights[9])
+        w = eng.weights[base + 5 * l: base + 5 * (l + 1)]
+        add(x, w[0], qkv, bias=w[1], rms_eps=d.rms_norm_eps)                   # RMSNorm folded: 1/rms computed inside the GEMM
+        add(ao, w[2], x, residual=x)
+        add(x, w[3], act, act="silu", swiglu=True, rms_eps=d.rms_norm_eps)
+        add(act, w[4], x, residual=x, splitk=True)      # the engine's decode step lets the down projection use split-K
+    add(x, eng.weights[7], logits, bias=eng.weights[9], rms_eps=d.rms_norm_eps, argmax_only=True)
 
     def run():
         for a, w, out, kw in calls:

@@ -47,6 +47,21 @@ int sb_gemm(int dtype, const void* A, int lda, const void* W, int ldw, void* C, 
             const float* bias, const void* residual, int ldr, int act, int swiglu, int out_f32, int force_bn,
             void* stream);
 
+/* nn.Linear applied to Qwen2RMSNorm(x) with the norm folded into the GEMM (decoder/__init__.py:241-258 followed by
+ * :147-158 / :37-50, and the final norm + lm_head / bbox_head of surya/common/surya/__init__.py:323-330):
+ *   C = epi(rs[m] * (A W^T) + bias),  W = nn.Linear weight x norm weight per column (packed by the caller),
+ *   rs[m] = rsqrt(mean_k A[m,k]^2 + eps): read from `rowscale` (fp32 [M], see sb_row_rstd) or, when rowscale is NULL, computed
+ *   inside the kernel from the A tiles with rms_eps (no separate pass over A; used by the decode steps).
+ * Optional online argmax epilogue (am_val != NULL): per (row, n-tile) partials (max logit, first argmax, sum exp(l - max)) of
+ * the 16-bit-rounded outputs into [M, am_ld] arrays, tile width = sb_gemm_argmax_tile(M, N); C is written only if store_c —
+ * RecognitionPredictor.process_outputs (surya/recognition/__init__.py:294-324) needs argmax and max-softmax only. */
+int sb_gemm_rmsnorm(int dtype, const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
+                    const float* bias, const void* residual, int ldr, int act, int swiglu, const float* rowscale, float rms_eps,
+                    float* am_val, int* am_idx, float* am_sum, int am_ld, int store_c, int force_bn, void* stream);
+int sb_gemm_argmax_tile(int M, int N);
+/* rs[row] = rsqrt(mean(x[row]^2) + eps) in the summation order sb_gemm_rmsnorm's in-kernel pass uses (bit-identical). */
+int sb_row_rstd(int dtype, const void* x, int ldx, float* rs, int rows, int H, float eps, const int* src_rows, void* stream);
+
 /* sb_gemm with an in-kernel timeline of CTA 0 (globaltimer ns into timeline_dev[0..42]); profiling aid. */
 int sb_gemm_timeline(int dtype, const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
                      const float* bias, const void* residual, int ldr, int act, int swiglu, int force_bn,
@@ -128,10 +143,10 @@ enum {
   SB_RW_MERGER_LN,        /* [enc_hidden] */
   SB_RW_MERGER_W0, SB_RW_MERGER_B0 /* fp32 */, SB_RW_MERGER_W2, SB_RW_MERGER_B2 /* fp32 */,
   SB_RW_ENC_INV_FREQ,     /* fp32 [head_dim/4] */
-  SB_RW_DEC_NORM,         /* [dec_hidden] */
-  SB_RW_EMBED,            /* [vocab, dec_hidden]  (tied lm_head weight) */
+  SB_RW_LM_W,             /* [vocab, dec_hidden] lm_head weight (= token embedding, tied) x decoder.norm.weight per column */
+  SB_RW_EMBED,            /* [vocab, dec_hidden] token embedding (input lookups) */
   SB_RW_LM_BIAS,          /* fp32 [vocab] */
-  SB_RW_BBOX_W, SB_RW_BBOX_B, /* [6, dec_hidden], [6] */
+  SB_RW_BBOX_W, SB_RW_BBOX_B, /* [6, dec_hidden] x decoder.norm.weight per column, [6] */
   SB_RW_H_EMBED, SB_RW_W_EMBED, /* [enc_size, dec_hidden] */
   SB_RW_DEC_INV_FREQ,     /* fp32 [head_dim/2] */
   SB_RW_ENC_BASE,         /* first per-block entry of the vision tower */
@@ -142,9 +157,11 @@ enum { /* per vision block */
   SB_RWE_GU_W /* [2*inter_pad, hidden] gate/up interleaved */, SB_RWE_GU_B /* fp32 */, SB_RWE_DOWN_W /* [hidden, inter_pad] */,
   SB_RWE_DOWN_B /* fp32 */, SB_RWE_STRIDE
 };
-enum { /* per decoder layer (base = SB_RW_ENC_BASE + enc_depth * SB_RWE_STRIDE) */
-  SB_RWD_IN_NORM = 0, SB_RWD_QKV_W /* [(nh+2nkv)*d, hidden] */, SB_RWD_QKV_B /* fp32 */, SB_RWD_O_W, SB_RWD_POST_NORM,
-  SB_RWD_GU_W /* interleaved */, SB_RWD_DOWN_W, SB_RWD_STRIDE
+enum { /* per decoder layer (base = SB_RW_ENC_BASE + enc_depth * SB_RWE_STRIDE).  The decoder's RMSNorm weights are folded
+        * into the GEMM that consumes the normalised activations: W'[n,k] = W[n,k] * g[k] (rounded once to cfg.dtype); the
+        * kernels apply the per-row 1/rms in the GEMM epilogue (decoder/__init__.py:241-258, 288-310). */
+  SB_RWD_QKV_W = 0 /* [(nh+2nkv)*d, hidden] x input_layernorm.weight */, SB_RWD_QKV_B /* fp32 */, SB_RWD_O_W,
+  SB_RWD_GU_W /* gate/up interleaved, x post_attention_layernorm.weight */, SB_RWD_DOWN_W, SB_RWD_STRIDE
 };
 
 int sb_rec_create(const sb_rec_config* cfg, const void* const* weights, int n_weights, sb_rec_engine** out);
@@ -179,11 +196,6 @@ int sb_rec_decode_steps(sb_rec_engine* eng, long long* ids_io, const int* slot, 
                         long long* tok_hist, float* score_hist, long long* bbox_hist, unsigned char* done_hist,
                         int use_graph, void* stream);
 
-/* Decode-step scheduling: the batch rows are cut into n_chains (1..4, default 1 or $SB_DECODE_CHAINS) groups whose kernel
- * chains run concurrently on forked streams inside the step / CUDA graph.  q_len = 1 decoding is a strictly sequential chain
- * of ~90 latency-bound kernels (decoder/__init__.py:417-490 per step); independent row groups overlap each other's launch
- * gaps, prologues and drains.  Results are bit-identical for any setting. */
-int sb_rec_set_decode_chains(sb_rec_engine* e, int n_chains);
 /* Parity taps: copy `bytes` of a named workspace ("feat" = merged image features in window order before the
  * 2-D position embedding, "x", "xl", "logits", "qkv") into dst (device). */
 int sb_rec_debug_copy(sb_rec_engine* eng, const char* name, void* dst, size_t bytes, void* stream);

@@ -22,6 +22,27 @@ int sb_gemm(int dtype, const void* A, int lda, const void* W, int ldw, void* C, 
   return gemm_launch(a, static_cast<cudaStream_t>(stream));
 }
 
+int sb_gemm_rmsnorm(int dtype, const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
+                    const float* bias, const void* residual, int ldr, int act, int swiglu, const float* rowscale, float rms_eps,
+                    float* am_val, int* am_idx, float* am_sum, int am_ld, int store_c, int force_bn, void* stream) {
+  GemmArgs a;
+  a.dtype = dtype; a.A = A; a.lda = lda; a.W = W; a.ldw = ldw; a.C = C; a.ldc = ldc;
+  a.M = M; a.N = N; a.K = K; a.bias = bias; a.residual = residual; a.ldr = ldr;
+  a.act = act; a.swiglu = swiglu;
+  a.force_bn = force_bn;
+  a.rowscale = rowscale;
+  if (!rowscale) { a.ssq_inline = 1; a.ssq_eps = rms_eps; a.ssq_k = K; }
+  a.am_val = am_val; a.am_idx = am_idx; a.am_sum = am_sum; a.am_ld = am_ld;
+  a.store_c = am_val ? store_c : 1;
+  return gemm_launch(a, static_cast<cudaStream_t>(stream));
+}
+
+int sb_gemm_argmax_tile(int M, int N) { return gemm_argmax_tile(M, N); }
+
+int sb_row_rstd(int dtype, const void* x, int ldx, float* rs, int rows, int H, float eps, const int* src_rows, void* stream) {
+  return row_rstd(dtype, x, ldx, rs, rows, H, eps, src_rows, static_cast<cudaStream_t>(stream));
+}
+
 int sb_gemm_timeline(int dtype, const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
                      const float* bias, const void* residual, int ldr, int act, int swiglu, int force_bn,
                      unsigned long long* timeline_dev, void* stream) {

@@ -199,7 +199,7 @@ static int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   if (rc) return rc;
   rc = make_tma_2d_sw(&mb, a.dtype, a.weight, a.Cout, a.ksize * a.ksize * a.Cin, a.ksize * a.ksize * a.Cin, BKC, BN, sw);
   if (rc) return rc;
-  ConvKParams cp;
+  ConvKParams cp{};
   cp.g.M = a.n_img * Ho * Wo; cp.g.N = a.Cout; cp.g.K = a.ksize * a.ksize * a.Cin;
   cp.g.C = a.out; cp.g.ldc = a.Cout; cp.g.bias = a.bias; cp.g.residual = a.residual; cp.g.ldr = a.Cout;
   cp.g.act = a.act; cp.g.swiglu = 0; cp.g.out_f32 = 0; cp.g.group_m = 8; cp.g.group_k = 0; cp.g.dbg = nullptr; cp.g.w_constant = 0;

@@ -33,7 +33,22 @@ struct GemmArgs {
   int w_constant = 0;                     // W is never written by a preceding kernel: its tiles may be prefetched
                                           // before the programmatic-dependency wait (engine weights)
   unsigned long long* dbg = nullptr;      // optional in-kernel timeline (see GemmKParams::dbg)
+  // RMSNorm folded into the GEMM: C = epi(rs[m] * (A W^T) + bias), W already multiplied by the norm weight.
+  //   rowscale  : rs given, fp32 [M] (row_rstd in ops.cu)
+  //   ssq_inline: rs = rsqrt(sum_k A[m,k]^2 / ssq_k + ssq_eps) computed inside the kernel from the A tiles
+  const float* rowscale = nullptr;
+  int ssq_inline = 0;
+  float ssq_eps = 0.f;
+  int ssq_k = 0;                          // number of real columns in the mean (0 = K)
+  // online argmax / softmax-denominator epilogue: per (row, n-tile) partials [M, am_ld]; C is only written when store_c
+  float* am_val = nullptr;
+  int* am_idx = nullptr;
+  float* am_sum = nullptr;
+  int am_ld = 0;
+  int store_c = 1;
 };
+// Tile width gemm_launch will use for an argmax-epilogue launch of this shape (partials per row = ceil(N / width)).
+int gemm_argmax_tile(int M, int N);
 
 // Returns cudaSuccess or an error; sets a message retrievable through sb_last_error().
 int gemm_launch(const GemmArgs& a, cudaStream_t stream);

@@ -19,6 +19,19 @@ struct GemmKParams {
   int group_m;
   int group_k;  // grouped 1x1 conv: A column offset per n-block (0 = dense)
   int w_constant;  // W tiles may be fetched before the programmatic-dependency wait
+  // RMSNorm folded into the GEMM (decoder layers): C = epi(rowscale[m] * (A W'^T) + bias) with W' = W * g and
+  // rowscale = rsqrt(mean_k(A[m,k]^2) + eps), either read from global (prefill: row_rstd kernel) or computed by the epilogue
+  // warps from the A stages while the main loop runs (ssq_inline: decode steps, no extra launch)
+  const float* rowscale;
+  int ssq_inline;
+  float ssq_eps, ssq_inv_k;
+  // lm_head with an online (max, argmax, sum exp) epilogue: per (row, n-tile) partials, logits never reach HBM unless
+  // store_c is set (surya/recognition/__init__.py:294-324 needs argmax + max softmax only)
+  float* am_val;
+  int* am_idx;
+  float* am_sum;
+  int am_ld;
+  int store_c;
   unsigned long long* dbg;  // optional timeline buffer (globaltimer ns) written by CTA 0: [0]=start [1]=setup done
                             // [2+kb]=k-block kb landed (first tile) [40]=accumulator ready [41]=epilogue done
 };
@@ -134,7 +147,8 @@ __device__ __noinline__ void epilogue_chunk(const uint32_t (&v)[32], const GemmK
 // Requires ldc % 8 == 0, ldr % 8 == 0, N % 8 == 0 (N % 16 == 0 and act == silu with SwiGLU), 16-bit output.
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_STAGE_BYTES = 32 * 128;                       // per warp: 32 rows x 128 B (swizzled, no padding)
-template <int BN> constexpr int epi_smem_bytes() { return EPI_WARPS * EPI_STAGE_BYTES + BN * 4; }
+constexpr int EPI_ROWSCALE_BYTES = 128 * 4;                     // per-row 1/rms of the tile's 128 rows (folded RMSNorm)
+template <int BN> constexpr int epi_smem_bytes() { return EPI_WARPS * EPI_STAGE_BYTES + BN * 4 + EPI_ROWSCALE_BYTES; }
 
 __device__ __forceinline__ bool epilogue_v2_ok(const GemmKParams& p) {
   if (p.out_f32 || (p.ldc & 7) || (p.residual && (p.ldr & 7))) return false;
@@ -193,7 +207,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // stage: 4 KB per warp = residual sub-tile (cp.async, prefetched one group ahead) + output sub-tile, both swizzled.
 template <typename T, int BN, int ACT, bool SWIGLU, typename RowFn>
 __device__ __forceinline__ void epilogue_tile_ct(uint32_t taddr, const GemmKParams& p, uint8_t* stage, const float* sbias,
-                                                 int lane, int half, RowFn row_fn, int n_col0) {
+                                                 int lane, int half, RowFn row_fn, int n_col0, float rs) {
   constexpr int GW = 32;                            // accumulator columns per group (one tcgen05.ld .x32)
   constexpr int NG = BN / GW;
   constexpr int GWO = SWIGLU ? GW / 2 : GW;         // output columns per group
@@ -235,8 +249,9 @@ __device__ __forceinline__ void epilogue_tile_ct(uint32_t taddr, const GemmKPara
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(bs + j);
-        const float x0 = __uint_as_float(v[j]) + b4.x, x1 = __uint_as_float(v[j + 1]) + b4.y;
-        const float x2 = __uint_as_float(v[j + 2]) + b4.z, x3 = __uint_as_float(v[j + 3]) + b4.w;
+        // rs = 1 without a folded norm: fma(acc, 1, b) == acc + b exactly, so the other callers keep their bits
+        const float x0 = fmaf(__uint_as_float(v[j]), rs, b4.x), x1 = fmaf(__uint_as_float(v[j + 1]), rs, b4.y);
+        const float x2 = fmaf(__uint_as_float(v[j + 2]), rs, b4.z), x3 = fmaf(__uint_as_float(v[j + 3]), rs, b4.w);
         if constexpr (SWIGLU) {
           // (x0,x1) = (gate_i, up_i), (x2,x3) = (gate_i+1, up_i+1); every eager op boundary rounds once
           const uint32_t t0 = Pk<T>::pack(x0, x1), t1 = Pk<T>::pack(x2, x3);
@@ -283,6 +298,95 @@ __device__ __forceinline__ void epilogue_tile_ct(uint32_t taddr, const GemmKPara
   }
 }
 
+// Online (max, first argmax, sum exp(x - max)) over the tile's columns for this lane's row; logits are rounded to the storage
+// type first (the reference takes argmax / softmax of the 16-bit lm_head output cast to fp32).  The two warps of a lane
+// quarter cover alternating 32-column groups; their partials meet in shared memory (`xch` = base of the epilogue staging blocks) and warp half 0 writes
+// the (row, n-tile) partial.  Columns beyond N are skipped.
+struct AmPartial { float m; int i; float s; };
+__device__ __forceinline__ void am_combine(AmPartial& a, const AmPartial& b) {
+  if (b.m == -INFINITY) return;
+  if (a.m == -INFINITY) { a = b; return; }
+  if (b.m > a.m || (b.m == a.m && b.i < a.i)) {
+    a.s = a.s * __expf(a.m - b.m) + b.s;
+    a.m = b.m;
+    a.i = b.i;
+  } else {
+    a.s += b.s * __expf(b.m - a.m);
+  }
+}
+
+template <typename T, int BN>
+__device__ __forceinline__ void epilogue_tile_argmax(uint32_t taddr, const GemmKParams& p, uint8_t* xch, const float* sbias,
+                                                     int lane, int half, int q, int row, int n_col0, int nb, float rs) {
+  constexpr int GW = 32, NG = BN / GW;
+  AmPartial a{-INFINITY, 0x7fffffff, 0.f};
+#pragma unroll 1
+  for (int g = half; g < NG; g += 2) {
+    const int acol0 = n_col0 + g * GW;
+    if (acol0 >= p.N) break;
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + g * GW, v);
+    tmem_ld_wait();
+    const float* bs = sbias + g * GW;
+    float x[32];
+    float cm = -INFINITY;
+    int ci = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      x[j] = rnd<T>(fmaf(__uint_as_float(v[j]), rs, bs[j]));
+      if (acol0 + j < p.N && x[j] > cm) { cm = x[j]; ci = acol0 + j; }     // ascending columns: the first maximum wins
+    }
+    if (cm == -INFINITY) continue;
+    if (cm > a.m) { a.s *= __expf(a.m - cm); a.m = cm; a.i = ci; }
+    float add = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (acol0 + j < p.N) add += __expf(x[j] - a.m);
+    a.s += add;
+  }
+  // exchange through the half-1 warp's OWN staging block (nobody else touches it, also not a store_c epilogue still draining)
+  float* mine = reinterpret_cast<float*>(xch + (4 + q) * EPI_STAGE_BYTES) + lane * 3;
+  if (half == 1) {
+    mine[0] = a.m;
+    mine[1] = __int_as_float(a.i);
+    mine[2] = a.s;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (half == 0) {
+    const float* other = mine;
+    AmPartial b{other[0], __float_as_int(other[1]), other[2]};
+    am_combine(a, b);
+    if (row >= 0) {
+      const size_t o = static_cast<size_t>(row) * p.am_ld + nb;
+      p.am_val[o] = a.m;
+      p.am_idx[o] = a.i;
+      p.am_sum[o] = a.s;
+    }
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");   // xch may be reused by the next tile
+}
+
+// Sum of squares of one 128 x 64 A stage (128-byte-swizzled, K-major) for the folded RMSNorm: thread t of the 256 epilogue
+// threads owns half a row (row t/2, logical 16-byte chunks 4*(t&1) .. +3, i.e. elements [32*(t&1), +32) of the k-block, in
+// order — row_rstd_kernel in ops.cu adds in exactly this order, so prefill and decode agree bit for bit).
+template <typename T>
+__device__ __forceinline__ float ssq_stage(const uint8_t* sa, int epi_tid, float acc) {
+  const int r = epi_tid >> 1, hf = epi_tid & 1;
+  const uint8_t* rowp = sa + r * 128;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int phys = (hf * 4 + j) ^ (r & 7);
+    const uint4 u = *reinterpret_cast<const uint4*>(rowp + phys * 16);
+    const T* e = reinterpret_cast<const T*>(&u);
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      const float f = to_f<T>(e[x]);
+      acc = fmaf(f, f, acc);
+    }
+  }
+  return acc;
+}
+
 // Stage the tile's bias slice (zeros when the GEMM has none); called by all epilogue threads before the accumulator wait.
 template <int BN>
 __device__ __forceinline__ void epilogue_stage_bias(const GemmKParams& p, float* sbias, int epi_tid, int n_col0) {
@@ -293,19 +397,19 @@ __device__ __forceinline__ void epilogue_stage_bias(const GemmKParams& p, float*
 // Runtime -> compile-time dispatch on (act, swiglu); once per tile, outside every loop.
 template <typename T, int BN, typename RowFn>
 __device__ __forceinline__ void epilogue_tile_v2(uint32_t taddr, const GemmKParams& p, uint8_t* stage, const float* sbias,
-                                                 int lane, int half, RowFn row_fn, int n_col0) {
+                                                 int lane, int half, RowFn row_fn, int n_col0, float rs = 1.0f) {
   if (p.swiglu) {   // SwiGLU (Qwen2 MLPs) or GeGLU (ADETR MLP, gelu_pytorch_tanh)
-    if (p.act == ACT_SILU) epilogue_tile_ct<T, BN, ACT_SILU, true>(taddr, p, stage, sbias, lane, half, row_fn, n_col0);
-    else epilogue_tile_ct<T, BN, ACT_GELU_TANH, true>(taddr, p, stage, sbias, lane, half, row_fn, n_col0);
+    if (p.act == ACT_SILU) epilogue_tile_ct<T, BN, ACT_SILU, true>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs);
+    else epilogue_tile_ct<T, BN, ACT_GELU_TANH, true>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs);
     return;
   }
   switch (p.act) {
-    case ACT_NONE: epilogue_tile_ct<T, BN, ACT_NONE, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0); break;
-    case ACT_GELU_ERF: epilogue_tile_ct<T, BN, ACT_GELU_ERF, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0); break;
-    case ACT_HARDSWISH: epilogue_tile_ct<T, BN, ACT_HARDSWISH, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0); break;
-    case ACT_RELU: epilogue_tile_ct<T, BN, ACT_RELU, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0); break;
-    case ACT_SILU: epilogue_tile_ct<T, BN, ACT_SILU, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0); break;
-    default: epilogue_tile_ct<T, BN, ACT_GELU_TANH, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0); break;
+    case ACT_NONE: epilogue_tile_ct<T, BN, ACT_NONE, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs); break;
+    case ACT_GELU_ERF: epilogue_tile_ct<T, BN, ACT_GELU_ERF, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs); break;
+    case ACT_HARDSWISH: epilogue_tile_ct<T, BN, ACT_HARDSWISH, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs); break;
+    case ACT_RELU: epilogue_tile_ct<T, BN, ACT_RELU, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs); break;
+    case ACT_SILU: epilogue_tile_ct<T, BN, ACT_SILU, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs); break;
+    default: epilogue_tile_ct<T, BN, ACT_GELU_TANH, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs); break;
   }
 }
 

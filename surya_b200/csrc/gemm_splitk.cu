@@ -286,7 +286,7 @@ static int launch_splitk(const GemmArgs& a, int pk, cudaStream_t stream) {
   if (rc) return rc;
   rc = make_tma_2d(&mb, a.dtype, a.W, a.N, a.K, a.ldw, BN);
   if (rc) return rc;
-  GemmKParams p;
+  GemmKParams p{};
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.C = a.C; p.ldc = a.ldc;
   p.bias = a.bias;

@@ -74,7 +74,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      // folded RMSNorm: the epilogue warps read every A stage too, so a stage is free after the MMA commit AND their 8 arrivals
+      mbar_init(&empty_bar[i], p.ssq_inline ? 1 + EPI_WARPS : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -166,8 +167,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int epi_tid = threadIdx.x - 128;
     uint8_t* stage = epi_smem + (warp - 4) * EPI_STAGE_BYTES;
     float* sbias = reinterpret_cast<float*>(epi_smem + EPI_WARPS * EPI_STAGE_BYTES);
+    float* srs = sbias + BN;                              // 128 per-row scales of the current tile (folded RMSNorm)
     int as = 0;
     uint32_t aph = 0;
+    int es = 0;                                           // pipeline stage / phase as seen by the sum-of-squares pass
+    uint32_t eph = 0;
     const bool vec_ok = (p.ldc % 8 == 0) && (!p.residual || p.ldr % 8 == 0);
     const bool v2 = epilogue_v2_ok(p);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -176,6 +180,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       if (v2) {
         asm volatile("bar.sync 1, 256;" ::: "memory");   // all epilogue warps are done with the previous tile's bias
         epilogue_stage_bias<BN>(p, sbias, epi_tid, nb * BN);
+        if (p.rowscale && epi_tid < BM) srs[epi_tid] = mb * BM + epi_tid < p.M ? __ldg(p.rowscale + mb * BM + epi_tid) : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      if (p.ssq_inline) {
+        // sum of squares of the tile's 128 A rows, taken from the pipeline stages while the MMA warp consumes them
+        float acc = 0.f;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[es], eph);
+          acc = ssq_stage<T>(smem + es * STAGE_BYTES, epi_tid, acc);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[es]);
+          if (++es == STAGES) { es = 0; eph ^= 1; }
+        }
+        const float tot = acc + __shfl_xor_sync(0xffffffffu, acc, 1);
+        if ((epi_tid & 1) == 0) srs[epi_tid >> 1] = rsqrtf(tot * p.ssq_inv_k + p.ssq_eps);
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       mbar_wait(&tfull_bar[as], aph);
@@ -184,8 +203,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       if (v2) {
         const int row0 = mb * BM + q * 32;
-        epilogue_tile_v2<T, BN>(tacc, p, stage, sbias, lane, half,
-                                [&](int r) { return row0 + r < p.M ? row0 + r : -1; }, nb * BN);
+        const float rs = (p.ssq_inline || p.rowscale) ? srs[q * 32 + lane] : 1.0f;
+        if (!p.am_val || p.store_c)
+          epilogue_tile_v2<T, BN>(tacc, p, stage, sbias, lane, half,
+                                  [&](int r) { return row0 + r < p.M ? row0 + r : -1; }, nb * BN, rs);
+        if (p.am_val)
+          epilogue_tile_argmax<T, BN>(tacc, p, epi_smem, sbias, lane, half, q,
+                                      row0 + lane < p.M ? row0 + lane : -1, nb * BN, nb, rs);
       } else if (half == 0) {
         const int row = mb * BM + q * 32 + lane;
         const bool row_ok = row < p.M;
@@ -368,7 +392,7 @@ static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   if (rc) return rc;
   rc = make_tma_2d(&mb, a.dtype, a.W, a.N, a.K, a.ldw, BN);  // grouped: W is [N, K] with K = padded per-group depth
   if (rc) return rc;
-  GemmKParams p;
+  GemmKParams p{};
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.C = a.C; p.ldc = a.ldc;
   p.bias = a.bias;
@@ -378,6 +402,11 @@ static int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   p.group_k = a.group_k;
   p.dbg = a.dbg;
   p.w_constant = a.w_constant;
+  p.rowscale = a.rowscale;
+  p.ssq_inline = a.ssq_inline;
+  p.ssq_eps = a.ssq_eps;
+  p.ssq_inv_k = 1.0f / static_cast<float>(a.ssq_k > 0 ? a.ssq_k : a.K);
+  p.am_val = a.am_val; p.am_idx = a.am_idx; p.am_sum = a.am_sum; p.am_ld = a.am_ld; p.store_c = a.store_c;
   int m_blocks = (a.M + 127) / 128, n_blocks = (a.N + BN - 1) / BN;
   int tiles = m_blocks * n_blocks;
   int grid = tiles < num_sms() ? tiles : num_sms();
@@ -389,7 +418,7 @@ template <typename T>
 static int launch_typed(const GemmArgs& a, cudaStream_t stream) {
   int bn = a.force_bn;
   if (bn >= 1000) return gemm_splitk_launch(a, bn / 1000, bn % 1000, stream);   // forced split-K: 1000 * pk + BN
-  if (bn == 0 && a.allow_splitk && splitk_enabled()) {
+  if (bn == 0 && a.allow_splitk && splitk_enabled() && !a.rowscale && !a.ssq_inline && !a.am_val) {
     int sbn = 0;
     const int pk = splitk_plan(a, &sbn);
     if (pk >= 2) return gemm_splitk_launch(a, pk, sbn, stream);
@@ -421,6 +450,7 @@ static int launch_typed(const GemmArgs& a, cudaStream_t stream) {
       }
     }
   }
+  if (a.am_val && a.force_bn == 0) bn = gemm_argmax_tile(a.M, a.N);   // the caller sized its partial buffers with this
   if (a.group_k) bn = a.group_n;  // one n-block per channel group
   switch (bn) {
     case 256: return launch_cfg<T, 256, 4>(a, stream);
@@ -432,8 +462,25 @@ static int launch_typed(const GemmArgs& a, cudaStream_t stream) {
   }
 }
 
+int gemm_argmax_tile(int M, int N) {
+  (void)M;
+  return N >= 4096 ? 256 : (N >= 1024 ? 128 : 64);
+}
+
 int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return 0;
+  if (a.rowscale || a.ssq_inline || a.am_val) {
+    // these ride on the staged 16-bit epilogue only (and on the plain kernel: split-K would change who owns a row's columns)
+    const bool v2 = !a.out_f32 && a.ldc % 8 == 0 && (!a.residual || a.ldr % 8 == 0) &&
+                    (a.swiglu ? ((a.act == ACT_SILU || a.act == ACT_GELU_TANH) && a.N % 16 == 0) : a.N % 8 == 0);
+    if (!v2 || a.group_k || a.force_bn >= 1000) {
+      set_error("gemm: rowscale / ssq_inline / argmax epilogues need the 16-bit staged epilogue (N %% 8 == 0, 16-byte pitches), "
+                "no grouped or split-K mode");
+      return -15;
+    }
+    if (a.rowscale && a.ssq_inline) { set_error("gemm: rowscale and ssq_inline are exclusive"); return -15; }
+    if (a.am_val && (!a.am_idx || !a.am_sum || a.am_ld <= 0)) { set_error("gemm: incomplete argmax partial buffers"); return -15; }
+  }
   if (a.swiglu && (a.N % 2 != 0)) {
     set_error("swiglu epilogue needs an even N");
     return -13;

@@ -8,6 +8,7 @@
 //   argmax / score     surya/recognition/__init__.py:294-324
 //   bbox head          surya/common/surya/__init__.py:329
 #include "ops.cuh"
+#include "gemm_epilogue.cuh"
 #include "sb_ptx.cuh"
 
 namespace sb {
@@ -89,6 +90,186 @@ int rmsnorm(int dtype, const void* x, int ldx, const void* w, void* y, int ldy, 
   else
     launch_pdl(rmsnorm_kernel<__half>, grid, block, 0, st, (const __half*)x, ldx, (const __half*)w, (__half*)y, ldy, rows, H,
                eps, src_rows, mode);
+  return launch_ok();
+}
+
+// ------------------------------------------------------------------------------------------ row 1/rms (folded RMSNorm)
+// rs[row] = rsqrt(sum_k x[row,k]^2 / H + eps) for GEMMs that fold the norm weight into W (gemm.cuh: rowscale).  Two threads
+// per row add the squares in exactly the order the GEMM's in-kernel pass does (gemm_epilogue.cuh: ssq_stage — per 64-column
+// block, thread h takes elements [32h, 32h + 32) in order; the halves meet at the end), so a sequence prefilled through this
+// kernel and continued by decode steps sees bit-identical scales.
+template <typename T>
+__global__ void row_rstd_kernel(const T* __restrict__ x, int ldx, float* __restrict__ rs, int rows, int H, float eps,
+                                const int* __restrict__ src_rows) {
+  pdl_trigger();
+  pdl_wait();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = t >> 1, hf = t & 1;
+  float acc = 0.f;
+  if (row < rows) {
+    const T* xr = x + static_cast<size_t>(src_rows ? src_rows[row] : row) * ldx;
+    for (int k0 = 0; k0 < H; k0 += 64) {
+      const int c0 = k0 + hf * 32;
+      if (c0 + 32 <= H) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 u = *reinterpret_cast<const uint4*>(xr + c0 + j * 8);
+          const T* e = reinterpret_cast<const T*>(&u);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float f = to_f<T>(e[i]);
+            acc = fmaf(f, f, acc);
+          }
+        }
+      } else {
+        for (int c = c0; c < c0 + 32 && c < H; ++c) {
+          const float f = to_f<T>(xr[c]);
+          acc = fmaf(f, f, acc);
+        }
+      }
+    }
+  }
+  const float tot = acc + __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (row < rows && hf == 0) rs[row] = rsqrtf(tot * (1.0f / static_cast<float>(H)) + eps);
+}
+
+int row_rstd(int dtype, const void* x, int ldx, float* rs, int rows, int H, float eps, const int* src_rows, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  if (ldx % 8) { set_error("row_rstd: row pitch must be a multiple of 8 elements"); return -1; }
+  dim3 grid((rows * 2 + 127) / 128), block(128);
+  if (dtype == DT_BF16)
+    launch_pdl(row_rstd_kernel<__nv_bfloat16>, grid, block, 0, st, (const __nv_bfloat16*)x, ldx, rs, rows, H, eps, src_rows);
+  else
+    launch_pdl(row_rstd_kernel<__half>, grid, block, 0, st, (const __half*)x, ldx, rs, rows, H, eps, src_rows);
+  return launch_ok();
+}
+
+// ------------------------------------------------------------------------------------------ decode tail
+// Everything between the lm_head GEMM of one greedy step and the first GEMM of the next (one block per batch row):
+//   * reduce the GEMM's per-tile (max, first argmax, sum exp) partials -> token, score = max softmax = 1 / sum exp(l - max),
+//     done = tok in {EOS, PAD}, next id = PAD if done (RecognitionPredictor.process_outputs, surya/recognition/__init__.py:294-324);
+//   * bbox head on the final hidden state with the final RMSNorm folded in: sig = T(sigmoid(T(rs * (x . Wb') + b))),
+//     box = trunc(sig * bbox_size) (surya/common/surya/__init__.py:323-330);
+//   * optional device-side bookkeeping of sb_rec_decode_steps: history append at *step, token feedback, position + 1, and the
+//     next step's input embedding written over this row of x (embed_tokens lookup of the decoder's next call);
+//   * the last block to finish advances *step.
+struct TailParams {
+  const float* am_val; const int* am_idx; const float* am_sum; int am_ld, n_tiles;
+  const void* x; int ldx; int H; float eps;
+  const void* bbox_w; const void* bbox_b; int n_box; float bbox_size;
+  const void* embed; void* x_next; int ldx_next;
+  long long* tok; float* score; long long* bbox; float* bbox_sig; unsigned char* done; long long* next_ids;
+  int* step; unsigned int* counter; int B;
+  long long* tok_hist; float* score_hist; long long* bbox_hist; unsigned char* done_hist;
+  long long* ids_io; int* pos_io;
+  int eos, pad;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) decode_tail_kernel(const TailParams p) {
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ float s_red[4][8];
+  __shared__ float s_m[4], s_s[4];
+  __shared__ int s_i[4];
+  __shared__ long long s_next;
+  const int s = p.step ? *p.step : 0;
+  // ---- token / score
+  AmPartial a{-INFINITY, 0x7fffffff, 0.f};
+  for (int t = tid; t < p.n_tiles; t += 128) {
+    const size_t o = static_cast<size_t>(b) * p.am_ld + t;
+    am_combine(a, AmPartial{p.am_val[o], p.am_idx[o], p.am_sum[o]});
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    AmPartial c{__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.i, o), __shfl_xor_sync(0xffffffffu, a.s, o)};
+    am_combine(a, c);
+  }
+  if (lane == 0) { s_m[warp] = a.m; s_i[warp] = a.i; s_s[warp] = a.s; }
+  // ---- bbox head partial sums: n_box dot products + the row's sum of squares
+  const T* xr = reinterpret_cast<const T*>(p.x) + static_cast<size_t>(b) * p.ldx;
+  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const bool want_box = p.bbox || p.bbox_sig;
+  if (want_box) {
+    for (int k = tid; k < p.H; k += 128) {
+      const float xv = to_f<T>(xr[k]);
+      acc[6] = fmaf(xv, xv, acc[6]);
+      for (int o = 0; o < p.n_box; ++o)
+        acc[o] = fmaf(xv, to_f<T>(reinterpret_cast<const T*>(p.bbox_w)[static_cast<size_t>(o) * p.H + k]), acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < 7; ++o) {
+      const float v = warp_sum(acc[o]);
+      if (lane == 0) s_red[warp][o] = v;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    AmPartial r{s_m[0], s_i[0], s_s[0]};
+    for (int w = 1; w < 4; ++w) am_combine(r, AmPartial{s_m[w], s_i[w], s_s[w]});
+    const bool d = (r.i == p.eos) || (r.i == p.pad);
+    const float sc = d ? 0.f : 1.f / r.s;
+    const long long nxt = d ? p.pad : r.i;
+    s_next = nxt;
+    if (p.tok) p.tok[b] = r.i;
+    if (p.score) p.score[b] = sc;
+    if (p.done) p.done[b] = d ? 1 : 0;
+    if (p.next_ids) p.next_ids[b] = nxt;
+    const size_t ho = static_cast<size_t>(s) * p.B + b;
+    if (p.tok_hist) p.tok_hist[ho] = r.i;
+    if (p.score_hist) p.score_hist[ho] = sc;
+    if (p.done_hist) p.done_hist[ho] = d ? 1 : 0;
+    if (p.ids_io) p.ids_io[b] = nxt;
+    if (p.pos_io) p.pos_io[b] += 1;
+  }
+  if (want_box && tid < p.n_box) {
+    const float ssq = s_red[0][6] + s_red[1][6] + s_red[2][6] + s_red[3][6];
+    const float rs = rsqrtf(ssq * (1.0f / static_cast<float>(p.H)) + p.eps);
+    const float dot = s_red[0][tid] + s_red[1][tid] + s_red[2][tid] + s_red[3][tid];
+    float v = rnd<T>(fmaf(dot, rs, to_f<T>(reinterpret_cast<const T*>(p.bbox_b)[tid])));
+    v = rnd<T>(1.f / (1.f + expf(-v)));
+    const long long box = static_cast<long long>(v * p.bbox_size);
+    if (p.bbox_sig) p.bbox_sig[static_cast<size_t>(b) * p.n_box + tid] = v;
+    if (p.bbox) p.bbox[static_cast<size_t>(b) * p.n_box + tid] = box;
+    if (p.bbox_hist) p.bbox_hist[(static_cast<size_t>(s) * p.B + b) * p.n_box + tid] = box;
+  }
+  __syncthreads();
+  // ---- next step's input embedding (after every read of this row of x above)
+  if (p.x_next) {
+    const uint4* e = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.embed) + static_cast<size_t>(s_next) * p.H);
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.x_next) + static_cast<size_t>(b) * p.ldx_next);
+    for (int i = tid; i < (p.H >> 3); i += 128) o[i] = e[i];
+  }
+  if (p.step) {
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      const unsigned int old = atomicAdd(p.counter, 1u);
+      if (old == gridDim.x - 1) {       // every other block has read *step and finished: advance it for the next launch
+        *p.counter = 0u;
+        *p.step = s + 1;
+      }
+    }
+  }
+}
+
+int decode_tail(int dtype, const DecodeTailArgs& a, cudaStream_t st) {
+  if (a.rows <= 0) return 0;
+  if (a.n_box > 6) { set_error("decode_tail: at most 6 box outputs"); return -1; }
+  if (a.x_next && (a.H % 8 || a.ldx_next % 8)) { set_error("decode_tail: H and pitch must be multiples of 8"); return -1; }
+  TailParams p;
+  p.am_val = a.am_val; p.am_idx = a.am_idx; p.am_sum = a.am_sum; p.am_ld = a.am_ld; p.n_tiles = a.n_tiles;
+  p.x = a.x; p.ldx = a.ldx; p.H = a.H; p.eps = a.eps;
+  p.bbox_w = a.bbox_w; p.bbox_b = a.bbox_b; p.n_box = a.n_box; p.bbox_size = a.bbox_size;
+  p.embed = a.embed; p.x_next = a.x_next; p.ldx_next = a.ldx_next;
+  p.tok = a.tok; p.score = a.score; p.bbox = a.bbox; p.bbox_sig = a.bbox_sig; p.done = a.done; p.next_ids = a.next_ids;
+  p.step = a.step; p.counter = a.counter; p.B = a.rows;
+  p.tok_hist = a.tok_hist; p.score_hist = a.score_hist; p.bbox_hist = a.bbox_hist; p.done_hist = a.done_hist;
+  p.ids_io = a.ids_io; p.pos_io = a.pos_io;
+  p.eos = a.eos; p.pad = a.pad;
+  if (dtype == DT_BF16) launch_pdl(decode_tail_kernel<__nv_bfloat16>, dim3(a.rows), dim3(128), 0, st, p);
+  else launch_pdl(decode_tail_kernel<__half>, dim3(a.rows), dim3(128), 0, st, p);
   return launch_ok();
 }
 

@@ -6,6 +6,25 @@ namespace sb {
 
 int rmsnorm(int dtype, const void* x, int ldx, const void* w, void* y, int ldy, int rows, int H, float eps,
             const int* src_rows, cudaStream_t st, int mode = 0);
+// rs[row] = rsqrt(mean_k x[row,k]^2 + eps): the per-row scale of a GEMM that folds the RMSNorm weight into W (gemm.cuh).
+int row_rstd(int dtype, const void* x, int ldx, float* rs, int rows, int H, float eps, const int* src_rows, cudaStream_t st);
+
+// Tail of a greedy decode step (ops.cu: decode_tail_kernel): argmax partial reduce, bbox head, bookkeeping, next embedding.
+struct DecodeTailArgs {
+  int rows = 0;
+  const float* am_val = nullptr; const int* am_idx = nullptr; const float* am_sum = nullptr; int am_ld = 0, n_tiles = 0;
+  const void* x = nullptr; int ldx = 0; int H = 0; float eps = 0.f;         // final hidden state BEFORE the final norm
+  const void* bbox_w = nullptr; const void* bbox_b = nullptr; int n_box = 6; float bbox_size = 0.f;   // bbox_w has the norm weight folded in
+  const void* embed = nullptr; void* x_next = nullptr; int ldx_next = 0;      // write embed[next_id] into x_next[row]
+  long long* tok = nullptr; float* score = nullptr; long long* bbox = nullptr; float* bbox_sig = nullptr;
+  unsigned char* done = nullptr; long long* next_ids = nullptr;
+  int* step = nullptr; unsigned int* counter = nullptr;                       // device step counter of sb_rec_decode_steps
+  long long* tok_hist = nullptr; float* score_hist = nullptr; long long* bbox_hist = nullptr; unsigned char* done_hist = nullptr;
+  long long* ids_io = nullptr; int* pos_io = nullptr;
+  int eos = 0, pad = 0;
+};
+int decode_tail(int dtype, const DecodeTailArgs& a, cudaStream_t st);
+
 int gather_pad_rows(int dtype, const void* src, int src_is_f32, int lds, const int* perm, void* dst, int ldd, int rows,
                     int K, int Kp, cudaStream_t st);
 int rope_vision(int dtype, void* qkv, int ld, const int* pos_rc, const float* inv_freq, int n_tok, int nh, int d,

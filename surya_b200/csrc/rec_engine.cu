@@ -2,8 +2,8 @@
 //
 // Stands in for SuryaModel.forward (surya/common/surya/__init__.py:274-338) under RecognitionPredictor.prefill /
 // decode (surya/recognition/__init__.py:326-352, 354-471).  The layer loops live here (not in Python) so that a
-// decode step is ~90 back-to-back kernel launches on one stream, capturable into a CUDA graph and replayed with
-// token feedback / position increment done on the device (sb_rec_decode_steps).
+// decode step is 62 back-to-back kernel launches on one stream (5 per decoder layer + lm_head + tail), capturable into a
+// CUDA graph and replayed with token feedback / position increment / history done on the device (sb_rec_decode_steps).
 #include "../../include/surya_b200.h"
 #include "ops.cuh"
 #include "sb_ptx.cuh"
@@ -34,7 +34,12 @@ struct sb_rec_engine {
   void* vcache = nullptr;
   // staging for the device-side decode loop
   long long* st_tok = nullptr; float* st_score = nullptr; long long* st_bbox = nullptr; unsigned char* st_done = nullptr;
-  long long* st_next = nullptr; int* st_step = nullptr;
+  long long* st_next = nullptr; int* st_step = nullptr; unsigned int* st_counter = nullptr;
+  // folded RMSNorm: per-row 1/rms of the residual stream (prefill; decode steps compute it inside the GEMM)
+  float* rs = nullptr;
+  // lm_head argmax partials [rows, am_ld]: (max, argmax, sum exp) per 128 x am_bn logit tile
+  float* am_val = nullptr; int* am_idx = nullptr; float* am_sum = nullptr;
+  int am_ld = 0, am_bn = 0;
   int qkv_w_enc = 0, qkv_w_dec = 0;
   // CUDA graph cache for decode_steps
   cudaGraphExec_t graph_exec = nullptr;
@@ -43,12 +48,6 @@ struct sb_rec_engine {
   // the legacy default stream cannot be captured: decode_steps hops onto an engine-owned stream, ordered by events
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-  // decode chains: the batch is cut into row groups whose (strictly sequential, latency-bound) kernel chains run side by side
-  // on forked streams inside one step / one CUDA graph
-  static constexpr int MAX_CHAINS = 4;
-  int n_chains = 1;
-  cudaStream_t chain_stream[MAX_CHAINS] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHAINS] = {nullptr, nullptr, nullptr, nullptr};
   const void* graph_key[8] = {nullptr};
 
   const void* W(int idx) const { return w[idx]; }
@@ -66,10 +65,14 @@ struct sb_rec_engine {
 
 static size_t al256(size_t v) { return (v + 255) & ~size_t(255); }
 
+// norm: 0 = plain, 1 = folded RMSNorm with the per-row scale in e->rs (prefill), 2 = folded RMSNorm with the scale computed
+// inside the GEMM from the A tiles (decode steps, lm_head)
 static int linear(const sb_rec_engine* e, const void* A, int lda, const void* Wt, int ldw, void* C, int ldc, int M, int N,
                   int K, const void* bias_f32, const void* residual, int ldr, int act, int swiglu, cudaStream_t st,
-                  int allow_splitk = 0) {
+                  int allow_splitk = 0, int norm = 0) {
   GemmArgs a;
+  if (norm == 1) a.rowscale = e->rs;
+  if (norm == 2) { a.ssq_inline = 1; a.ssq_eps = e->c.rms_eps; a.ssq_k = K; }
   a.dtype = e->c.dtype;
   a.A = A; a.lda = lda; a.W = Wt; a.ldw = ldw; a.C = C; a.ldc = ldc;
   a.M = M; a.N = N; a.K = K;
@@ -129,39 +132,56 @@ static int run_vision(sb_rec_engine* e, const void* tiles, int tiles_f32, int n,
 }
 
 // ------------------------------------------------------------------------------------------------ decoder pieces
-static int dec_mlp_block(sb_rec_engine* e, int l, int rows, cudaStream_t st) {
-  const sb_rec_config& c = e->c;
-  const int D = c.dec_hidden;
-  CK(rmsnorm(c.dtype, e->x, D, e->WD(l, SB_RWD_POST_NORM), e->nbuf, D, rows, D, c.rms_eps, nullptr, st));
-  CK(linear(e, e->nbuf, D, e->WD(l, SB_RWD_GU_W), D, e->act, c.dec_inter_pad, rows, 2 * c.dec_inter_pad, D, nullptr,
-            nullptr, 0, ACT_SILU, 1, st));
-  CK(linear(e, e->act, c.dec_inter_pad, e->WD(l, SB_RWD_DOWN_W), c.dec_inter_pad, e->x, D, rows, D, c.dec_inter_pad,
-            nullptr, e->x, D, ACT_NONE, 0, st));
-  return 0;
-}
+// Every decoder RMSNorm is folded into the GEMM that consumes it (W' = W * g packed by the host, the GEMM epilogue scales each
+// row by 1/rms): the normalised activations never exist in memory and decode steps lose 25 launches.
+struct HeadOut {
+  void* logits = nullptr;
+  long long* tok = nullptr; float* score = nullptr; long long* bbox = nullptr; float* bbox_sig = nullptr;
+  unsigned char* done = nullptr; long long* next_ids = nullptr;
+  // device-side greedy loop (sb_rec_decode_steps)
+  int loop = 0;
+  long long* tok_hist = nullptr; float* score_hist = nullptr; long long* bbox_hist = nullptr; unsigned char* done_hist = nullptr;
+  long long* ids_io = nullptr; int* pos_io = nullptr;
+};
 
-static int run_heads(sb_rec_engine* e, const void* hidden, int rows, void* logits_out, long long* tok, float* score,
-                     long long* bbox, float* bbox_sig, unsigned char* done, long long* next_ids, cudaStream_t st) {
+// lm_head (tied embedding x final norm weight, online argmax epilogue) + decode_tail; `hidden` = residual stream rows BEFORE
+// the final norm.  The [rows, vocab] logits are only written when the caller asks for them.
+static int run_heads(sb_rec_engine* e, void* hidden, int rows, const HeadOut& o, cudaStream_t st) {
   const sb_rec_config& c = e->c;
   const int D = c.dec_hidden;
-  void* lg = logits_out ? logits_out : e->logits;
-  CK(linear(e, hidden, D, e->W(SB_RW_EMBED), D, lg, c.vocab, rows, c.vocab, D, e->W(SB_RW_LM_BIAS), nullptr, 0, ACT_NONE,
-            0, st));
-  if (tok || score || done || next_ids) {
-    CK(argmax_score(c.dtype, lg, c.vocab, rows, c.vocab, tok ? tok : e->st_tok, score ? score : e->st_score, done,
-                    next_ids, c.eos_id, c.pad_id, st));
+  GemmArgs a;
+  a.dtype = c.dtype;
+  a.A = hidden; a.lda = D; a.W = e->W(SB_RW_LM_W); a.ldw = D;
+  a.C = o.logits ? o.logits : e->logits; a.ldc = c.vocab;
+  a.M = rows; a.N = c.vocab; a.K = D;
+  a.bias = static_cast<const float*>(e->W(SB_RW_LM_BIAS));
+  a.w_constant = 1;
+  a.ssq_inline = 1; a.ssq_eps = c.rms_eps; a.ssq_k = D;
+  a.am_val = e->am_val; a.am_idx = e->am_idx; a.am_sum = e->am_sum; a.am_ld = e->am_ld;
+  a.store_c = o.logits ? 1 : 0;
+  CK(gemm_launch(a, st));
+  DecodeTailArgs t;
+  t.rows = rows;
+  t.am_val = e->am_val; t.am_idx = e->am_idx; t.am_sum = e->am_sum; t.am_ld = e->am_ld;
+  t.n_tiles = (c.vocab + e->am_bn - 1) / e->am_bn;
+  t.x = hidden; t.ldx = D; t.H = D; t.eps = c.rms_eps;
+  t.bbox_w = e->W(SB_RW_BBOX_W); t.bbox_b = e->W(SB_RW_BBOX_B); t.n_box = 6; t.bbox_size = c.bbox_size;
+  t.tok = o.tok; t.score = o.score; t.bbox = o.bbox; t.bbox_sig = o.bbox_sig; t.done = o.done; t.next_ids = o.next_ids;
+  t.eos = c.eos_id; t.pad = c.pad_id;
+  if (o.loop) {
+    t.embed = e->W(SB_RW_EMBED); t.x_next = hidden; t.ldx_next = D;
+    t.step = e->st_step; t.counter = e->st_counter;
+    t.tok_hist = o.tok_hist; t.score_hist = o.score_hist; t.bbox_hist = o.bbox_hist; t.done_hist = o.done_hist;
+    t.ids_io = o.ids_io; t.pos_io = o.pos_io;
+    if (!t.bbox && o.bbox_hist) t.bbox = e->st_bbox;   // the tail computes boxes when any box output is requested
   }
-  if (bbox || bbox_sig) {
-    CK(small_head(c.dtype, hidden, D, e->W(SB_RW_BBOX_W), e->W(SB_RW_BBOX_B), rows, D, 6, 1, bbox_sig, bbox, c.bbox_size, st));
-  }
-  return 0;
+  return decode_tail(c.dtype, t, st);
 }
 
 static int run_decoder_prefill(sb_rec_engine* e, const long long* ids, int n_tok, const int* feat_row, const int* hidx,
                                const int* widx, const int* tok_pos, const int* tok_slot, const int* seq_start,
-                               const int* seq_len, int n_seq, int max_len, const int* last_tok, void* logits,
-                               long long* tok, float* score, long long* bbox, float* bbox_sig, unsigned char* done,
-                               long long* next_ids, cudaStream_t st) {
+                               const int* seq_len, int n_seq, int max_len, const int* last_tok, const HeadOut& out,
+                               cudaStream_t st) {
   const sb_rec_config& c = e->c;
   const int D = c.dec_hidden, nh = c.dec_heads, nkv = c.dec_kv_heads, hd = c.dec_head_dim;
   const int Q = (nh + 2 * nkv) * hd;
@@ -170,9 +190,9 @@ static int run_decoder_prefill(sb_rec_engine* e, const long long* ids, int n_tok
                   e->W(SB_RW_W_EMBED), e->x, D, n_tok, D, st));
   uint8_t* qkv8 = static_cast<uint8_t*>(e->qkv);
   for (int l = 0; l < c.dec_layers; ++l) {
-    CK(rmsnorm(dt, e->x, D, e->WD(l, SB_RWD_IN_NORM), e->nbuf, D, n_tok, D, c.rms_eps, nullptr, st));
-    CK(linear(e, e->nbuf, D, e->WD(l, SB_RWD_QKV_W), D, e->qkv, Q, n_tok, Q, D, e->WD(l, SB_RWD_QKV_B), nullptr, 0,
-              ACT_NONE, 0, st));
+    CK(row_rstd(dt, e->x, D, e->rs, n_tok, D, c.rms_eps, nullptr, st));
+    CK(linear(e, e->x, D, e->WD(l, SB_RWD_QKV_W), D, e->qkv, Q, n_tok, Q, D, e->WD(l, SB_RWD_QKV_B), nullptr, 0, ACT_NONE, 0,
+              st, 0, /*norm=*/1));
     CK(rope_kv_append(dt, e->qkv, Q, tok_pos, tok_slot, static_cast<const float*>(e->W(SB_RW_DEC_INV_FREQ)), e->kc(l),
                       e->vc(l), n_tok, nh, nkv, hd, c.s_max, st));
     AttnArgs a;
@@ -186,107 +206,43 @@ static int run_decoder_prefill(sb_rec_engine* e, const long long* ids, int n_tok
     a.scale = 1.0f / sqrtf(static_cast<float>(hd));
     CK(attn_varlen(a, st));
     CK(linear(e, e->ao, nh * hd, e->WD(l, SB_RWD_O_W), nh * hd, e->x, D, n_tok, D, nh * hd, nullptr, e->x, D, ACT_NONE, 0, st));
-    CK(dec_mlp_block(e, l, n_tok, st));
+    CK(row_rstd(dt, e->x, D, e->rs, n_tok, D, c.rms_eps, nullptr, st));
+    CK(linear(e, e->x, D, e->WD(l, SB_RWD_GU_W), D, e->act, c.dec_inter_pad, n_tok, 2 * c.dec_inter_pad, D, nullptr, nullptr, 0,
+              ACT_SILU, 1, st, 0, /*norm=*/1));
+    CK(linear(e, e->act, c.dec_inter_pad, e->WD(l, SB_RWD_DOWN_W), c.dec_inter_pad, e->x, D, n_tok, D, c.dec_inter_pad,
+              nullptr, e->x, D, ACT_NONE, 0, st));
   }
-  CK(rmsnorm(dt, e->x, D, e->W(SB_RW_DEC_NORM), e->xl, D, n_seq, D, c.rms_eps, last_tok, st));
-  return run_heads(e, e->xl, n_seq, logits, tok, score, bbox, bbox_sig, done, next_ids, st);
+  // hidden[:, -1:, :] (surya/common/surya/__init__.py:323): the last real token of every sequence, still un-normalised
+  CK(gather_pad_rows(dt, e->x, 0, D, last_tok, e->xl, D, n_seq, D, D, st));
+  return run_heads(e, e->xl, n_seq, out, st);
 }
 
-// One greedy decode step for batch rows [r0, r0 + B): every workspace is row-major, so a row group is a pointer offset.
-static int run_decode_step(sb_rec_engine* e, const long long* ids, const int* slot, const int* pos, int r0, int B, void* logits,
-                           long long* tok, float* score, long long* bbox, float* bbox_sig, unsigned char* done,
-                           long long* next_ids, cudaStream_t st) {
+// One greedy decode step for `B` rows: 5 launches per layer (qkv GEMM -> attention -> o GEMM -> gate/up GEMM -> down GEMM)
+// + lm_head + tail.  ids == nullptr means e->x already holds the input embeddings (written by the previous step's tail).
+static int run_decode_step(sb_rec_engine* e, const long long* ids, const int* slot, const int* pos, int B, const HeadOut& out,
+                           cudaStream_t st) {
   const sb_rec_config& c = e->c;
   const int D = c.dec_hidden, nh = c.dec_heads, nkv = c.dec_kv_heads, hd = c.dec_head_dim;
   const int Q = (nh + 2 * nkv) * hd;
   const int dt = c.dtype;
-  auto rows = [&](void* base, size_t width) { return static_cast<void*>(static_cast<uint8_t*>(base) + static_cast<size_t>(r0) * width * e->esz); };
-  void* x = rows(e->x, D);
-  void* nbuf = rows(e->nbuf, D);
-  void* qkv = rows(e->qkv, Q);
-  void* ao = rows(e->ao, nh * hd);
-  void* act = rows(e->act, c.dec_inter_pad);
-  void* xl = rows(e->xl, D);
-  ids += r0; slot += r0; pos += r0;
-  CK(embed_rows(dt, ids, e->W(SB_RW_EMBED), x, D, B, D, st));
+  void* x = e->x;
+  if (ids) CK(embed_rows(dt, ids, e->W(SB_RW_EMBED), x, D, B, D, st));
   for (int l = 0; l < c.dec_layers; ++l) {
-    CK(rmsnorm(dt, x, D, e->WD(l, SB_RWD_IN_NORM), nbuf, D, B, D, c.rms_eps, nullptr, st));
-    CK(linear(e, nbuf, D, e->WD(l, SB_RWD_QKV_W), D, qkv, Q, B, Q, D, e->WD(l, SB_RWD_QKV_B), nullptr, 0, ACT_NONE, 0, st));
+    CK(linear(e, x, D, e->WD(l, SB_RWD_QKV_W), D, e->qkv, Q, B, Q, D, e->WD(l, SB_RWD_QKV_B), nullptr, 0, ACT_NONE, 0, st, 0,
+              /*norm=*/2));
     DecodeAttnArgs a;
-    a.dtype = dt; a.qkv = qkv; a.ld = Q; a.kcache = e->kc(l); a.vcache = e->vc(l); a.slot = slot; a.pos = pos;
+    a.dtype = dt; a.qkv = e->qkv; a.ld = Q; a.kcache = e->kc(l); a.vcache = e->vc(l); a.slot = slot; a.pos = pos;
     a.inv_freq = static_cast<const float*>(e->W(SB_RW_DEC_INV_FREQ));
-    a.out = ao; a.ldo = nh * hd; a.batch = B; a.n_heads = nh; a.n_kv_heads = nkv; a.head_dim = hd; a.s_max = c.s_max;
+    a.out = e->ao; a.ldo = nh * hd; a.batch = B; a.n_heads = nh; a.n_kv_heads = nkv; a.head_dim = hd; a.s_max = c.s_max;
     a.scale = 1.0f / sqrtf(static_cast<float>(hd));
     CK(decode_attn(a, st));
-    CK(linear(e, ao, nh * hd, e->WD(l, SB_RWD_O_W), nh * hd, x, D, B, D, nh * hd, nullptr, x, D, ACT_NONE, 0, st));
-    CK(rmsnorm(dt, x, D, e->WD(l, SB_RWD_POST_NORM), nbuf, D, B, D, c.rms_eps, nullptr, st));
-    CK(linear(e, nbuf, D, e->WD(l, SB_RWD_GU_W), D, act, c.dec_inter_pad, B, 2 * c.dec_inter_pad, D, nullptr, nullptr, 0,
-              ACT_SILU, 1, st));
-    CK(linear(e, act, c.dec_inter_pad, e->WD(l, SB_RWD_DOWN_W), c.dec_inter_pad, x, D, B, D, c.dec_inter_pad, nullptr, x, D,
+    CK(linear(e, e->ao, nh * hd, e->WD(l, SB_RWD_O_W), nh * hd, x, D, B, D, nh * hd, nullptr, x, D, ACT_NONE, 0, st));
+    CK(linear(e, x, D, e->WD(l, SB_RWD_GU_W), D, e->act, c.dec_inter_pad, B, 2 * c.dec_inter_pad, D, nullptr, nullptr, 0,
+              ACT_SILU, 1, st, 0, /*norm=*/2));
+    CK(linear(e, e->act, c.dec_inter_pad, e->WD(l, SB_RWD_DOWN_W), c.dec_inter_pad, x, D, B, D, c.dec_inter_pad, nullptr, x, D,
               ACT_NONE, 0, st, /*allow_splitk=*/1));
   }
-  CK(rmsnorm(dt, x, D, e->W(SB_RW_DEC_NORM), xl, D, B, D, c.rms_eps, nullptr, st));
-  void* lg = logits ? static_cast<void*>(static_cast<uint8_t*>(logits) + static_cast<size_t>(r0) * c.vocab * e->esz)
-                    : rows(e->logits, c.vocab);
-  return run_heads(e, xl, B, lg, tok ? tok + r0 : nullptr, score ? score + r0 : nullptr, bbox ? bbox + static_cast<size_t>(r0) * 6 : nullptr,
-                   bbox_sig ? bbox_sig + static_cast<size_t>(r0) * 6 : nullptr, done ? done + r0 : nullptr,
-                   next_ids ? next_ids + r0 : nullptr, st);
-}
-
-// The whole batch as n_chains row groups on forked streams (joined back into `st`); works eagerly and under stream capture.
-static int run_decode_step_chained(sb_rec_engine* e, const long long* ids, const int* slot, const int* pos, int B, void* logits,
-                                   long long* tok, float* score, long long* bbox, float* bbox_sig, unsigned char* done,
-                                   long long* next_ids, cudaStream_t st) {
-  int nc = e->n_chains;
-  if (nc > sb_rec_engine::MAX_CHAINS) nc = sb_rec_engine::MAX_CHAINS;
-  while (nc > 1 && B / nc < 32) --nc;            // do not cut below one warp-row group
-  if (nc <= 1) return run_decode_step(e, ids, slot, pos, 0, B, logits, tok, score, bbox, bbox_sig, done, next_ids, st);
-  if (!e->ev_fork) {
-    if (cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); set_error("chain event"); return -20; }
-    for (int i = 1; i < sb_rec_engine::MAX_CHAINS; ++i) {
-      if (cudaStreamCreateWithFlags(&e->chain_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
-          cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
-        cudaGetLastError(); set_error("chain stream"); return -20;
-      }
-    }
-  }
-  const int per = ((B + nc - 1) / nc + 7) & ~7;   // row groups in multiples of 8
-  if (cudaEventRecord(e->ev_fork, st) != cudaSuccess) { cudaGetLastError(); set_error("chain fork"); return -21; }
-  for (int i = 0; i < nc; ++i) {
-    const int r0 = i * per;
-    const int n = (r0 + per <= B) ? per : B - r0;
-    if (n <= 0) break;
-    cudaStream_t s = i == 0 ? st : e->chain_stream[i];
-    if (i) cudaStreamWaitEvent(s, e->ev_fork, 0);
-    CK(run_decode_step(e, ids, slot, pos, r0, n, logits, tok, score, bbox, bbox_sig, done, next_ids, s));
-    if (i) {
-      cudaEventRecord(e->ev_join[i], s);
-      cudaStreamWaitEvent(st, e->ev_join[i], 0);
-    }
-  }
-  return 0;
-}
-
-// Device-side bookkeeping between two greedy steps: history append, token feedback, position increment.
-__global__ void record_step_kernel(int* step, int B, const long long* tok, const float* score, const long long* bbox,
-                                   const unsigned char* done, const long long* next, long long* tok_hist,
-                                   float* score_hist, long long* bbox_hist, unsigned char* done_hist,
-                                   long long* ids_io, int* pos_io) {
-  pdl_trigger();
-  pdl_wait();
-  const int s = *step;
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    size_t o = static_cast<size_t>(s) * B + b;
-    if (tok_hist) tok_hist[o] = tok[b];
-    if (score_hist) score_hist[o] = score[b];
-    if (done_hist) done_hist[o] = done[b];
-    if (bbox_hist)
-      for (int j = 0; j < 6; ++j) bbox_hist[o * 6 + j] = bbox[b * 6 + j];
-    ids_io[b] = next[b];
-    pos_io[b] += 1;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) *step = s + 1;
+  return run_heads(e, x, B, out, st);
 }
 
 extern "C" {
@@ -305,10 +261,6 @@ int sb_rec_create(const sb_rec_config* cfg, const void* const* weights, int n_we
     if (!weights[i]) { set_error("sb_rec_create: weight pointer %d is null", i); return -5; }
   auto* e = new sb_rec_engine();
   e->c = *cfg;
-  if (const char* ev = getenv("SB_DECODE_CHAINS")) {
-    const int v = atoi(ev);
-    if (v >= 1 && v <= sb_rec_engine::MAX_CHAINS) e->n_chains = v;
-  }
   e->w.assign(weights, weights + n_weights);
   const sb_rec_config& c = e->c;
   const size_t es = e->esz;
@@ -321,12 +273,16 @@ int sb_rec_create(const sb_rec_config* cfg, const void* const* weights, int n_we
   const size_t nm = (size_t)c.max_patches / c.merge_unit + 1;
   const size_t kv_bytes = (size_t)c.dec_layers * c.max_slots * c.dec_kv_heads * c.s_max * c.dec_head_dim * es;
   const size_t rows_out = (size_t)(c.max_seqs > c.max_slots ? c.max_seqs : c.max_slots);
+  e->am_bn = gemm_argmax_tile(static_cast<int>(rows_out), c.vocab);
+  e->am_ld = (c.vocab + e->am_bn - 1) / e->am_bn;
+  const size_t am_elems = rows_out * static_cast<size_t>(e->am_ld);
   size_t sizes[] = {
       R * Hm * es, R * Hm * es, R * qkvw * es, R * aow * es, R * actw * es,           // x nbuf qkv ao act
       (size_t)c.max_patches * c.patch_dim_pad * es, nm * c.merge_unit * c.enc_hidden * es,  // x0 m1
       nm * c.enc_out_hidden * es, rows_out * c.dec_hidden * es, rows_out * c.vocab * es,   // feat xl logits
       kv_bytes, kv_bytes,
-      rows_out * 8, rows_out * 4, rows_out * 6 * 8, rows_out, rows_out * 8, 256};
+      rows_out * 8, rows_out * 4, rows_out * 6 * 8, rows_out, rows_out * 8, 256, 256,
+      R * 4, am_elems * 4, am_elems * 4, am_elems * 4};
   size_t total = 0;
   for (size_t s : sizes) total += al256(s);
   cudaError_t ce = cudaMalloc(&e->arena, total);
@@ -339,7 +295,8 @@ int sb_rec_create(const sb_rec_config* cfg, const void* const* weights, int n_we
   uint8_t* p = e->arena;
   void** slots[] = {&e->x, &e->nbuf, &e->qkv, &e->ao, &e->act, &e->x0, &e->m1, &e->feat, &e->xl, &e->logits,
                     &e->kcache, &e->vcache, (void**)&e->st_tok, (void**)&e->st_score, (void**)&e->st_bbox,
-                    (void**)&e->st_done, (void**)&e->st_next, (void**)&e->st_step};
+                    (void**)&e->st_done, (void**)&e->st_next, (void**)&e->st_step, (void**)&e->st_counter,
+                    (void**)&e->rs, (void**)&e->am_val, (void**)&e->am_idx, (void**)&e->am_sum};
   for (size_t i = 0; i < sizeof(sizes) / sizeof(sizes[0]); ++i) {
     *slots[i] = p;
     p += al256(sizes[i]);
@@ -355,11 +312,6 @@ void sb_rec_destroy(sb_rec_engine* e) {
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
-  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
-  for (int i = 1; i < sb_rec_engine::MAX_CHAINS; ++i) {
-    if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
-    if (e->chain_stream[i]) cudaStreamDestroy(e->chain_stream[i]);
-  }
   if (e->arena) cudaFree(e->arena);
   delete e;
 }
@@ -386,8 +338,10 @@ int sb_rec_prefill(sb_rec_engine* e, const void* tiles, int tiles_f32, int n_pat
   if (n_patches > 0)
     CK(run_vision(e, tiles, tiles_f32, n_patches, patch_perm, patch_pos_rc, win_start, win_len, n_win, max_win_len,
                   img_start, img_len, n_img, max_img_len, st));
+  HeadOut o;
+  o.logits = logits; o.tok = tok; o.score = score; o.bbox = bbox; o.bbox_sig = bbox_sig; o.done = done; o.next_ids = next_ids;
   return run_decoder_prefill(e, input_ids, n_tok, tok_feat_row, tok_hidx, tok_widx, tok_pos, tok_slot, seq_start,
-                             seq_len, n_seq, max_seq_len, last_tok, logits, tok, score, bbox, bbox_sig, done, next_ids, st);
+                             seq_len, n_seq, max_seq_len, last_tok, o, st);
 }
 
 int sb_rec_decode(sb_rec_engine* e, const long long* input_ids, const int* slot, const int* pos, int batch, void* logits,
@@ -395,8 +349,10 @@ int sb_rec_decode(sb_rec_engine* e, const long long* input_ids, const int* slot,
                   long long* next_ids, void* stream) {
   if (!e) { set_error("sb_rec_decode: null engine"); return -1; }
   if (batch > e->c.max_slots || batch > e->c.max_tokens) { set_error("sb_rec_decode: batch %d exceeds capacity", batch); return -2; }
-  return run_decode_step(e, input_ids, slot, pos, 0, batch, logits, tok, score, bbox, bbox_sig, done, next_ids,
-                         static_cast<cudaStream_t>(stream));
+  if (!input_ids) { set_error("sb_rec_decode: null input_ids"); return -3; }
+  HeadOut o;
+  o.logits = logits; o.tok = tok; o.score = score; o.bbox = bbox; o.bbox_sig = bbox_sig; o.done = done; o.next_ids = next_ids;
+  return run_decode_step(e, input_ids, slot, pos, batch, o, static_cast<cudaStream_t>(stream));
 }
 
 int sb_rec_decode_steps(sb_rec_engine* e, long long* ids_io, const int* slot, int* pos_io, int batch, int n_steps,
@@ -425,15 +381,15 @@ int sb_rec_decode_steps(sb_rec_engine* e, long long* ids_io, const int* slot, in
     bool on; cudaStream_t own, caller; cudaEvent_t ev;
     ~Rejoin() { if (on) { cudaEventRecord(ev, own); cudaStreamWaitEvent(caller, ev, 0); } }
   } rejoin{hop, e->own_stream, caller, e->ev_out};
-  if (cudaMemsetAsync(e->st_step, 0, sizeof(int), st) != cudaSuccess) { cudaGetLastError(); set_error("memset failed"); return -3; }
-  auto one_step = [&](cudaStream_t s) -> int {
-    CK(run_decode_step_chained(e, ids_io, slot, pos_io, batch, nullptr, e->st_tok, e->st_score, e->st_bbox, nullptr,
-                               e->st_done, e->st_next, s));
-    launch_pdl(record_step_kernel, dim3(1), dim3(256), 0, s, e->st_step, batch, (const long long*)e->st_tok,
-               (const float*)e->st_score, (const long long*)e->st_bbox, (const unsigned char*)e->st_done,
-               (const long long*)e->st_next, tok_hist, score_hist, bbox_hist, done_hist, ids_io, pos_io);
-    return launch_ok();
-  };
+  if (cudaMemsetAsync(e->st_step, 0, sizeof(int), st) != cudaSuccess ||
+      cudaMemsetAsync(e->st_counter, 0, sizeof(unsigned int), st) != cudaSuccess) { cudaGetLastError(); set_error("memset failed"); return -3; }
+  // the first step's input embeddings; every later step finds them written by the previous step's tail kernel
+  CK(embed_rows(e->c.dtype, ids_io, e->W(SB_RW_EMBED), e->x, e->c.dec_hidden, batch, e->c.dec_hidden, st));
+  HeadOut ho;
+  ho.loop = 1;
+  ho.tok_hist = tok_hist; ho.score_hist = score_hist; ho.bbox_hist = bbox_hist; ho.done_hist = done_hist;
+  ho.ids_io = ids_io; ho.pos_io = pos_io;
+  auto one_step = [&](cudaStream_t s) -> int { return run_decode_step(e, nullptr, slot, pos_io, batch, ho, s); };
   if (!use_graph) {
     for (int i = 0; i < n_steps; ++i) CK(one_step(st));
     return 0;
@@ -465,14 +421,6 @@ int sb_rec_decode_steps(sb_rec_engine* e, long long* ids_io, const int* slot, in
     if (cudaGraphLaunch(e->graph_exec, st) != cudaSuccess) { cudaGetLastError(); set_error("cudaGraphLaunch failed"); return -7; }
     count_launches(e->graph_nodes);
   }
-  return 0;
-}
-
-int sb_rec_set_decode_chains(sb_rec_engine* e, int n_chains) {
-  if (!e) { set_error("sb_rec_set_decode_chains: null engine"); return -1; }
-  if (n_chains < 1 || n_chains > sb_rec_engine::MAX_CHAINS) { set_error("sb_rec_set_decode_chains: 1..%d", sb_rec_engine::MAX_CHAINS); return -2; }
-  if (n_chains != e->n_chains && e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
-  e->n_chains = n_chains;
   return 0;
 }
 

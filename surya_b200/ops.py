@@ -10,7 +10,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import c_float, c_int, check, ptr, stream_ptr
+from ._lib import c_float, c_int, c_void_p, check, ptr, stream_ptr
 
 ACT = {"none": 0, "gelu": 1, "gelu_erf": 1, "silu": 2, "hardswish": 3, "relu": 4, "gelu_tanh": 5}
 
@@ -28,9 +28,13 @@ def _rowmajor(t: torch.Tensor) -> int:
     return t.stride(0)
 
 
-def gemm(a, w, bias=None, residual=None, act="none", swiglu=False, out=None, out_f32=False, force_bn=0, splitk=False):
+def gemm(a, w, bias=None, residual=None, act="none", swiglu=False, out=None, out_f32=False, force_bn=0, splitk=False,
+         rms_eps=None, rowscale=None, argmax=None, argmax_only=False):
     """out[M, Nout] = epi(a[M,K] @ w[N,K]^T); bias fp32 [N]; see sb_gemm.  splitk=True lets the heuristic use the split-K
-    cluster kernel (decode-sized M only)."""
+    cluster kernel (decode-sized M only).
+    rms_eps / rowscale: RMSNorm folded into the GEMM (sb_gemm_rmsnorm): w already carries the norm weight, rows are scaled by
+    `rowscale` (fp32 [M]) or by 1/rms computed in the kernel with rms_eps.  argmax: dict filled with the per-tile partials
+    (val, idx, sum) of the online argmax epilogue; argmax_only skips writing the logits."""
     if splitk and force_bn == 0:
         force_bn = -1
     lib = _lib.load()
@@ -42,10 +46,39 @@ def gemm(a, w, bias=None, residual=None, act="none", swiglu=False, out=None, out
         out = torch.empty((M, n_out), device=a.device, dtype=torch.float32 if out_f32 else a.dtype)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() >= N
+    if rms_eps is not None or rowscale is not None or argmax is not None or argmax_only:
+        assert not out_f32
+        am = None
+        if argmax is not None or argmax_only:
+            bn = force_bn if force_bn > 0 else int(lib.sb_gemm_argmax_tile(c_int(M), c_int(N)))
+            nt = (N + bn - 1) // bn
+            am = (torch.empty((M, nt), device=a.device, dtype=torch.float32), torch.empty((M, nt), device=a.device, dtype=torch.int32),
+                  torch.empty((M, nt), device=a.device, dtype=torch.float32))
+            if argmax is not None:
+                argmax.update(val=am[0], idx=am[1], sum=am[2], tile=bn)
+            force_bn = bn
+        check(lib.sb_gemm_rmsnorm(dt_code(a.dtype), ptr(a), c_int(_rowmajor(a)), ptr(w), c_int(_rowmajor(w)), ptr(out),
+                                  c_int(_rowmajor(out)), c_int(M), c_int(N), c_int(K), ptr(bias), ptr(residual),
+                                  c_int(_rowmajor(residual) if residual is not None else 0), c_int(ACT[act]),
+                                  c_int(1 if swiglu else 0), ptr(rowscale), c_float(rms_eps if rms_eps is not None else 0.0),
+                                  ptr(am[0]) if am else c_void_p(0), ptr(am[1]) if am else c_void_p(0),
+                                  ptr(am[2]) if am else c_void_p(0), c_int(am[0].shape[1] if am else 0),
+                                  c_int(0 if argmax_only else 1), c_int(max(force_bn, 0)), stream_ptr()), "sb_gemm_rmsnorm")
+        return out
     check(lib.sb_gemm(dt_code(a.dtype), ptr(a), c_int(_rowmajor(a)), ptr(w), c_int(_rowmajor(w)), ptr(out),
                       c_int(_rowmajor(out)), c_int(M), c_int(N), c_int(K), ptr(bias), ptr(residual),
                       c_int(_rowmajor(residual) if residual is not None else 0), c_int(ACT[act]),
                       c_int(1 if swiglu else 0), c_int(1 if out_f32 else 0), c_int(force_bn), stream_ptr()), "sb_gemm")
+    return out
+
+
+def row_rstd(x, eps=1e-6, src_rows=None):
+    """fp32 [rows]: rsqrt(mean(x^2) + eps) per row, summed in the order the GEMM's in-kernel pass uses."""
+    lib = _lib.load()
+    rows = x.shape[0] if src_rows is None else src_rows.numel()
+    out = torch.empty(rows, device=x.device, dtype=torch.float32)
+    check(lib.sb_row_rstd(dt_code(x.dtype), ptr(x), c_int(_rowmajor(x)), ptr(out), c_int(rows), c_int(x.shape[1]), c_float(eps),
+                          ptr(src_rows), stream_ptr()), "sb_row_rstd")
     return out
 
 

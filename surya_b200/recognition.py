@@ -79,20 +79,28 @@ def pack_rec_weights(sd: Dict[str, torch.Tensor], cfg: RecConfig, dtype: torch.d
     def F32(x):
         return x.float().contiguous().to(device)
 
+    def FOLD(w, g):
+        """Linear weight with the preceding RMSNorm weight folded in: W'[n, k] = W[n, k] * g[k], formed from the 16-bit images
+        of both (what `model.to(dtype)` holds) in fp32 and rounded once.  The reference computes W @ (g * T(x * rstd))
+        (decoder/__init__.py:241-258); the engine computes rstd * (W' @ x) with rstd applied to the fp32 accumulator in the GEMM
+        epilogue — same algebra, one rounding moved from the activations to the weights."""
+        return (w.to(dtype).float() * g.to(dtype).float()[None, :]).to(dtype).contiguous().to(device)
+
     ip_e, ip_d = align(e.intermediate_size, 8), align(d.intermediate_size, 8)
     pdp = align(e.patch_dim, 8)
     hd_e, hd_d = e.head_dim, d.head_dim
     p = "vision_encoder."
+    g_final = sd["decoder.norm.weight"]
     fixed = [
         T(_pad_cols(sd[p + "patch_embed.proj.weight"].reshape(e.hidden_size, -1), pdp)),
         T(sd[p + "merger.ln_q.weight"]),
         T(sd[p + "merger.mlp.0.weight"]), B32(sd[p + "merger.mlp.0.bias"]),
         T(sd[p + "merger.mlp.2.weight"]), B32(sd[p + "merger.mlp.2.bias"]),
         F32(1.0 / (10000.0 ** (torch.arange(0, hd_e // 2, 2, dtype=torch.float) / (hd_e // 2)))),
-        T(sd["decoder.norm.weight"]),
+        FOLD(sd["embedder.token_embed.weight"], g_final),       # lm_head is tied to the embedding (surya/common/surya/__init__.py:111-116)
         T(sd["embedder.token_embed.weight"]),
         B32(sd["lm_head.bias"]),
-        T(sd["bbox_head.weight"]), T(sd["bbox_head.bias"]),
+        FOLD(sd["bbox_head.weight"], g_final), T(sd["bbox_head.bias"]),
         T(sd["img_h_embed.weight"]), T(sd["img_w_embed.weight"]),
         F32(1.0 / (d.rope_theta ** (torch.arange(0, hd_d, 2, dtype=torch.int64).float() / hd_d))),
     ]
@@ -123,11 +131,10 @@ def pack_rec_weights(sd: Dict[str, torch.Tensor], cfg: RecConfig, dtype: torch.d
         qkv_b = torch.cat([sd[b + "self_attn.q_proj.bias"], sd[b + "self_attn.k_proj.bias"],
                            sd[b + "self_attn.v_proj.bias"]], 0)
         dec += [
-            T(sd[b + "input_layernorm.weight"]),
-            T(qkv_w), B32(qkv_b),
+            FOLD(qkv_w, sd[b + "input_layernorm.weight"]), B32(qkv_b),
             T(sd[b + "self_attn.o_proj.weight"]),
-            T(sd[b + "post_attention_layernorm.weight"]),
-            T(_interleave_rows(sd[b + "mlp.gate_proj.weight"], sd[b + "mlp.up_proj.weight"], ip_d)),
+            FOLD(_interleave_rows(sd[b + "mlp.gate_proj.weight"], sd[b + "mlp.up_proj.weight"], ip_d),
+                 sd[b + "post_attention_layernorm.weight"]),
             T(_pad_cols(sd[b + "mlp.down_proj.weight"], ip_d)),
         ]
     return fixed + enc + dec
@@ -371,10 +378,6 @@ class RecEngine:
                                      ptr(out["tok"]), ptr(out["score"]), ptr(out["bbox"]), ptr(out["bbox_sig"]),
                                      ptr(out["done"]), ptr(out["next_ids"]), stream_ptr()), "sb_rec_decode")
         return out
-
-    def set_decode_chains(self, n: int):
-        """Row groups whose decode kernel chains overlap on forked streams (sb_rec_set_decode_chains); results unchanged."""
-        check(self.lib.sb_rec_set_decode_chains(self._h, c_int(n)), "sb_rec_set_decode_chains")
 
     def decode_steps(self, ids_io: torch.Tensor, slot: torch.Tensor, pos_io: torch.Tensor, n_steps: int,
                      hist: Optional[dict] = None, use_graph: bool = True, max_pos: Optional[int] = None):

@@ -42,7 +42,7 @@ def rec_state_dict(cfg: RecConfig, seed: int = 0, std: float | None = None) -> D
       * token embedding: first half of the channels N(0, 0.3) (the token survives in the residual stream), second half N(0, std);
         final RMSNorm weight is ZERO on the first half, so the tied lm_head reads only channels where the embedding is small —
         otherwise logit[tok] = |E_tok| * cos(h, E_tok) dominates and greedy decoding repeats its own input;
-      * lm_head bias -20 on the special ids except EOS (they are never valid outputs)."""
+      * lm_head bias -6 on the special ids except EOS (they are never valid outputs)."""
     sd: Dict[str, torch.Tensor] = {}
     e, d = cfg.vision_encoder, cfg.decoder
     H = e.hidden_size
@@ -98,8 +98,8 @@ def rec_state_dict(cfg: RecConfig, seed: int = 0, std: float | None = None) -> D
     sd["lm_head.bias"] = _normal("lm_head.bias", (cfg.vocab_size,), std, seed)
     # special ids other than EOS are never valid outputs (feeding IMAGE back trips an assert in the reference,
     # surya/common/surya/__init__.py:227); a trained head suppresses them, the synthetic one does it through the bias
-    sd["lm_head.bias"][2:16] = -20.0
-    sd["lm_head.bias"][0] = -20.0
+    sd["lm_head.bias"][2:16] = -6.0
+    sd["lm_head.bias"][0] = -6.0
     sd["bbox_head.weight"] = _normal("bbox_head.weight", (6, D), std, seed)
     sd["bbox_head.bias"] = _normal("bbox_head.bias", (6,), std, seed)
     sd["img_h_embed.weight"] = _normal("img_h_embed.weight", (cfg.image_embed_encoding_size, D), std, seed)

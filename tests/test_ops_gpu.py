@@ -137,6 +137,79 @@ def test_rmsnorm(built_lib, dtype):
 
 
 @pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("M,N,K,swiglu,bias,res", [(256, 1920, 1280, False, True, False), (256, 6848, 1280, True, False, False),
+                                                   (200, 1280, 592, False, False, True), (1000, 1920, 1280, False, True, False),
+                                                   (37, 640, 320, False, True, False)])
+def test_gemm_folded_rmsnorm(built_lib, dtype, M, N, K, swiglu, bias, res):
+    """RMSNorm folded into the GEMM (sb_gemm_rmsnorm): C = epi(rs[m] * (x W'^T) + b).  (a) against the fp32 restatement with
+    the output roundings; (b) the in-kernel 1/rms (decode path) and the row_rstd + rowscale path (prefill) must agree BIT FOR
+    BIT, and both with an fp32 torch rsqrt to 2 ulp of fp32; (c) tiles wider / narrower than the default give the same bits."""
+    from surya_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M * 11 + N + K)
+    x = (torch.randn(M, K, device="cuda", generator=g) * 1.5).to(dtype)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.03).to(dtype)
+    b = (torch.randn(N, device="cuda", generator=g) * 0.1).to(dtype).float() if bias else None
+    r = (torch.randn(M, N, device="cuda", generator=g) * 0.5).to(dtype) if res else None
+    eps = 1e-6
+    rs = ops.row_rstd(x, eps)
+    rs_ref = torch.rsqrt(x.float().pow(2).mean(-1) + eps)
+    assert ((rs - rs_ref).abs() <= 4e-7 * rs_ref.abs()).all()
+    got_inline = ops.gemm(x, w, bias=b, residual=r, act="silu" if swiglu else "none", swiglu=swiglu, rms_eps=eps)
+    got_scale = ops.gemm(x, w, bias=b, residual=r, act="silu" if swiglu else "none", swiglu=swiglu, rowscale=rs)
+    assert torch.equal(got_inline, got_scale), "in-kernel 1/rms and row_rstd path differ"
+    if not swiglu and N % 128 == 0:
+        assert torch.equal(ops.gemm(x, w, bias=b, residual=r, rowscale=rs, force_bn=128), got_scale)
+        assert torch.equal(ops.gemm(x, w, bias=b, residual=r, rms_eps=eps, force_bn=64), got_scale)
+    acc = (x.float() @ w.float().t()) * rs_ref[:, None]
+    if b is not None:
+        acc = acc + b
+    lin = acc.to(dtype).float()
+    if swiglu:
+        gt, up = lin[:, 0::2], lin[:, 1::2]
+        ref = (torch.nn.functional.silu(gt).to(dtype).float() * up).to(dtype)
+    else:
+        ref = lin if r is None else (lin + r.float())
+        ref = ref.to(dtype)
+    _close(got_inline, ref, dtype, ulps=2.0, what="folded rmsnorm gemm", scale=lin if r is not None else None)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("M,N,K", [(256, 65792, 1280), (5, 1000, 320), (130, 4104, 640)])
+def test_gemm_argmax_epilogue(built_lib, dtype, M, N, K):
+    """lm_head with the online argmax epilogue: per-tile (max, first argmax, sum exp) partials reduce to exactly the argmax /
+    max-softmax of the 16-bit logits the plain path writes (surya/recognition/__init__.py:294-324), ties resolved to the
+    lowest index like torch.argmax; argmax_only must not touch C."""
+    from surya_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    x = (torch.randn(M, K, device="cuda", generator=g)).to(dtype)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.02).to(dtype)
+    w[N // 3] = w[N // 7]                      # force exact ties between two columns
+    b = (torch.randn(N, device="cuda", generator=g) * 0.02).to(dtype).float()
+    b[N // 3] = b[N // 7]
+    eps = 1e-6
+    am = {}
+    logits = ops.gemm(x, w, bias=b, rms_eps=eps, argmax=am)
+    ref_logits = ops.gemm(x, w, bias=b, rms_eps=eps)
+    assert torch.equal(logits, ref_logits)
+    val, idx, ssum = am["val"], am["idx"].long(), am["sum"]
+    m = val.max(-1).values
+    cand = torch.where(val == m[:, None], idx, torch.full_like(idx, 1 << 40))
+    tok = cand.min(-1).values
+    lf = ref_logits.float()
+    assert torch.equal(tok, lf.argmax(-1)), "argmax of the partials differs from torch.argmax of the logits"
+    denom = (ssum * torch.exp(val - m[:, None])).sum(-1)
+    score = 1.0 / denom
+    ref_score = torch.softmax(lf, -1).max(-1).values
+    assert ((score - ref_score).abs() <= 2e-5 + 1e-4 * ref_score).all()
+    canary = torch.full((M, N), 7.0, device="cuda", dtype=dtype)
+    am2 = {}
+    ops.gemm(x, w, bias=b, rms_eps=eps, argmax=am2, argmax_only=True, out=canary)
+    assert (canary == 7.0).all() and torch.equal(am2["idx"], am["idx"]) and torch.equal(am2["val"], am["val"])
+
+
+@pytest.mark.parametrize("dtype", DT)
 def test_gather_pad(built_lib, dtype):
     from surya_b200 import ops
 
