@@ -161,7 +161,7 @@ def test_weight_packing_layout():
     sd = rec_state_dict(cfg, seed=0)
     w = pack_rec_weights(sd, cfg, torch.bfloat16, "cpu")
     e, d = cfg.vision_encoder, cfg.decoder
-    assert len(w) == 15 + 10 * e.depth + 7 * d.num_hidden_layers
+    assert len(w) == 15 + 10 * e.depth + 5 * d.num_hidden_layers
     assert w[0].shape == (e.hidden_size, align(e.patch_dim, 8)) and (w[0][:, e.patch_dim:] == 0).all()
     gu = w[15 + 6]
     ip = align(e.intermediate_size, 8)
@@ -169,8 +169,17 @@ def test_weight_packing_layout():
     assert torch.equal(gu[0::2][: e.intermediate_size], sd["vision_encoder.blocks.0.mlp.gate_proj.weight"].to(torch.bfloat16))
     assert torch.equal(gu[1::2][: e.intermediate_size], sd["vision_encoder.blocks.0.mlp.up_proj.weight"].to(torch.bfloat16))
     assert (gu[2 * e.intermediate_size:] == 0).all()
-    qkv = w[15 + 10 * e.depth + 1]
+    qkv = w[15 + 10 * e.depth + 0]
     assert qkv.shape == ((d.num_attention_heads + 2 * d.num_key_value_heads) * d.head_dim, d.hidden_size)
+    # decoder RMSNorm weights are folded into the consuming GEMM's weight: W'[n, k] = bf16(bf16(W)[n, k] * bf16(g)[k])
+    bf = torch.bfloat16
+    g_in = sd["decoder.layers.0.input_layernorm.weight"].to(bf).float()
+    q0 = sd["decoder.layers.0.self_attn.q_proj.weight"].to(bf).float()
+    assert torch.equal(qkv[: q0.shape[0]], (q0 * g_in[None, :]).to(bf))
+    g_f = sd["decoder.norm.weight"].to(bf).float()
+    assert torch.equal(w[7], (sd["embedder.token_embed.weight"].to(bf).float() * g_f[None, :]).to(bf))       # SB_RW_LM_W
+    assert torch.equal(w[8], sd["embedder.token_embed.weight"].to(bf))                                        # SB_RW_EMBED
+    assert torch.equal(w[10], (sd["bbox_head.weight"].to(bf).float() * g_f[None, :]).to(bf))                  # SB_RW_BBOX_W
 
 
 def test_detect_repeat_token_matches_oracle():

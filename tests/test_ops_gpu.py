@@ -154,7 +154,7 @@ def test_gemm_folded_rmsnorm(built_lib, dtype, M, N, K, swiglu, bias, res):
     eps = 1e-6
     rs = ops.row_rstd(x, eps)
     rs_ref = torch.rsqrt(x.float().pow(2).mean(-1) + eps)
-    assert ((rs - rs_ref).abs() <= 4e-7 * rs_ref.abs()).all()
+    assert ((rs - rs_ref).abs() <= 2e-6 * rs_ref.abs()).all()      # rsqrt.approx (2 ulp) + a different summation order
     got_inline = ops.gemm(x, w, bias=b, residual=r, act="silu" if swiglu else "none", swiglu=swiglu, rms_eps=eps)
     got_scale = ops.gemm(x, w, bias=b, residual=r, act="silu" if swiglu else "none", swiglu=swiglu, rowscale=rs)
     assert torch.equal(got_inline, got_scale), "in-kernel 1/rms and row_rstd path differ"
