@@ -234,6 +234,16 @@ int sb_det_forward(sb_det_engine* eng, const void* pixel_values, int in_f32, int
                    void* stream);
 /* F.interpolate(logits, size=(HO, WO), mode="bilinear").float() : NCHW fp32 out (surya/detection/__init__.py:120-132). */
 int sb_det_upsample(int dtype, const void* logits, float* out, int planes, int hs, int ws, int HO, int WO, void* stream);
+/* Front half of the detection post-processing on the device, TEXT channel only (surya/detection/__init__.py:120-132 upsample +
+ * .float(); surya/detection/heatmap.py:14-24 get_dynamic_thresholds; :33 `linemap > low_text`):
+ *   map16      [B, HO, WO] engine-dtype image of F.interpolate(logits[:, 0]) — exactly the values the reference casts to fp32
+ *   mask       [B, HO, WO] uint8 = map > low_text(page)          (input of cv2.connectedComponentsWithStats)
+ *   thresholds [B, 4] fp32 = text_threshold, low_text, top-10 % mean, scaling factor (per page)
+ *   hist_scratch [B, 16384] uint32, zero on entry, zero on exit
+ * 3 bytes per pixel leave the device instead of 8 and the host no longer partitions a megapixel per page. */
+int sb_det_text_front(int dtype, const void* logits, int n_labels, int B, int hs, int ws, int HO, int WO, void* map16,
+                      unsigned char* mask, float* thresholds, unsigned int* hist_scratch, float text_threshold, float low_text,
+                      void* stream);
 /* parity tap: copy workspace buffer `buf` (NHWC) into dst. */
 int sb_det_debug_copy(sb_det_engine* eng, int buf, void* dst, size_t bytes, void* stream);
 

@@ -93,7 +93,7 @@ def vision_window_index(grid_thw: np.ndarray, window_size: int, merge: int, patc
 def _block_attention(q, k, v, cu_seqlens: np.ndarray, scale_div: float):
     """Qwen2_5_VLVisionAttention eager path — encoder/__init__.py:238-261 (block-diagonal mask, fp32 softmax)."""
     n = q.shape[0]
-    mask = torch.full((1, n, n), torch.finfo(q.dtype).min, dtype=q.dtype)
+    mask = torch.full((1, n, n), torch.finfo(q.dtype).min, dtype=q.dtype, device=q.device)
     for i in range(1, len(cu_seqlens)):
         a, b = int(cu_seqlens[i - 1]), int(cu_seqlens[i])
         mask[..., a:b, a:b] = 0
@@ -105,8 +105,21 @@ def _block_attention(q, k, v, cu_seqlens: np.ndarray, scale_div: float):
     return o.transpose(0, 1).reshape(n, -1)
 
 
+# bench.py's `gpu_eager_baseline` flips this: equal-length segments go through ONE batched F.scaled_dot_product_attention call
+# and the decoder uses SDPA with enable_gqa — a PyTorch-eager path at least as fast as what the reference runs on a GPU (its
+# SDPA branch pads windows in Python loops, encoder/__init__.py:298-330).  Parity tests never set it.
+FAST_ATTENTION = False
+
+
 def _block_attention_chunked(q, k, v, cu_seqlens: np.ndarray, scale_div: float):
     """Same math as _block_attention evaluated per sequence (identical results, O(sum L^2) instead of O(N^2))."""
+    lens = np.diff(np.asarray(cu_seqlens))
+    if FAST_ATTENTION and len(lens) and (lens == lens[0]).all():
+        L, nseg = int(lens[0]), len(lens)
+        nh, hd = q.shape[1], q.shape[2]
+        qq, kk, vv = (t.reshape(nseg, L, nh, hd).transpose(1, 2) for t in (q, k, v))
+        o = F.scaled_dot_product_attention(qq, kk, vv, scale=1.0 / scale_div)
+        return o.transpose(1, 2).reshape(nseg * L, nh * hd)
     outs = []
     for i in range(1, len(cu_seqlens)):
         a, b = int(cu_seqlens[i - 1]), int(cu_seqlens[i])
@@ -131,12 +144,13 @@ def vision_tower(sd: SD, cfg, tiles: torch.Tensor, grid_thw: np.ndarray, chunked
     x = F.linear(tiles.to(dt), wpe)
     # rotary table (:76-87, :523-550) and window permutation (:614-634)
     pos = vision_rot_pos_ids(grid_thw, e.spatial_merge_size)
-    inv_freq = 1.0 / (10000.0 ** (torch.arange(0, hd // 2, 2, dtype=torch.float) / (hd // 2)))
+    dev = tiles.device
+    inv_freq = 1.0 / (10000.0 ** (torch.arange(0, hd // 2, 2, dtype=torch.float, device=dev) / (hd // 2)))
     max_grid = int(grid_thw[:, 1:].max())
-    freqs_full = torch.outer(torch.arange(max_grid, dtype=torch.float), inv_freq)
-    rot = freqs_full[torch.from_numpy(pos)].flatten(1)  # [N, hd/2]
+    freqs_full = torch.outer(torch.arange(max_grid, dtype=torch.float, device=dev), inv_freq)
+    rot = freqs_full[torch.from_numpy(pos).to(dev)].flatten(1)  # [N, hd/2]
     widx, cu_win = vision_window_index(grid_thw, e.window_size, e.spatial_merge_size, e.patch_size)
-    widx_t = torch.from_numpy(widx)
+    widx_t = torch.from_numpy(widx).to(dev)
     n = x.shape[0]
     x = x.reshape(n // unit, unit, -1)[widx_t].reshape(n, -1)
     rot = rot.reshape(n // unit, unit, -1)[widx_t].reshape(n, -1)
@@ -175,10 +189,11 @@ def learned_2d_embeddings(sd: SD, cfg, grid_thw: np.ndarray) -> torch.Tensor:
     mult = cfg.image_embed_encoding_multiplier
     for _, gh, gw in grid_thw:
         lh, lw = int(gh) // cfg.merge_size, int(gw) // cfg.merge_size
+        dev = sd["img_h_embed.weight"].device
         hv = torch.arange(lh) / max(1, lh - 1) * mult
         wv = torch.arange(lw) / max(1, lw - 1) * mult
-        he = sd["img_h_embed.weight"][hv.to(torch.long)]
-        we = sd["img_w_embed.weight"][wv.to(torch.long)]
+        he = sd["img_h_embed.weight"][hv.to(torch.long).to(dev)]
+        we = sd["img_w_embed.weight"][wv.to(torch.long).to(dev)]
         outs.append((he[:, None] + we[None, :]).flatten(0, 1))
     return torch.cat(outs, 0)
 
@@ -221,9 +236,10 @@ def causal_padding_mask(attention_mask: torch.Tensor, q_len: int, past_len: int,
     key j visible to query at cache position p iff j <= p and attention_mask[b, j] == 1; masked = finfo.min."""
     B, target = attention_mask.shape
     min_v = torch.finfo(dtype).min
-    cache_position = torch.arange(past_len, past_len + q_len)
-    m = torch.full((q_len, target), min_v, dtype=dtype)
-    m = m * (torch.arange(target) > cache_position.reshape(-1, 1))
+    dev = attention_mask.device
+    cache_position = torch.arange(past_len, past_len + q_len, device=dev)
+    m = torch.full((q_len, target), min_v, dtype=dtype, device=dev)
+    m = m * (torch.arange(target, device=dev) > cache_position.reshape(-1, 1))
     m = m[None, None].expand(B, 1, -1, -1).clone()
     pad = (m + attention_mask[:, None, None, :].to(dtype)) == 0
     return m.masked_fill(pad, min_v)
@@ -239,7 +255,7 @@ def decoder_forward(sd: SD, cfg, x: torch.Tensor, attention_mask: torch.Tensor, 
     nh, nkv, hd = d.num_attention_heads, d.num_key_value_heads, d.head_dim
     past = cache.seq_len()
     mask = causal_padding_mask(attention_mask, q_len, past, dt)
-    inv_freq = 1.0 / (d.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
+    inv_freq = 1.0 / (d.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64, device=x.device).float() / hd))
     freqs = (inv_freq[None, :, None].float().expand(B, -1, 1) @ position_ids[:, None, :].float()).transpose(1, 2)
     emb = torch.cat((freqs, freqs), dim=-1)
     cos, sin = emb.cos().to(dt).unsqueeze(1), emb.sin().to(dt).unsqueeze(1)
@@ -253,12 +269,16 @@ def decoder_forward(sd: SD, cfg, x: torch.Tensor, attention_mask: torch.Tensor, 
         k = (k * cos) + (rotate_half(k) * sin)
         k_all, v_all = cache.update(li, k, v)
         rep = nh // nkv
-        kk = k_all[:, :, None].expand(B, nkv, rep, k_all.shape[-2], hd).reshape(B, nh, -1, hd)
-        vv = v_all[:, :, None].expand(B, nkv, rep, v_all.shape[-2], hd).reshape(B, nh, -1, hd)
-        w = torch.matmul(q, kk.transpose(2, 3)) * (hd ** -0.5)
-        w = w + mask[:, :, :, : kk.shape[-2]]
-        w = F.softmax(w, dim=-1, dtype=torch.float32).to(dt)
-        a = torch.matmul(w, vv).transpose(1, 2).reshape(B, q_len, -1)
+        if FAST_ATTENTION:
+            a = F.scaled_dot_product_attention(q, k_all, v_all, attn_mask=mask[:, :, :, : k_all.shape[-2]], enable_gqa=True)
+            a = a.transpose(1, 2).reshape(B, q_len, -1)
+        else:
+            kk = k_all[:, :, None].expand(B, nkv, rep, k_all.shape[-2], hd).reshape(B, nh, -1, hd)
+            vv = v_all[:, :, None].expand(B, nkv, rep, v_all.shape[-2], hd).reshape(B, nh, -1, hd)
+            w = torch.matmul(q, kk.transpose(2, 3)) * (hd ** -0.5)
+            w = w + mask[:, :, :, : kk.shape[-2]]
+            w = F.softmax(w, dim=-1, dtype=torch.float32).to(dt)
+            a = torch.matmul(w, vv).transpose(1, 2).reshape(B, q_len, -1)
         x = x + F.linear(a, sd[b + "self_attn.o_proj.weight"])
         hn = rms_norm(x, sd[b + "post_attention_layernorm.weight"], d.rms_norm_eps)
         g = F.linear(hn, sd[b + "mlp.gate_proj.weight"])
@@ -282,7 +302,7 @@ def process_outputs(lm_logits, bbox_logits, cfg):
     nb = bbox_logits[:, -1:, :].clone().float()
     preds = torch.argmax(nt, dim=-1)
     done = ((preds == cfg.eos_token_id) | (preds == cfg.pad_token_id)).squeeze(-1)
-    input_ids = torch.where(done.unsqueeze(1), torch.tensor(cfg.pad_token_id), preds).to(torch.long)
+    input_ids = torch.where(done.unsqueeze(1), torch.tensor(cfg.pad_token_id, device=preds.device), preds).to(torch.long)
     scores = torch.max(F.softmax(nt[:, -1], dim=-1), dim=-1).values
     scores = scores.masked_fill(done, 0).unsqueeze(1)
     boxes = (nb * cfg.bbox_size).to(torch.long)

@@ -169,6 +169,14 @@ int sb_det_upsample(int dtype, const void* logits, float* out, int planes, int h
   return det_upsample_nchw(dtype, logits, out, planes, hs, ws, HO, WO, static_cast<cudaStream_t>(stream));
 }
 
+int sb_det_text_front(int dtype, const void* logits, int n_labels, int B, int hs, int ws, int HO, int WO, void* map16,
+                      unsigned char* mask, float* thresholds, unsigned int* hist_scratch, float text_threshold, float low_text,
+                      void* stream) {
+  if (!logits || !map16 || !mask || !thresholds || !hist_scratch) { set_error("sb_det_text_front: null argument"); return -1; }
+  return det_text_front(dtype, logits, n_labels, B, hs, ws, HO, WO, map16, mask, thresholds, hist_scratch, text_threshold,
+                        low_text, static_cast<cudaStream_t>(stream));
+}
+
 int sb_det_debug_copy(sb_det_engine* e, int buf, void* dst, size_t bytes, void* stream) {
   if (!e || buf < 0 || buf >= (int)e->bufs.size()) { set_error("sb_det_debug_copy: bad buffer"); return -1; }
   cudaError_t ce = cudaMemcpyAsync(dst, e->bufs[buf], bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));

@@ -443,6 +443,14 @@ int det_classifier(int dtype, const void* x, const void* w, const void* b, void*
   return launch_ok();
 }
 
+// bilinear blend with a pinned operation order (no compiler-chosen FMA contraction): the fp32 up-sampler and the
+// post-processing front half must produce the same bits
+__device__ __forceinline__ float bilerp(float hy, float ly, float hx, float lx, float a, float b, float c, float d) {
+  const float p = __fmaf_rn(lx, b, __fmul_rn(hx, a));
+  const float q = __fmaf_rn(lx, d, __fmul_rn(hx, c));
+  return __fmaf_rn(ly, q, __fmul_rn(hy, p));
+}
+
 // ------------------------------------------------------------------------------------------------ x4 bilinear to fp32 (NCHW)
 template <typename T>
 __global__ void __launch_bounds__(256) upsample_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int hs, int ws,
@@ -465,7 +473,7 @@ __global__ void __launch_bounds__(256) upsample_nchw_kernel(const T* __restrict_
     const int x0 = static_cast<int>(sx);
     const int x1 = x0 + (x0 < ws - 1 ? 1 : 0);
     const float lx = sx - x0, hx = 1.f - lx;
-    const float t = hy * (hx * to_f<T>(r0[x0]) + lx * to_f<T>(r0[x1])) + ly * (hx * to_f<T>(r1[x0]) + lx * to_f<T>(r1[x1]));
+    const float t = bilerp(hy, ly, hx, lx, to_f<T>(r0[x0]), to_f<T>(r0[x1]), to_f<T>(r1[x0]), to_f<T>(r1[x1]));
     v[j] = rnd<T>(t);  // F.interpolate runs in the model dtype; .float() afterwards
   }
   float* o = out + (static_cast<size_t>(pl) * HO + oy) * WO + ox0;
@@ -484,6 +492,172 @@ int det_upsample_nchw(int dtype, const void* in, float* out, int planes, int hs,
   dim3 grid((WO + 1023) / 1024, HO, planes);
   if (dtype == DT_F16) upsample_nchw_kernel<__half><<<grid, 256, 0, st>>>((const __half*)in, out, hs, ws, HO, WO);
   else upsample_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, out, hs, ws, HO, WO);
+  return launch_ok();
+}
+
+// ------------------------------------------------------------------------------------------------ post-processing front half
+// Device side of DetectionPredictor.batch_detection's tail + get_dynamic_thresholds + the binarisation of detect_boxes
+// (surya/detection/__init__.py:120-132, surya/detection/heatmap.py:14-24, 33): for the TEXT channel of every page
+//   line  = F.interpolate(logits, (HO, WO), bilinear).float()        (values are the model-dtype roundings, kept as 16-bit)
+//   avg   = mean of the n - int(0.9 n) largest pixels               (np.partition in the reference)
+//   sf    = clip(avg / 0.7, 0, 1) ** 0.5 ; low = clip(low_text * sf, 0.1, 0.6) ; tt = clip(text_threshold * sf, 0.15, 0.8)
+//   mask  = line > low                                              (uint8, what cv2.connectedComponentsWithStats consumes)
+// Because the up-sampled values are 16-bit floats in [0, 1], the top-10 % mean is EXACT from a histogram over the bit
+// pattern (<= 15 361 bins for fp16, <= 16 257 for bf16): no sort, no selection passes.  The host receives 3 bytes per pixel
+// (16-bit map + mask) instead of 8 (two fp32 channels) and no longer runs np.partition over a megapixel per page.
+constexpr int FRONT_BINS = 16384;
+
+template <typename T>
+__device__ __forceinline__ unsigned short bits16(float v) {
+  T t = from_f<T>(v);
+  return *reinterpret_cast<unsigned short*>(&t);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) det_front_map_kernel(const T* __restrict__ logits, int plane_stride, T* __restrict__ map,
+                                                            unsigned int* __restrict__ hist, int hs, int ws, int HO, int WO,
+                                                            int rows_per_block) {
+  // block = rows_per_block output rows of page blockIdx.y; thread = 4 consecutive columns at a time
+  extern __shared__ unsigned int sh[];
+  for (int i = threadIdx.x; i < FRONT_BINS; i += 256) sh[i] = 0u;
+  __syncthreads();
+  const int pg = blockIdx.y;
+  const T* in = logits + static_cast<size_t>(pg) * plane_stride;
+  const int oy0 = blockIdx.x * rows_per_block;
+  for (int r = 0; r < rows_per_block; ++r) {
+    const int oy = oy0 + r;
+    if (oy >= HO) break;
+    const float sy = fmaxf((oy + 0.5f) * (static_cast<float>(hs) / HO) - 0.5f, 0.f);
+    const int y0 = static_cast<int>(sy);
+    const int y1 = y0 + (y0 < hs - 1 ? 1 : 0);
+    const float ly = sy - y0, hy = 1.f - ly;
+    const T* r0 = in + static_cast<size_t>(y0) * ws;
+    const T* r1 = in + static_cast<size_t>(y1) * ws;
+    T* orow = map + (static_cast<size_t>(pg) * HO + oy) * WO;
+    for (int ox = threadIdx.x; ox < WO; ox += 256) {
+      const float sx = fmaxf((ox + 0.5f) * (static_cast<float>(ws) / WO) - 0.5f, 0.f);
+      const int x0 = static_cast<int>(sx);
+      const int x1 = x0 + (x0 < ws - 1 ? 1 : 0);
+      const float lx = sx - x0, hx = 1.f - lx;
+      // same expression as upsample_nchw_kernel: the two paths must agree bit for bit
+      const float t = bilerp(hy, ly, hx, lx, to_f<T>(r0[x0]), to_f<T>(r0[x1]), to_f<T>(r1[x0]), to_f<T>(r1[x1]));
+      const T o = from_f<T>(t);
+      orow[ox] = o;
+      unsigned short b = *reinterpret_cast<const unsigned short*>(&o);
+      if (b & 0x8000u) b = 0;                        // -0 / negatives cannot come out of a sigmoid; keep the index in range
+      atomicAdd(&sh[b < FRONT_BINS ? b : FRONT_BINS - 1], 1u);
+    }
+  }
+  __syncthreads();
+  unsigned int* gh = hist + static_cast<size_t>(pg) * FRONT_BINS;
+  for (int i = threadIdx.x; i < FRONT_BINS; i += 256)
+    if (sh[i]) atomicAdd(&gh[i], sh[i]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) det_front_threshold_kernel(unsigned int* __restrict__ hist, float* __restrict__ thr,
+                                                                  long long n_pix, float text_threshold, float low_text,
+                                                                  float typical) {
+  // one block per page: walk the histogram from the top bin down until n - int(0.9 n) pixels are covered
+  __shared__ unsigned int cnt[256];
+  __shared__ double sum[256];
+  __shared__ long long s_before[257];
+  unsigned int* gh = hist + static_cast<size_t>(blockIdx.x) * FRONT_BINS;
+  const long long k = n_pix - static_cast<long long>(static_cast<double>(n_pix) * 0.9);   // int(len * 0.9) truncates
+  constexpr int PER = FRONT_BINS / 256;
+  // thread t owns bins [hi - PER + 1, hi] counted from the top: t = 0 holds the largest values
+  const int t = threadIdx.x;
+  const int top = FRONT_BINS - 1 - t * PER;
+  unsigned int c = 0;
+  for (int j = 0; j < PER; ++j) c += gh[top - j];
+  cnt[t] = c;
+  __syncthreads();
+  if (t == 0) {
+    long long acc = 0;
+    for (int i = 0; i < 256; ++i) { s_before[i] = acc; acc += cnt[i]; }
+    s_before[256] = acc;
+  }
+  __syncthreads();
+  // each thread adds what falls inside the top-k set from its own bins
+  double sm = 0.0;
+  long long before = s_before[t];
+  for (int j = 0; j < PER && before < k; ++j) {
+    const int b = top - j;
+    const unsigned int cb = gh[b];
+    if (!cb) continue;
+    const long long take = (before + cb <= k) ? cb : (k - before);
+    unsigned short bits = static_cast<unsigned short>(b);
+    const float v = to_f<T>(*reinterpret_cast<const T*>(&bits));
+    sm += static_cast<double>(take) * static_cast<double>(v);
+    before += cb;
+  }
+  sum[t] = sm;
+  __syncthreads();
+  if (t == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < 256; ++i) tot += sum[i];
+    const float avg = k > 0 ? static_cast<float>(tot / static_cast<double>(k)) : 0.f;
+    float sf = avg / typical;
+    sf = fminf(fmaxf(sf, 0.f), 1.f);
+    sf = sqrtf(sf);
+    const float low = fminf(fmaxf(low_text * sf, 0.1f), 0.6f);
+    const float tt = fminf(fmaxf(text_threshold * sf, 0.15f), 0.8f);
+    thr[blockIdx.x * 4 + 0] = tt;
+    thr[blockIdx.x * 4 + 1] = low;
+    thr[blockIdx.x * 4 + 2] = avg;
+    thr[blockIdx.x * 4 + 3] = sf;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < FRONT_BINS; i += 256) gh[i] = 0u;      // ready for the next call
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) det_front_mask_kernel(const T* __restrict__ map, const float* __restrict__ thr,
+                                                             unsigned char* __restrict__ mask, long long n_pix) {
+  const float low = thr[blockIdx.y * 4 + 1];
+  const T* m = map + static_cast<size_t>(blockIdx.y) * n_pix;
+  unsigned char* o = mask + static_cast<size_t>(blockIdx.y) * n_pix;
+  const long long i0 = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 8;
+  if (i0 + 8 <= n_pix) {
+    const uint4 u = *reinterpret_cast<const uint4*>(m + i0);
+    const T* e = reinterpret_cast<const T*>(&u);
+    unsigned long long pk = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pk |= static_cast<unsigned long long>(to_f<T>(e[j]) > low ? 1u : 0u) << (8 * j);
+    *reinterpret_cast<unsigned long long*>(o + i0) = pk;
+  } else {
+    for (long long i = i0; i < n_pix; ++i) o[i] = to_f<T>(m[i]) > low ? 1 : 0;
+  }
+}
+
+int det_text_front(int dtype, const void* logits, int n_labels, int B, int hs, int ws, int HO, int WO, void* map16,
+                   unsigned char* mask, float* thr, unsigned int* hist, float text_threshold, float low_text, cudaStream_t st) {
+  if (B <= 0) return 0;
+  if (B > 65535) { set_error("det_text_front: too many pages for the grid"); return -1; }
+  const long long n_pix = static_cast<long long>(HO) * WO;
+  if (n_pix % 8) { set_error("det_text_front: H*W must be a multiple of 8"); return -1; }
+  const int rows_per_block = 16;
+  dim3 g1((HO + rows_per_block - 1) / rows_per_block, B);
+  const size_t smem = FRONT_BINS * sizeof(unsigned int);
+  const int plane_stride = n_labels * hs * ws;         // channel 0 of page b
+  dim3 g3(static_cast<unsigned int>((n_pix / 8 + 255) / 256), B);
+  if (dtype == DT_F16) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(det_front_map_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    det_front_map_kernel<__half><<<g1, 256, smem, st>>>((const __half*)logits, plane_stride, (__half*)map16, hist, hs, ws, HO, WO, rows_per_block);
+    if (int rc = launch_ok()) return rc;
+    det_front_threshold_kernel<__half><<<B, 256, 0, st>>>(hist, thr, n_pix, text_threshold, low_text, 0.7f);
+    if (int rc = launch_ok()) return rc;
+    det_front_mask_kernel<__half><<<g3, 256, 0, st>>>((const __half*)map16, thr, mask, n_pix);
+  } else {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(det_front_map_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    det_front_map_kernel<__nv_bfloat16><<<g1, 256, smem, st>>>((const __nv_bfloat16*)logits, plane_stride, (__nv_bfloat16*)map16, hist, hs, ws, HO, WO, rows_per_block);
+    if (int rc = launch_ok()) return rc;
+    det_front_threshold_kernel<__nv_bfloat16><<<B, 256, 0, st>>>(hist, thr, n_pix, text_threshold, low_text, 0.7f);
+    if (int rc = launch_ok()) return rc;
+    det_front_mask_kernel<__nv_bfloat16><<<g3, 256, 0, st>>>((const __nv_bfloat16*)map16, thr, mask, n_pix);
+  }
   return launch_ok();
 }
 

@@ -108,7 +108,27 @@ __global__ void row_rstd_kernel(const T* __restrict__ x, int ldx, float* __restr
   float acc = 0.f;
   if (row < rows) {
     const T* xr = x + static_cast<size_t>(src_rows ? src_rows[row] : row) * ldx;
-    for (int k0 = 0; k0 < H; k0 += 64) {
+    constexpr int UB = 4;                 // k-blocks whose 16 loads are issued before the (strictly ordered) fma chain
+    int k0 = 0;
+    for (; k0 + 64 * UB <= H; k0 += 64 * UB) {
+      uint4 u[UB][4];
+#pragma unroll
+      for (int b = 0; b < UB; ++b)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) u[b][j] = *reinterpret_cast<const uint4*>(xr + k0 + b * 64 + hf * 32 + j * 8);
+#pragma unroll
+      for (int b = 0; b < UB; ++b)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const T* e = reinterpret_cast<const T*>(&u[b][j]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float f = to_f<T>(e[i]);
+            acc = fmaf(f, f, acc);
+          }
+        }
+    }
+    for (; k0 < H; k0 += 64) {
       const int c0 = k0 + hf * 32;
       if (c0 + 32 <= H) {
 #pragma unroll
@@ -136,7 +156,7 @@ __global__ void row_rstd_kernel(const T* __restrict__ x, int ldx, float* __restr
 int row_rstd(int dtype, const void* x, int ldx, float* rs, int rows, int H, float eps, const int* src_rows, cudaStream_t st) {
   if (rows <= 0) return 0;
   if (ldx % 8) { set_error("row_rstd: row pitch must be a multiple of 8 elements"); return -1; }
-  dim3 grid((rows * 2 + 127) / 128), block(128);
+  dim3 grid((rows * 2 + 31) / 32), block(32);      // one warp per 16 rows: small batches spread over many SMs
   if (dtype == DT_BF16)
     launch_pdl(row_rstd_kernel<__nv_bfloat16>, grid, block, 0, st, (const __nv_bfloat16*)x, ldx, rs, rows, H, eps, src_rows);
   else

@@ -84,6 +84,12 @@ int det_classifier(int dtype, const void* x, const void* w, const void* b, void*
                    cudaStream_t st);
 int det_upsample_nchw(int dtype, const void* in, float* out, int planes, int hs, int ws, int HO, int WO, cudaStream_t st);
 
+// Front half of the detection post-processing on the device (det_ops.cu): text-channel x4 bilinear map (16-bit), exact
+// top-10 % mean -> dynamic thresholds, binarised mask.  hist: B x 16384 zeroed uint32 scratch (left zeroed); thr: B x 4 floats
+// (text_threshold, low_text, top-10 % mean, scaling factor).
+int det_text_front(int dtype, const void* logits, int n_labels, int B, int hs, int ws, int HO, int WO, void* map16,
+                   unsigned char* mask, float* thr, unsigned int* hist, float text_threshold, float low_text, cudaStream_t st);
+
 // Layout / table_rec kernels (layout_ops.cu).
 int layernorm(int dtype, const void* x, const void* w, const void* b, void* y, int rows, int C, float eps, cudaStream_t st);
 int patch_gather(int dtype, const void* in, int in_f32, void* out, int B, int Cin, int H, int W, int P, int Kp, cudaStream_t st);

@@ -156,7 +156,11 @@ static int run_heads(sb_rec_engine* e, void* hidden, int rows, const HeadOut& o,
   a.M = rows; a.N = c.vocab; a.K = D;
   a.bias = static_cast<const float*>(e->W(SB_RW_LM_BIAS));
   a.w_constant = 1;
-  a.ssq_inline = 1; a.ssq_eps = c.rms_eps; a.ssq_k = D;
+  // 1/rms of the final norm: separate pass + rowscale rather than the in-kernel sum of squares — this GEMM runs several tiles
+  // per CTA, and the in-kernel pass would serialise each tile's main loop behind the previous tile's epilogue (lm_head
+  // 63 vs 48 us, profiles/r02_decode_parts.md)
+  CK(row_rstd(c.dtype, hidden, D, e->rs, rows, D, c.rms_eps, nullptr, st));
+  a.rowscale = e->rs;
   a.am_val = e->am_val; a.am_idx = e->am_idx; a.am_sum = e->am_sum; a.am_ld = e->am_ld;
   a.store_c = o.logits ? 1 : 0;
   CK(gemm_launch(a, st));

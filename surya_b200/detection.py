@@ -250,6 +250,30 @@ class DetEngine:
                                        c_int(ws), c_int(size[0]), c_int(size[1]), stream_ptr()), "sb_det_upsample")
         return out
 
+    def text_front(self, logits: torch.Tensor, size: Tuple[int, int], text_threshold: float = 0.6, low_text: float = 0.35,
+                   out: Dict[str, torch.Tensor] | None = None) -> Dict[str, torch.Tensor]:
+        """Device-side front half of the detection post-processing for the TEXT channel (sb_det_text_front): the x4 bilinear map
+        in the engine dtype (exactly the values `F.interpolate(...).to(float32)` holds, surya/detection/__init__.py:120-132), the
+        dynamic thresholds of get_dynamic_thresholds (surya/detection/heatmap.py:14-24; defaults = settings.DETECTOR_TEXT_THRESHOLD
+        / DETECTOR_BLANK_THRESHOLD) and the binarised `map > low_text` mask (:33).  Returns device tensors
+        {"map": [B,H,W] dtype, "mask": [B,H,W] uint8, "thr": [B,4] fp32 (text_threshold, low_text, top-10 % mean, scale)}."""
+        B, L, hs, ws = logits.shape
+        H, W = size
+        dev = logits.device
+        if out is None:
+            out = {"map": torch.empty((B, H, W), dtype=logits.dtype, device=dev),
+                   "mask": torch.empty((B, H, W), dtype=torch.uint8, device=dev),
+                   "thr": torch.empty((B, 4), dtype=torch.float32, device=dev)}
+        hist = getattr(self, "_front_hist", None)
+        if hist is None or hist.shape[0] < B:
+            hist = torch.zeros((max(B, self.max_batch), 16384), dtype=torch.int32, device=dev)
+            self._front_hist = hist
+        check(self.lib.sb_det_text_front(c_int(dt_code(logits.dtype)), ptr(logits.contiguous()), c_int(L), c_int(B), c_int(hs),
+                                         c_int(ws), c_int(H), c_int(W), ptr(out["map"]), ptr(out["mask"]), ptr(out["thr"]),
+                                         ptr(hist), ctypes.c_float(text_threshold), ctypes.c_float(low_text), stream_ptr()),
+              "sb_det_text_front")
+        return out
+
     def debug_buffer(self, name: str, B: int, H: int, W: int, C: int) -> torch.Tensor:
         idx = self.prog.buf_names.index(name)
         out = torch.empty((B, H, W, C), dtype=self.dtype, device=self.device)
@@ -353,3 +377,111 @@ def detect_pages_host(engine: DetEngine, pages_host: torch.Tensor, out_host: tor
             if ev is not None:
                 ev.synchronize()
     return out_host
+
+
+def detect_text_front_host(engine: DetEngine, pages_host: torch.Tensor, chunk: int = 8, out_size: Tuple[int, int] | None = None,
+                           text_threshold: float = 0.6, low_text: float = 0.35, sync: bool = True):
+    """Host-to-host detection with the post-processing front half on the device: pinned NCHW pages in, per page the 16-bit text
+    map, the binarised mask and the dynamic thresholds out (3 bytes per pixel over PCIe instead of the 8 of two fp32 heat maps;
+    same three-stream pipeline as detect_pages_host).  Returns pinned tensors {"map": [B,H,W], "mask": [B,H,W] u8, "thr": [B,4]};
+    feed them to text_boxes_from_front()."""
+    B, _, H, W = pages_host.shape
+    size = out_size or (H, W)
+    dev = engine.device
+    L = engine.cfg.num_labels
+    key = ("front", chunk, H, W, size, pages_host.dtype, B)
+    st = getattr(engine, "_pipe_front", None)
+    if st is None or st["key"] != key:
+        st = {"key": key, "s_in": torch.cuda.Stream(dev), "s_c": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
+              "x": [torch.empty((chunk, 3, H, W), dtype=pages_host.dtype, device=dev) for _ in range(2)],
+              "lg": [torch.empty((chunk, L, H // 4, W // 4), dtype=engine.dtype, device=dev) for _ in range(2)],
+              "o": [{"map": torch.empty((chunk, size[0], size[1]), dtype=engine.dtype, device=dev),
+                     "mask": torch.empty((chunk, size[0], size[1]), dtype=torch.uint8, device=dev),
+                     "thr": torch.empty((chunk, 4), dtype=torch.float32, device=dev)} for _ in range(2)],
+              "host": {"map": torch.empty((B, size[0], size[1]), dtype=engine.dtype).pin_memory(),
+                       "mask": torch.empty((B, size[0], size[1]), dtype=torch.uint8).pin_memory(),
+                       "thr": torch.empty((B, 4), dtype=torch.float32).pin_memory()}}
+        engine._pipe_front = st
+    s_in, s_c, s_out = st["s_in"], st["s_c"], st["s_out"]
+    host = st["host"]
+    cur = torch.cuda.current_stream(dev)
+    for s_ in (s_in, s_c, s_out):
+        s_.wait_stream(cur)
+    ev_c, ev_o = [None, None], [None, None]
+    for i, b0 in enumerate(range(0, B, chunk)):
+        b1 = min(B, b0 + chunk)
+        n, k = b1 - b0, i & 1
+        with torch.cuda.stream(s_in):
+            if ev_c[k] is not None:
+                s_in.wait_event(ev_c[k])
+            st["x"][k][:n].copy_(pages_host[b0:b1], non_blocking=True)
+            ev_in = torch.cuda.Event()
+            ev_in.record(s_in)
+        with torch.cuda.stream(s_c):
+            s_c.wait_event(ev_in)
+            if ev_o[k] is not None:
+                s_c.wait_event(ev_o[k])
+            engine.forward(st["x"][k][:n], out=st["lg"][k][:n])
+            o = st["o"][k]
+            engine.text_front(st["lg"][k][:n], size, text_threshold, low_text,
+                              out={"map": o["map"][:n], "mask": o["mask"][:n], "thr": o["thr"][:n]})
+            ev_c[k] = torch.cuda.Event()
+            ev_c[k].record(s_c)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_c[k])
+            for name in ("map", "mask", "thr"):
+                host[name][b0:b1].copy_(st["o"][k][name][:n], non_blocking=True)
+            ev_o[k] = torch.cuda.Event()
+            ev_o[k].record(s_out)
+    cur.wait_stream(s_out)
+    cur.wait_stream(s_c)
+    if sync:
+        for ev in ev_o:
+            if ev is not None:
+                ev.synchronize()
+    return host
+
+
+def text_boxes_from_front(line_map, mask, text_threshold: float, low_text: float):
+    """Back half of detect_boxes (surya/detection/heatmap.py:33-107) on the host, fed by the device-side front half: connected
+    components of the binarised mask, size / peak filtering, dilation, minimum-area rectangle, diamond fix-up, clockwise order,
+    confidences normalised by the page maximum.  line_map: [H, W] 16-bit or fp32 map, mask: [H, W] uint8, thresholds as computed
+    on the device for this page.  Returns (list of 4x2 float32 boxes, list of confidences) exactly like detect_boxes."""
+    import cv2
+    import numpy as np
+
+    linemap = np.asarray(line_map)
+    if linemap.dtype != np.float32:
+        linemap = linemap.astype(np.float32)
+    img_h, img_w = linemap.shape
+    label_count, labels, stats, _ = cv2.connectedComponentsWithStats(np.ascontiguousarray(mask), connectivity=4)
+    det, confidences, max_confidence = [], [], 0
+    for k in range(1, label_count):
+        if stats[k, cv2.CC_STAT_AREA] < 10:
+            continue
+        x, y, w, h = stats[k, [cv2.CC_STAT_LEFT, cv2.CC_STAT_TOP, cv2.CC_STAT_WIDTH, cv2.CC_STAT_HEIGHT]]
+        niter = int(np.sqrt(min(w, h)))
+        buffer = 1
+        sx, sy = max(0, x - niter - buffer), max(0, y - niter - buffer)
+        ex, ey = min(img_w, x + w + niter + buffer), min(img_h, y + h + niter + buffer)
+        comp = labels[sy:ey, sx:ex] == k
+        line_max = np.max(linemap[sy:ey, sx:ex][comp])
+        if line_max < text_threshold:
+            continue
+        ksize = buffer + niter
+        seg = cv2.dilate(comp.astype(np.uint8), cv2.getStructuringElement(cv2.MORPH_RECT, (ksize, ksize)))
+        y_inds, x_inds = np.nonzero(seg)
+        contours = np.column_stack((x_inds + sx, y_inds + sy))
+        box = cv2.boxPoints(cv2.minAreaRect(contours))
+        bw, bh = np.linalg.norm(box[0] - box[1]), np.linalg.norm(box[1] - box[2])
+        if abs(1 - max(bw, bh) / (min(bw, bh) + 1e-5)) <= 0.1:
+            left, right = contours[:, 0].min(), contours[:, 0].max()
+            top, bottom = contours[:, 1].min(), contours[:, 1].max()
+            box = np.array([[left, top], [right, top], [right, bottom], [left, bottom]], dtype=np.float32)
+        box = np.roll(box, 4 - box.sum(axis=1).argmin(), 0)
+        max_confidence = max(max_confidence, line_max)
+        confidences.append(line_max)
+        det.append(box)
+    if max_confidence > 0:
+        confidences = [c / max_confidence for c in confidences]
+    return det, confidences

@@ -108,10 +108,11 @@ def page_slices(n_pages: int, n_ranks: int) -> List[Tuple[int, int]]:
     return out
 
 
-def sharded_pages(run_local: Callable[[int, int], torch.Tensor], n_pages: int, device=None) -> torch.Tensor:
+def sharded_pages(run_local: Callable[[int, int], torch.Tensor], n_pages: int, device=None, result_meta=None) -> torch.Tensor:
     """Run `run_local(lo, hi)` -> tensor [hi - lo, ...] on this rank's page range and all-gather the per-page results of ALL
     ranks in page order (detection heatmaps [n, 2, H/4, W/4], layout / table token histories [n, steps, cols], ...).
-    Shares are padded to the largest share so the collective has a fixed shape."""
+    Shares are padded to the largest share so the collective has a fixed shape.  result_meta = (per-page shape, dtype) skips
+    the (host-side, pickled) metadata exchange when the caller knows the result layout — the steady-state serving path."""
     rank, n_ranks = world()
     if n_pages <= 0:
         return torch.zeros((0,), device=_collective_device(device))
@@ -121,10 +122,13 @@ def sharded_pages(run_local: Callable[[int, int], torch.Tensor], n_pages: int, d
     if n_ranks == 1:
         return mine
     # every rank needs the trailing shape / dtype even if its share is empty
-    meta = [None] * n_ranks
-    dist.all_gather_object(meta, None if mine is None else (tuple(mine.shape[1:]), str(mine.dtype).split(".")[-1]))
-    shape, dname = next(m for m in meta if m is not None)
-    dtype = getattr(torch, dname)
+    if result_meta is not None:
+        shape, dtype = tuple(result_meta[0]), result_meta[1]
+    else:
+        meta = [None] * n_ranks
+        dist.all_gather_object(meta, None if mine is None else (tuple(mine.shape[1:]), str(mine.dtype).split(".")[-1]))
+        shape, dname = next(m for m in meta if m is not None)
+        dtype = getattr(torch, dname)
     cap = max(h - l for l, h in slices)
     # every rank must hand the collective a tensor on the backend's device type, also the ranks whose share is empty
     dev = _collective_device(device)
@@ -134,3 +138,20 @@ def sharded_pages(run_local: Callable[[int, int], torch.Tensor], n_pages: int, d
     outs = [torch.empty_like(buf) for _ in range(n_ranks)]
     dist.all_gather(outs, buf)
     return torch.cat([o[: h - l] for o, (l, h) in zip(outs, slices)], 0)
+
+
+def gather_step_results(tok: torch.Tensor, score: torch.Tensor, bbox: torch.Tensor):
+    """All-gather of one recognition step's fixed-shape DEVICE results over the replicas: token ids as int32
+    [T, B], scores fp32 [T, B], boxes int16 [T, B, 6] (boxes are < 1025).  Returns per-rank lists in rank order; a no-op list of
+    the local tensors for world size 1.  ~2.6 KB per crop on the wire."""
+    rank, n = world()
+    parts = (tok.to(torch.int32), score.to(torch.float32), bbox.to(torch.int16))
+    if n == 1:
+        return tuple([p] for p in parts)
+    out = []
+    for p in parts:
+        p = p.contiguous()
+        bufs = [torch.empty_like(p) for _ in range(n)]
+        dist.all_gather(bufs, p)
+        out.append(bufs)
+    return tuple(out)

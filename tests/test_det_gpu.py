@@ -7,6 +7,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from oracle import det_oracle as D
+
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 OUT = ROOT / "gpurun_out"
@@ -147,6 +149,121 @@ def test_engine_vs_reference_golden(built_lib):
                            "reference_fp16_vs_fp32_gap": ref_gap})
     assert err16 < 5e-3, f"vs the reference's fp16 path: {err16}"
     assert err < 2.5 * ref_gap, f"engine error {err} vs the reference's own fp16-fp32 gap {ref_gap}"
+    eng.close()
+
+
+def test_stage_error_growth_vs_reference_fp16_path(built_lib):
+    """Where does the fp16 error come from?  Per feature stage (and for the heat maps): engine vs the fp32 oracle next to the
+    reference ALGORITHM evaluated in fp16 (oracle on CPU half tensors = model.half()) vs the same fp32 oracle, one 512x512
+    text-like page, default config.  Written to gpurun_out/det_parity.json; the engine may not be worse than 1.5x the
+    reference's own fp16 path at any stage."""
+    from surya_b200.config import det_default
+    from surya_b200.detection import DetEngine
+    from surya_b200.synth import det_normalize, det_state_dict, det_synthetic_pages
+
+    cfg = det_default()
+    sd = det_state_dict(cfg, seed=0)
+    x = det_normalize(det_synthetic_pages(1, 512, seed=11, text_like=True))
+    eng = DetEngine(cfg, sd, torch.float16, max_batch=1, max_hw=(512, 512))
+    got = eng.forward(x.cuda()).float().cpu()
+    with torch.inference_mode():
+        f32 = D.backbone(sd, cfg, x)
+        h32 = torch.special.expit(D.decode_head(sd, cfg, f32))
+        sd16 = {k: v.half() for k, v in sd.items()}
+        f16 = D.backbone(sd16, cfg, x.half())
+        h16 = torch.special.expit(D.decode_head(sd16, cfg, f16)).float()
+    rep = {}
+    for i, (a, b) in enumerate(zip(f32, f16)):
+        C, H, W = a.shape[1:]
+        e = eng.debug_buffer(f"feat{i}", 1, H, W, C).float().cpu().permute(0, 3, 1, 2)
+        scale = a.abs().max().item()
+        rep[f"feat{i}"] = {"engine_err": (e - a).abs().max().item(), "reference_fp16_err": (b.float() - a).abs().max().item(),
+                           "engine_rel_fro": ((e - a).norm() / a.norm()).item(),
+                           "reference_fp16_rel_fro": ((b.float() - a).norm() / a.norm()).item(), "absmax": scale}
+    rep["heatmap"] = {"engine_err": (got - h32).abs().max().item(), "reference_fp16_err": (h16 - h32).abs().max().item(),
+                      "engine_rms": (got - h32).pow(2).mean().sqrt().item(), "reference_fp16_rms": (h16 - h32).pow(2).mean().sqrt().item()}
+    _report("stage_error_growth_512", rep)
+    for k, v in rep.items():
+        if k == "heatmap":
+            assert v["engine_rms"] <= 1.5 * v["reference_fp16_rms"] + 1e-5, (k, v)
+        else:
+            assert v["engine_rel_fro"] <= 1.5 * v["reference_fp16_rel_fro"] + 1e-5, (k, v)
+    eng.close()
+
+
+def test_default_batch32_vs_oracle(built_lib):
+    """BASELINE config 3 at full size: 32 pages of 1024x1024 (4 distinct text-like pages x 8 replicas) through the default
+    EfficientViT in one call.  The 4 distinct pages are compared with the fp32 oracle (tolerance = 1.5x the reference's own fp16
+    gap measured on one of them, floor 1e-3); replicas must be bit-identical wherever they sit in the batch."""
+    from surya_b200.config import det_default
+    from surya_b200.detection import DetEngine
+    from surya_b200.synth import det_normalize, det_state_dict, det_synthetic_pages
+
+    cfg = det_default()
+    sd = det_state_dict(cfg, seed=0)
+    base = det_normalize(det_synthetic_pages(4, 1024, seed=21, text_like=True))
+    x = base.repeat(8, 1, 1, 1)
+    eng = DetEngine(cfg, sd, torch.float16, max_batch=32, max_hw=(1024, 1024))
+    got = eng.forward(x.half().cuda()).float().cpu()
+    torch.set_num_threads(max(1, min(64, len(__import__("os").sched_getaffinity(0)))))
+    ref = D.forward(sd, cfg, base)
+    with torch.inference_mode():
+        sd16 = {k: v.half() for k, v in sd.items()}
+        ref16 = torch.special.expit(D.decode_head(sd16, cfg, D.backbone(sd16, cfg, base[:1].half()))).float()
+    ref_gap = (ref16 - ref[:1]).abs().max().item()
+    err = (got[:4] - ref).abs().max().item()
+    rms = (got[:4] - ref).pow(2).mean().sqrt().item()
+    ref_rms = (ref16 - ref[:1]).pow(2).mean().sqrt().item()
+    for r in range(4, 32):
+        assert torch.equal(got[r], got[r % 4]), f"page {r} differs from its replica"
+    _report("default_1024_batch32", {"max_abs_err_vs_fp32_oracle": err, "reference_own_fp16_gap": ref_gap, "rms_err": rms,
+                                     "reference_own_fp16_rms": ref_rms})
+    assert err <= max(1e-3, 1.5 * ref_gap), f"{err} vs the reference's own fp16 gap {ref_gap}"
+    assert rms <= 1.5 * ref_rms + 1e-5
+    eng.close()
+
+
+@pytest.mark.parametrize("kind", ["default", "tiny"])
+def test_text_front_matches_numpy_reference_path(built_lib, kind):
+    """upsample + dynamic thresholds + binarisation on the device vs the reference's NumPy path (oracle restatement
+    of surya/detection/heatmap.py:14-24, 27-107) on the fp32 maps the predictor would have copied to the host: the 16-bit map is
+    bit-identical to the fp32 up-sampled text channel, thresholds agree to fp32 rounding, masks are identical, and the boxes /
+    confidences produced from (map, mask, thresholds) equal detect_boxes on the fp32 map.  Also the pipelined host path."""
+    import numpy as np
+
+    from surya_b200.config import det_default, det_tiny
+    from surya_b200.detection import DetEngine, detect_text_front_host, text_boxes_from_front
+    from surya_b200.synth import det_normalize, det_state_dict, det_synthetic_pages
+
+    cfg, S = (det_default(), 512) if kind == "default" else (det_tiny(), 256)
+    sd = det_state_dict(cfg, seed=0)
+    x = det_normalize(det_synthetic_pages(5, S, seed=31, text_like=True)).half()
+    eng = DetEngine(cfg, sd, torch.float16, max_batch=5, max_hw=(S, S))
+    logits = eng.forward(x.cuda())
+    up = eng.upsample(logits, (S, S)).cpu()                      # what the reference ships to the host (fp32, both channels)
+    front = {k: v.cpu() for k, v in eng.text_front(logits, (S, S)).items()}
+    assert torch.equal(front["map"].float(), up[:, 0]), "16-bit text map is not the fp32 up-sampled channel"
+    n_boxes = 0
+    for b in range(5):
+        line = up[b, 0].numpy()
+        tt, low, avg = D.dynamic_thresholds(line)
+        assert abs(front["thr"][b, 2].item() - float(avg)) <= 2e-6 * max(1.0, abs(float(avg)))
+        assert abs(front["thr"][b, 0].item() - float(tt)) <= 2e-6 and abs(front["thr"][b, 1].item() - float(low)) <= 2e-6
+        assert np.array_equal(front["mask"][b].numpy(), (line > np.float32(front["thr"][b, 1].item())).astype(np.uint8))
+        assert np.array_equal(front["mask"][b].numpy(), (line > low).astype(np.uint8)), "mask differs from the NumPy path"
+        ref_boxes, ref_conf = D.detect_boxes(line)
+        boxes, conf = text_boxes_from_front(front["map"][b].numpy(), front["mask"][b].numpy(), front["thr"][b, 0].item(),
+                                            front["thr"][b, 1].item())
+        assert len(boxes) == len(ref_boxes)
+        for p, q in zip(boxes, ref_boxes):
+            assert np.array_equal(p, q)
+        assert np.allclose(conf, ref_conf, rtol=0, atol=1e-6)
+        n_boxes += len(boxes)
+    host = detect_text_front_host(eng, x.pin_memory(), chunk=2)
+    for k in ("map", "mask", "thr"):
+        assert torch.equal(host[k], front[k]), k
+    _report(f"text_front_{kind}", {"pages": 5, "boxes": n_boxes, "bytes_per_pixel_to_host": 3,
+                                   "top10_mean": [round(v, 4) for v in front["thr"][:, 2].tolist()]})
     eng.close()
 
 

@@ -179,3 +179,37 @@ def test_reference_detection_predictor_config1_and_dropin_cpu():
         a = ref_model(pixel_values=x).logits
     b = B200EfficientViT(RP.OracleDetEngine(cfg, sd))(pixel_values=x).logits
     assert (a - b).abs().max().item() < 1e-4
+
+
+@needs_reference
+def test_det_postprocess_oracle_pinned_to_reference():
+    """oracle.det_oracle.dynamic_thresholds / detect_boxes and the product's text_boxes_from_front against the reference's own
+    surya.detection.heatmap functions on synthetic heat maps (smooth blobs of text-line shape): identical thresholds, boxes and
+    confidences."""
+    import cv2
+
+    from oracle import det_oracle as D
+    from oracle import ref_predictors as RP
+    from surya_b200.detection import text_boxes_from_front
+
+    RP.install_predictors()
+    from surya.detection.heatmap import detect_boxes, get_dynamic_thresholds
+
+    rng = np.random.default_rng(5)
+    for trial in range(3):
+        m = np.zeros((512, 640), np.float32)
+        for _ in range(25):
+            x, y = int(rng.integers(0, 560)), int(rng.integers(0, 480))
+            w, h = int(rng.integers(30, 200)), int(rng.integers(6, 24))
+            m[y:y + h, x:x + w] = rng.uniform(0.3, 1.0)
+        m = cv2.GaussianBlur(m, (0, 0), 2.0).astype(np.float16).astype(np.float32)     # 16-bit-valued like the engine's maps
+        tt_ref, low_ref = get_dynamic_thresholds(m, 0.6, 0.35)
+        tt, low, _ = D.dynamic_thresholds(m)
+        assert float(tt) == float(tt_ref) and float(low) == float(low_ref)
+        ref_boxes, ref_conf = detect_boxes(m, 0.6, 0.35)
+        boxes, conf = D.detect_boxes(m)
+        pboxes, pconf = text_boxes_from_front(m.astype(np.float16), (m > low).astype(np.uint8), float(tt), float(low))
+        assert len(ref_boxes) == len(boxes) == len(pboxes) and len(boxes) > 3
+        for a, b, c in zip(ref_boxes, boxes, pboxes):
+            assert np.array_equal(a, b) and np.array_equal(a, c)
+        assert np.allclose(ref_conf, conf, atol=0) and np.allclose(ref_conf, pconf, atol=1e-7)

@@ -256,6 +256,84 @@ def test_layout_default_config_runs(built_lib):
     assert torch.equal(tok1[0], tok3[1])
 
 
+def test_layout_default_config_vs_oracle(built_lib):
+    """BASELINE config 4 (layout half) against the CPU oracle at the DEFAULT config: Swin (2,2,16,2) at 768x768 + 8-layer ADETR
+    decoder, 2 pages x 16 greedy steps.  Encoder states vs the fp32 oracle; decoder step-wise: the oracle (fp32 math on the
+    fp16-rounded weights) is teacher-forced with the tokens the engine chose and its encoder states, and must agree with every
+    step's bbox / class outputs; the engine's tokens must be what its own outputs imply."""
+    from oracle import layout_oracle as L
+    from surya_b200.config import layout_default
+    from surya_b200.layout import LayoutEngine, layout_greedy
+    from surya_b200.synth import adetr_layout_state_dict, layout_synthetic_pages, swin_state_dict
+
+    cfg = layout_default()
+    d = cfg.decoder
+    sde, sdd = swin_state_dict(cfg.encoder, 0), adetr_layout_state_dict(d, 0)
+    eng = LayoutEngine(cfg, sde, sdd, dtype=torch.float16)
+    x = layout_synthetic_pages(2, cfg.encoder.image_size, seed=5)
+    steps = 16
+    tok, bbox, cls, enc = layout_greedy(eng, x.cuda(), steps)
+    tok, bbox_c, cls_c = tok.cpu(), bbox.cpu(), cls.cpu()
+    torch.set_num_threads(max(1, min(64, len(__import__("os").sched_getaffinity(0)))))
+    with torch.inference_mode():
+        ref_enc = L.swin_forward(sde, cfg.encoder, x)
+    rel = ((enc.float().cpu() - ref_enc).norm() / ref_enc.norm()).item()
+    mx = (enc.float().cpu() - ref_enc).abs().max().item() / ref_enc.abs().max().item()
+    assert rel < 5e-3 and mx < 2e-2, (rel, mx)
+    assert torch.equal(tok[..., :6], (bbox_c * d.bbox_size).to(torch.long)) and torch.equal(tok[..., 6], cls_c.argmax(-1))
+    st = L.AdetrState(d.num_hidden_layers)
+    sd32 = {k: v.to(torch.float16).float() for k, v in sdd.items()}
+    boxes = torch.full((2, 1, 7), d.bos_token_id, dtype=torch.long)
+    worst_b = worst_c = 0.0
+    with torch.inference_mode():
+        for s in range(steps):
+            rb, rc = L.adetr_forward(sd32, d, boxes, enc.float().cpu(), torch.tensor([s]), st)
+            worst_b = max(worst_b, (rb[:, -1] - bbox_c[:, s]).abs().max().item())
+            worst_c = max(worst_c, (rc[:, -1] - cls_c[:, s]).abs().max().item())
+            boxes = tok[:, s].unsqueeze(1)
+    print(f"layout default: encoder rel {rel:.3g} max/absmax {mx:.3g}; decoder bbox err {worst_b:.3g}, class err {worst_c:.3g}")
+    assert worst_b < 5e-3 and worst_c < 3e-2, (worst_b, worst_c)
+
+
+def test_table_default_config_vs_oracle(built_lib):
+    """BASELINE config 4 (table_rec half), DEFAULT config: Swin (2,2,12,2) at 768x768 + 6-layer decoder, 2 pages, 3-token query
+    prompt + 16 greedy steps, same step-wise protocol as the layout test (five property heads, predictor token formation)."""
+    from oracle import layout_oracle as L
+    from surya_b200.config import table_default
+    from surya_b200.layout import LayoutEngine, table_greedy
+    from surya_b200.synth import adetr_table_state_dict, layout_synthetic_pages, swin_state_dict, table_query_tokens
+
+    cfg = table_default()
+    d = cfg.decoder
+    sde, sdd = swin_state_dict(cfg.encoder, 0), adetr_table_state_dict(d, 0)
+    eng = LayoutEngine(cfg, sde, sdd, dtype=torch.float16)
+    x = layout_synthetic_pages(2, cfg.encoder.image_size, seed=6)
+    prompt = table_query_tokens(d, 2)
+    steps = 16
+    tok, done, heads, enc = table_greedy(eng, x.cuda(), prompt, steps)
+    tok_c = tok.cpu()
+    torch.set_num_threads(max(1, min(64, len(__import__("os").sched_getaffinity(0)))))
+    with torch.inference_mode():
+        ref_enc = L.swin_forward(sde, cfg.encoder, x)
+    rel = ((enc.float().cpu() - ref_enc).norm() / ref_enc.norm()).item()
+    assert rel < 5e-3, rel
+    sd32 = {k: v.to(torch.float16).float() for k, v in sdd.items()}
+    st = L.AdetrState(d.num_hidden_layers)
+    ids, pos = prompt.clone(), torch.arange(prompt.shape[1])
+    worst = {}
+    with torch.inference_mode():
+        for s in range(steps):
+            ref = L.adetr_forward(sd32, d, ids, enc.float().cpu(), pos, st)
+            pos = pos[-1:] + 1
+            for k in ref:
+                worst[k] = max(worst.get(k, 0.0), (ref[k][:, -1] - heads[k][:, s].cpu()).abs().max().item())
+            ref_tok, ref_done = L.table_next_tokens({k: heads[k][:, s:s + 1].cpu() for k in heads}, d)
+            assert torch.equal(ref_tok, tok_c[:, s]) and torch.equal(ref_done, done[:, s].cpu().bool())
+            ids = tok_c[:, s].unsqueeze(1)
+    print("table default: encoder rel %.3g; head errs %s" % (rel, {k: round(v, 5) for k, v in worst.items()}))
+    assert all(v < 3e-2 for v in worst.values()), worst
+
+
 # ------------------------------------------------------------------------------------------------ table_rec
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_label_embed(built_lib, dtype):
