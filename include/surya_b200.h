@@ -62,6 +62,25 @@ int sb_gemm_argmax_tile(int M, int N);
 /* rs[row] = rsqrt(mean(x[row]^2) + eps) in the summation order sb_gemm_rmsnorm's in-kernel pass uses (bit-identical). */
 int sb_row_rstd(int dtype, const void* x, int ldx, float* rs, int rows, int H, float eps, const int* src_rows, void* stream);
 
+/* A chain of up to 4 dependent nn.Linear calls on <= 256 rows in ONE persistent launch (grid-wide barrier between phases): the
+ * o_proj -> gate/up -> down -> next-layer qkv sequence of a Qwen2DecoderLayer at q_len = 1 (decoder/__init__.py:288-310), where
+ * every Linear needs the complete rows of its predecessor.  Phase semantics are sb_gemm's (rms_eps > 0: sb_gemm_rmsnorm's
+ * in-kernel folded norm); results are bit-identical to separate launches with the same tile width (force_bn, 0 = sb_gemm_chain_bn).
+ * barrier: 3 zero-initialised uint32 in device memory owned by the caller ([2] != 0 after a launch = barrier timeout). */
+typedef struct {
+  const void* A; int lda;
+  const void* W; int ldw;
+  void* C; int ldc;
+  int M, N, K;
+  const float* bias;
+  const void* residual; int ldr;
+  int act, swiglu;
+  float rms_eps;
+  int force_bn;
+} sb_gemm_phase;
+int sb_gemm_chain(int dtype, const sb_gemm_phase* phases, int n_phases, unsigned int* barrier, void* stream);
+int sb_gemm_chain_bn(int M, int N, int swiglu);
+
 /* sb_gemm with an in-kernel timeline of CTA 0 (globaltimer ns into timeline_dev[0..42]); profiling aid. */
 int sb_gemm_timeline(int dtype, const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
                      const float* bias, const void* residual, int ldr, int act, int swiglu, int force_bn,

@@ -47,6 +47,10 @@ struct GemmArgs {
   int am_ld = 0;
   int store_c = 1;
 };
+// Several dependent skinny GEMMs in one persistent launch with grid-wide barriers between them (gemm_chain.cu); `bar` = 3
+// zero-initialised uint32 owned by the caller (re-armed by the kernel).  phases[i].force_bn > 0 fixes that phase's tile width.
+int gemm_chain_launch(const GemmArgs* phases, int n, unsigned int* bar, cudaStream_t stream);
+int gemm_chain_bn(int M, int N, int swiglu);
 // Tile width gemm_launch will use for an argmax-epilogue launch of this shape (partials per row = ceil(N / width)).
 int gemm_argmax_tile(int M, int N);
 

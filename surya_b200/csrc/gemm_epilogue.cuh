@@ -205,11 +205,10 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // row of the warp's r-th row or -1; n_col0: first weight row (accumulator column) of the tile; half: 0/1 = which of the two
 // warps sharing this lane quarter; sbias: the tile's bias slice (BN floats, already staged, zeros when absent).
 // stage: 4 KB per warp = residual sub-tile (cp.async, prefetched one group ahead) + output sub-tile, both swizzled.
-template <typename T, int BN, int ACT, bool SWIGLU, typename RowFn>
+template <typename T, int ACT, bool SWIGLU, typename RowFn>
 __device__ __forceinline__ void epilogue_tile_ct(uint32_t taddr, const GemmKParams& p, uint8_t* stage, const float* sbias,
-                                                 int lane, int half, RowFn row_fn, int n_col0, float rs) {
-  constexpr int GW = 32;                            // accumulator columns per group (one tcgen05.ld .x32)
-  constexpr int NG = BN / GW;
+                                                 int lane, int half, RowFn row_fn, int n_col0, float rs, const int NG) {
+  constexpr int GW = 32;                            // accumulator columns per group (one tcgen05.ld .x32); NG groups per tile
   constexpr int GWO = SWIGLU ? GW / 2 : GW;         // output columns per group
   constexpr int CPR = GWO / 8;                      // 16-byte chunks per staged row
   constexpr int ITERS = CPR;                        // 32 rows x CPR chunks / 32 lanes
@@ -394,23 +393,34 @@ __device__ __forceinline__ void epilogue_stage_bias(const GemmKParams& p, float*
     sbias[j] = (p.bias && n_col0 + j < p.N) ? __ldg(p.bias + n_col0 + j) : 0.f;
 }
 
-// Runtime -> compile-time dispatch on (act, swiglu); once per tile, outside every loop.
-template <typename T, int BN, typename RowFn>
-__device__ __forceinline__ void epilogue_tile_v2(uint32_t taddr, const GemmKParams& p, uint8_t* stage, const float* sbias,
-                                                 int lane, int half, RowFn row_fn, int n_col0, float rs = 1.0f) {
+__device__ __forceinline__ void epilogue_stage_bias_rt(const GemmKParams& p, float* sbias, int epi_tid, int n_col0, int bn) {
+  for (int j = epi_tid; j < bn; j += EPI_WARPS * 32)
+    sbias[j] = (p.bias && n_col0 + j < p.N) ? __ldg(p.bias + n_col0 + j) : 0.f;
+}
+
+// Runtime -> compile-time dispatch on (act, swiglu); once per tile, outside every loop.  ng = 32-column groups in the tile.
+template <typename T, typename RowFn>
+__device__ __forceinline__ void epilogue_tile_rt(uint32_t taddr, const GemmKParams& p, uint8_t* stage, const float* sbias,
+                                                 int lane, int half, RowFn row_fn, int n_col0, float rs, int ng) {
   if (p.swiglu) {   // SwiGLU (Qwen2 MLPs) or GeGLU (ADETR MLP, gelu_pytorch_tanh)
-    if (p.act == ACT_SILU) epilogue_tile_ct<T, BN, ACT_SILU, true>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs);
-    else epilogue_tile_ct<T, BN, ACT_GELU_TANH, true>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs);
+    if (p.act == ACT_SILU) epilogue_tile_ct<T, ACT_SILU, true>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs, ng);
+    else epilogue_tile_ct<T, ACT_GELU_TANH, true>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs, ng);
     return;
   }
   switch (p.act) {
-    case ACT_NONE: epilogue_tile_ct<T, BN, ACT_NONE, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs); break;
-    case ACT_GELU_ERF: epilogue_tile_ct<T, BN, ACT_GELU_ERF, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs); break;
-    case ACT_HARDSWISH: epilogue_tile_ct<T, BN, ACT_HARDSWISH, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs); break;
-    case ACT_RELU: epilogue_tile_ct<T, BN, ACT_RELU, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs); break;
-    case ACT_SILU: epilogue_tile_ct<T, BN, ACT_SILU, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs); break;
-    default: epilogue_tile_ct<T, BN, ACT_GELU_TANH, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs); break;
+    case ACT_NONE: epilogue_tile_ct<T, ACT_NONE, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs, ng); break;
+    case ACT_GELU_ERF: epilogue_tile_ct<T, ACT_GELU_ERF, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs, ng); break;
+    case ACT_HARDSWISH: epilogue_tile_ct<T, ACT_HARDSWISH, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs, ng); break;
+    case ACT_RELU: epilogue_tile_ct<T, ACT_RELU, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs, ng); break;
+    case ACT_SILU: epilogue_tile_ct<T, ACT_SILU, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs, ng); break;
+    default: epilogue_tile_ct<T, ACT_GELU_TANH, false>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs, ng); break;
   }
+}
+
+template <typename T, int BN, typename RowFn>
+__device__ __forceinline__ void epilogue_tile_v2(uint32_t taddr, const GemmKParams& p, uint8_t* stage, const float* sbias,
+                                                 int lane, int half, RowFn row_fn, int n_col0, float rs = 1.0f) {
+  epilogue_tile_rt<T>(taddr, p, stage, sbias, lane, half, row_fn, n_col0, rs, BN / 32);
 }
 
 }  // namespace sb

@@ -210,6 +210,71 @@ def test_gemm_argmax_epilogue(built_lib, dtype, M, N, K):
 
 
 @pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B", [256, 200, 16])
+def test_gemm_chain_equals_separate_launches(built_lib, dtype, B):
+    """gemm_chain (o_proj -> gate/up -> down -> next qkv in ONE persistent launch with grid barriers) must give, bit for bit,
+    what four separate launches with the same tile widths give — eagerly, relaunched (barrier counters re-arm themselves) and
+    replayed from a CUDA graph; the barrier-timeout flag must stay 0."""
+    from surya_b200 import ops
+
+    D, Q, IP = 1280, 1920, 3424
+    g = torch.Generator(device="cuda").manual_seed(B)
+    rn = lambda *s, sc=1.0: (torch.randn(*s, device="cuda", generator=g) * sc).to(dtype)
+    ao, x0 = rn(B, D), rn(B, D)
+    wo, wg, wd, wq = rn(D, D, sc=0.03), rn(2 * IP, D, sc=0.03), rn(D, IP, sc=0.02), rn(Q, D, sc=0.03)
+    bq = (torch.randn(Q, device="cuda", generator=g) * 0.1).to(dtype).float()
+    eps = 1e-6
+    bns = [ops.gemm_chain_bn(B, D), ops.gemm_chain_bn(B, 2 * IP, True), ops.gemm_chain_bn(B, D), ops.gemm_chain_bn(B, Q)]
+
+    def separate():
+        x = x0.clone()
+        act = torch.empty(B, IP, device="cuda", dtype=dtype)
+        qkv = torch.empty(B, Q, device="cuda", dtype=dtype)
+        ops.gemm(ao, wo, residual=x, out=x, force_bn=bns[0])
+        ops.gemm(x, wg, act="silu", swiglu=True, out=act, force_bn=bns[1], rms_eps=eps)
+        ops.gemm(act, wd, residual=x, out=x, force_bn=bns[2])
+        ops.gemm(x, wq, bias=bq, out=qkv, force_bn=bns[3], rms_eps=eps)
+        return x, act, qkv
+
+    ref = separate()
+    bar = torch.zeros(4, dtype=torch.int32, device="cuda")
+    x = x0.clone()
+    act = torch.empty(B, IP, device="cuda", dtype=dtype)
+    qkv = torch.empty(B, Q, device="cuda", dtype=dtype)
+    phases = [dict(a=ao, w=wo, out=x, residual=x), dict(a=x, w=wg, out=act, act="silu", swiglu=True, rms_eps=eps),
+              dict(a=act, w=wd, out=x, residual=x), dict(a=x, w=wq, out=qkv, bias=bq, rms_eps=eps)]
+
+    def check(tag):
+        torch.cuda.synchronize()
+        assert bar.tolist() == [0, 0, 0, 0], f"{tag}: barrier state {bar.tolist()}"
+        for got, want, name in zip((x, act, qkv), ref, ("x", "act", "qkv")):
+            assert torch.equal(got, want), f"{tag}: {name} differs, max {(got.float() - want.float()).abs().max().item()}"
+
+    for rep in range(3):
+        x.copy_(x0)
+        ops.gemm_chain(phases, bar)
+        check(f"eager {rep}")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        x.copy_(x0)
+        ops.gemm_chain(phases, bar)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            x.copy_(x0)
+            ops.gemm_chain(phases, bar)
+    for rep in range(3):
+        act.zero_()
+        qkv.zero_()
+        gr.replay()
+        check(f"graph {rep}")
+    # a 3-phase chain (the last decoder layer has no next qkv) and a single phase
+    x.copy_(x0)
+    ops.gemm_chain(phases[:3], bar)
+    torch.cuda.synchronize()
+    assert torch.equal(x, ref[0]) and bar.tolist() == [0, 0, 0, 0]
+
+
+@pytest.mark.parametrize("dtype", DT)
 def test_gather_pad(built_lib, dtype):
     from surya_b200 import ops
 
