@@ -80,6 +80,10 @@ typedef struct {
 } sb_gemm_phase;
 int sb_gemm_chain(int dtype, const sb_gemm_phase* phases, int n_phases, unsigned int* barrier, void* stream);
 int sb_gemm_chain_bn(int M, int N, int swiglu);
+/* sb_gemm_chain with a timeline of CTA 0 (globaltimer ns): timeline_dev[8 * phase + {0 phase start, 1 first k-block landed,
+ * 2 last MMA issued, 3 accumulator ready, 4 epilogue done, 5 grid barrier passed}]; profiling aid. */
+int sb_gemm_chain_timeline(int dtype, const sb_gemm_phase* phases, int n_phases, unsigned int* barrier,
+                           unsigned long long* timeline_dev, void* stream);
 
 /* sb_gemm with an in-kernel timeline of CTA 0 (globaltimer ns into timeline_dev[0..42]); profiling aid. */
 int sb_gemm_timeline(int dtype, const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
@@ -215,6 +219,10 @@ int sb_rec_decode_steps(sb_rec_engine* eng, long long* ids_io, const int* slot, 
                         long long* tok_hist, float* score_hist, long long* bbox_hist, unsigned char* done_hist,
                         int use_graph, void* stream);
 
+/* Engine switches.  "chain" (0/1, default 0 or $SB_CHAIN): run o_proj -> gate/up -> down -> next-layer qkv of every decoder layer
+ * as one persistent sb_gemm_chain launch instead of four launches (same results up to the down projection's fp32 summation order:
+ * the separate path uses the split-K kernel for it). */
+int sb_rec_set_option(sb_rec_engine* eng, const char* name, int value);
 /* Parity taps: copy `bytes` of a named workspace ("feat" = merged image features in window order before the
  * 2-D position embedding, "x", "xl", "logits", "qkv") into dst (device). */
 int sb_rec_debug_copy(sb_rec_engine* eng, const char* name, void* dst, size_t bytes, void* stream);

@@ -46,6 +46,8 @@ struct ChainParams {
   ChainPhase ph[CH_MAX_PHASES];
   unsigned int* bar;       // [0] arrivals, [1] exits, [2] timeout flag
   int group_m;
+  unsigned long long* dbg; // optional timeline of CTA 0 (globaltimer ns): [8*phase + {0 start, 1 first tile data landed,
+                           // 2 last MMA issued, 3 accumulator ready, 4 epilogue done, 5 barrier passed}]
 };
 struct ChainMaps { CUtensorMap a[CH_MAX_PHASES]; CUtensorMap b[CH_MAX_PHASES]; };
 
@@ -140,8 +142,12 @@ __global__ void __launch_bounds__(384, 1) gemm_chain_kernel(const __grid_constan
   int es = 0;           // epilogue: ring slot seen by the per-k-block pass
   uint32_t eph = 0;
 
+  auto stamp = [&](int slot) {
+    if (p.dbg && blockIdx.x == 0) p.dbg[slot] = globaltimer_ns();
+  };
   for (int pi = 0; pi < p.n_phases; ++pi) {
     const ChainPhase& P = p.ph[pi];
+    if (threadIdx.x == 0) stamp(8 * pi + 0);
     const int bn = P.bn;
     const int m_blocks = (P.M + BM - 1) / BM;
     const int n_blocks = (P.N + bn - 1) / bn;
@@ -194,6 +200,7 @@ __global__ void __launch_bounds__(384, 1) gemm_chain_kernel(const __grid_constan
           for (int kb = 0; kb < k_blocks; ++kb) {
             mbar_wait(&full_bar[s], ph);
             tc_fence_after();
+            if (kb == 0 && tile == static_cast<int>(blockIdx.x)) stamp(8 * pi + 1);
             const uint32_t sa = smem_u32(smem + s * CH_SLOT_BYTES);
             const uint64_t da = umma_desc_k128(sa);
             const uint64_t db = umma_desc_k128(sa + CH_A_BYTES);
@@ -203,6 +210,7 @@ __global__ void __launch_bounds__(384, 1) gemm_chain_kernel(const __grid_constan
             if (++s == CH_STAGES) { s = 0; ph ^= 1; }
           }
           umma_commit(&tfull_bar[as]);
+          if (tile == static_cast<int>(blockIdx.x)) stamp(8 * pi + 2);
           as ^= 1;
           if (as == 0) aph ^= 1;
         }
@@ -244,6 +252,7 @@ __global__ void __launch_bounds__(384, 1) gemm_chain_kernel(const __grid_constan
         }
         mbar_wait(&tfull_bar[as], aph);
         tc_fence_after();
+        if (warp == 4 && lane == 0 && tile == static_cast<int>(blockIdx.x)) stamp(8 * pi + 3);
         const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * CH_BN_MAX;
         const int row0 = mb * BM + q * 32;
         const float rs = P.ssq_inline ? srs[q * 32 + lane] : 1.0f;
@@ -252,11 +261,13 @@ __global__ void __launch_bounds__(384, 1) gemm_chain_kernel(const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (warp == 4 && lane == 0 && tile == static_cast<int>(blockIdx.x)) stamp(8 * pi + 4);
         as ^= 1;
         if (as == 0) aph ^= 1;
       }
     }
     if (pi + 1 < p.n_phases) chain_grid_sync(p.bar, static_cast<unsigned int>(pi + 1) * gridDim.x);
+    if (threadIdx.x == 0) stamp(8 * pi + 5);
   }
 
   tc_fence_before();
@@ -305,6 +316,7 @@ static int chain_launch_typed(const GemmArgs* ph, int n, unsigned int* bar, cuda
   p.n_phases = n;
   p.bar = bar;
   p.group_m = 8;
+  p.dbg = ph[0].dbg;
   for (int i = 0; i < n; ++i) {
     const GemmArgs& a = ph[i];
     const int bn = a.force_bn > 0 ? a.force_bn : gemm_chain_bn(a.M, a.N, a.swiglu);

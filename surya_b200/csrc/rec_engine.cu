@@ -40,9 +40,12 @@ struct sb_rec_engine {
   // lm_head argmax partials [rows, am_ld]: (max, argmax, sum exp) per 128 x am_bn logit tile
   float* am_val = nullptr; int* am_idx = nullptr; float* am_sum = nullptr;
   int am_ld = 0, am_bn = 0;
-  // gemm_chain (o_proj -> gate/up -> down -> next qkv in one persistent launch): barrier counters + switch ($SB_CHAIN=0 disables)
+  // gemm_chain (o_proj -> gate/up -> down -> next qkv in one persistent launch): barrier counters + switch.  OFF by default:
+  // measured 50.7 us per layer chain vs 46.4 us for the four PDL-chained launches (profiles/r02_chain_timeline.md) — each phase
+  // still pays ~1.5 us first-tile latency + ~2 us grid barrier, and the down projection loses its split-K kernel.  $SB_CHAIN=1
+  // or sb_rec_set_option("chain", 1) turns it on.
   unsigned int* chain_bar = nullptr;
-  int use_chain = 1;
+  int use_chain = 0;
   int qkv_w_enc = 0, qkv_w_dec = 0;
   // CUDA graph cache for decode_steps
   cudaGraphExec_t graph_exec = nullptr;
@@ -468,6 +471,18 @@ int sb_rec_decode_steps(sb_rec_engine* e, long long* ids_io, const int* slot, in
     count_launches(e->graph_nodes);
   }
   return 0;
+}
+
+int sb_rec_set_option(sb_rec_engine* e, const char* name, int value) {
+  if (!e || !name) { set_error("sb_rec_set_option: null argument"); return -1; }
+  std::string n(name);
+  if (n == "chain") {
+    if ((value != 0) != (e->use_chain != 0) && e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    e->use_chain = value != 0;
+    return 0;
+  }
+  set_error("sb_rec_set_option: unknown option '%s'", name);
+  return -2;
 }
 
 int sb_rec_debug_copy(sb_rec_engine* e, const char* name, void* dst, size_t bytes, void* stream) {

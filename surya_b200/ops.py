@@ -78,7 +78,7 @@ class _GemmPhaseC(ctypes.Structure):
                 ("act", c_int), ("swiglu", c_int), ("rms_eps", c_float), ("force_bn", c_int)]
 
 
-def gemm_chain(phases, barrier):
+def gemm_chain(phases, barrier, timeline=None):
     """sb_gemm_chain: up to 4 dependent skinny GEMMs in one persistent launch.  phases: dicts with a, w, out and optionally
     bias, residual, act, swiglu, rms_eps, force_bn (same meaning as gemm()); barrier: zeroed int32[4] device tensor."""
     lib = _lib.load()
@@ -96,6 +96,10 @@ def gemm_chain(phases, barrier):
         q.rms_eps = float(ph.get("rms_eps") or 0.0)
         q.force_bn = int(ph.get("force_bn", 0))
         keep.append((a, w, out, res))
+    if timeline is not None:
+        check(lib.sb_gemm_chain_timeline(dt_code(phases[0]["a"].dtype), arr, c_int(len(phases)), ptr(barrier), ptr(timeline),
+                                         stream_ptr()), "sb_gemm_chain_timeline")
+        return
     check(lib.sb_gemm_chain(dt_code(phases[0]["a"].dtype), arr, c_int(len(phases)), ptr(barrier), stream_ptr()), "sb_gemm_chain")
 
 
