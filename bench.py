@@ -412,6 +412,52 @@ def detection_bench(dev, peaks, world, steps, warmup):
     return res
 
 
+def pipeline_bench(dev, world, rank, rec_eng):
+    """BASELINE config 5 (secondary): the ocr_text data flow end to end — 64 synthetic 1024x1024 pages per GPU (8 GPUs = the 512
+    pages of the config), detect -> host boxes -> polygon crops -> width-sorted recognition (surya_b200.pipeline.OcrPipeline),
+    sharded by pages with an all-gather of the per-line results (sharded_ocr).  Pages are white with black text-like bars; with
+    synthetic weights the detector fires on a few large regions per page, so this measures the plumbing and the host/device
+    split, not a realistic line count."""
+    import torch.distributed as dist
+
+    from surya_b200.config import det_default
+    from surya_b200.detection import DetEngine
+    from surya_b200.pipeline import OcrPipeline, sharded_ocr
+    from surya_b200.synth import det_state_dict, det_synthetic_pages
+
+    from surya_b200.recognition import RecEngine
+
+    P, S = 64, 1024
+    cfg = det_default()
+    det = DetEngine(cfg, det_state_dict(cfg, 0), torch.float16, device=dev, max_batch=8, max_hw=(S, S))
+    # detected regions are far larger than the 48x512 benchmark crops (up to ~370 image tokens each): a second engine over the
+    # same packed weights with room for long prompts (s_max = prompt + max_tokens) and ragged prefills
+    rec = RecEngine(rec_eng.cfg, None, dtype=rec_eng.dtype, device=dev, max_slots=B_PER_GPU + 1, s_max=640, max_patches=65536,
+                    max_tokens=32768, packed_weights=rec_eng.weights)
+    pipe = OcrPipeline(det, rec, rec_batch=B_PER_GPU, max_tokens=MAX_TOKENS, det_chunk=8, workers=min(16, host_threads()))
+    pages_all = np.concatenate([det_synthetic_pages(P, S, seed=1234 + r, text_like=True) for r in range(world)], 0)
+    sharded_ocr(pipe, pages_all[: 8 * world], MAX_TOKENS, device=dev)          # warm-up (allocations, graph capture)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res, timings = sharded_ocr(pipe, pages_all, MAX_TOKENS, device=dev)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([dt], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = tt.item()
+    n_lines = sum(len(p) for p in res)
+    det.close()
+    rec.close()
+    return {"metric": "pages/sec (ocr_text pipeline, end to end)", "value": P * world / dt, "unit": "pages/s", "seconds": dt,
+            "pages_total": P * world, "pages_per_gpu": P, "lines_total": n_lines, "lines_per_second": n_lines / dt,
+            "breakdown_rank0_s": {k: round(v, 4) for k, v in timings.items()},
+            "api": "surya_b200.pipeline.sharded_ocr(OcrPipeline) — uint8 pages on the host in, per-line polygons / tokens / scores out",
+            "timing": "wall clock around the public call (host post-processing is part of the flow), max over ranks"}
+
+
 def layout_bench(dev, peaks, world, kind, steps, warmup):
     """BASELINE config 4 (parity-test configs, reported for completeness): 16 synthetic 768x768 pages per GPU through the Swin
     encoder + ADETR decoder; layout = 100 greedy box steps, table_rec = 3-token query prompt + 150 steps (row/column pass)."""
@@ -487,6 +533,7 @@ def main():
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU secondary baseline")
     ap.add_argument("--no-detection", action="store_true")
     ap.add_argument("--no-layout", action="store_true", help="skip the layout / table_rec (config 4) secondary numbers")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the ocr_text pipeline (config 5) secondary number")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -645,6 +692,15 @@ def main():
             except Exception as e:      # noqa: BLE001
                 lay[kind] = {"error": f"{type(e).__name__}: {e}"}
                 log(f"{kind} failed: {lay[kind]['error']}")
+    pipe = None
+    if not args.no_pipeline:
+        log("ocr_text pipeline (config 5)")
+        try:
+            pipe = pipeline_bench(dev, world, rank, eng)
+            log(f"pipeline: {pipe['value']:.1f} pages/s end to end, {pipe['lines_total']} lines")
+        except Exception as e:      # noqa: BLE001
+            pipe = {"error": f"{type(e).__name__}: {e}"}
+            log(f"pipeline failed: {pipe['error']}")
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -684,7 +740,7 @@ def main():
             "phases_ms": {"prefill(vision+decoder)": ms_prefill, f"decode x{MAX_TOKENS - 1}": ms_decode,
                           "decode_step": ms_decode / (MAX_TOKENS - 1)},
             "algorithmic": alg, "engine_workspace_gb": eng.workspace_bytes / 1e9, "detection": det,
-            "layout": lay["layout"] if lay else None, "table_rec": lay["table"] if lay else None,
+            "layout": lay["layout"] if lay else None, "table_rec": lay["table"] if lay else None, "ocr_pipeline": pipe,
         }))
     eng.close()
     if world > 1:

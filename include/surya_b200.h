@@ -261,6 +261,9 @@ int sb_det_forward(sb_det_engine* eng, const void* pixel_values, int in_f32, int
                    void* stream);
 /* F.interpolate(logits, size=(HO, WO), mode="bilinear").float() : NCHW fp32 out (surya/detection/__init__.py:120-132). */
 int sb_det_upsample(int dtype, const void* logits, float* out, int planes, int hs, int ws, int HO, int WO, void* stream);
+/* SegformerImageProcessor's rescale + normalise on the device (surya/detection/processor.py:94-95, 126-146):
+ * uint8 NHWC [B,H,W,3] -> NCHW engine dtype, x = (u8 / 255 - mean) / std in fp32 with the ImageNet default mean / std. */
+int sb_det_normalize_u8(int dtype, const unsigned char* pages_nhwc, void* out_nchw, int B, int H, int W, void* stream);
 /* Front half of the detection post-processing on the device, TEXT channel only (surya/detection/__init__.py:120-132 upsample +
  * .float(); surya/detection/heatmap.py:14-24 get_dynamic_thresholds; :33 `linemap > low_text`):
  *   map16      [B, HO, WO] engine-dtype image of F.interpolate(logits[:, 0]) — exactly the values the reference casts to fp32

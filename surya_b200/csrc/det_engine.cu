@@ -169,6 +169,11 @@ int sb_det_upsample(int dtype, const void* logits, float* out, int planes, int h
   return det_upsample_nchw(dtype, logits, out, planes, hs, ws, HO, WO, static_cast<cudaStream_t>(stream));
 }
 
+int sb_det_normalize_u8(int dtype, const unsigned char* pages_nhwc, void* out_nchw, int B, int H, int W, void* stream) {
+  if (!pages_nhwc || !out_nchw) { set_error("sb_det_normalize_u8: null argument"); return -1; }
+  return det_normalize_u8(dtype, pages_nhwc, out_nchw, B, H, W, static_cast<cudaStream_t>(stream));
+}
+
 int sb_det_text_front(int dtype, const void* logits, int n_labels, int B, int hs, int ws, int HO, int WO, void* map16,
                       unsigned char* mask, float* thresholds, unsigned int* hist_scratch, float text_threshold, float low_text,
                       void* stream) {

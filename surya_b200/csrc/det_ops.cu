@@ -495,6 +495,33 @@ int det_upsample_nchw(int dtype, const void* in, float* out, int planes, int hs,
   return launch_ok();
 }
 
+// ------------------------------------------------------------------------------------------------ uint8 pages -> network input
+// SegformerImageProcessor on the device (surya/detection/processor.py:94-95, 126-146): x = (u8 * (1/255) - mean) / std in fp32,
+// NHWC uint8 -> NCHW engine dtype.  Pages cross PCIe as 3 bytes per pixel instead of 6 (fp16) or 12 (fp32).
+template <typename T>
+__global__ void __launch_bounds__(256) det_normalize_u8_kernel(const unsigned char* __restrict__ in, T* __restrict__ out, long long HW) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= HW) return;
+  const int b = blockIdx.y;
+  const unsigned char* px = in + (static_cast<size_t>(b) * HW + i) * 3;
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = __fdiv_rn(__fsub_rn(__fmul_rn(static_cast<float>(px[c]), 1.0f / 255.0f), mean[c]), stdv[c]);
+    out[(static_cast<size_t>(b) * 3 + c) * HW + i] = from_f<T>(v);
+  }
+}
+
+int det_normalize_u8(int dtype, const unsigned char* in, void* out, int B, int H, int W, cudaStream_t st) {
+  if (B <= 0) return 0;
+  if (B > 65535) { set_error("det_normalize_u8: too many pages for the grid"); return -1; }
+  const long long HW = static_cast<long long>(H) * W;
+  dim3 grid(static_cast<unsigned int>((HW + 255) / 256), B);
+  if (dtype == DT_F16) det_normalize_u8_kernel<__half><<<grid, 256, 0, st>>>(in, (__half*)out, HW);
+  else det_normalize_u8_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(in, (__nv_bfloat16*)out, HW);
+  return launch_ok();
+}
+
 // ------------------------------------------------------------------------------------------------ post-processing front half
 // Device side of DetectionPredictor.batch_detection's tail + get_dynamic_thresholds + the binarisation of detect_boxes
 // (surya/detection/__init__.py:120-132, surya/detection/heatmap.py:14-24, 33): for the TEXT channel of every page

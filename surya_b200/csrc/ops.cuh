@@ -84,6 +84,7 @@ int det_classifier(int dtype, const void* x, const void* w, const void* b, void*
                    cudaStream_t st);
 int det_upsample_nchw(int dtype, const void* in, float* out, int planes, int hs, int ws, int HO, int WO, cudaStream_t st);
 
+int det_normalize_u8(int dtype, const unsigned char* in, void* out, int B, int H, int W, cudaStream_t st);
 // Front half of the detection post-processing on the device (det_ops.cu): text-channel x4 bilinear map (16-bit), exact
 // top-10 % mean -> dynamic thresholds, binarised mask.  hist: B x 16384 zeroed uint32 scratch (left zeroed); thr: B x 4 floats
 // (text_threshold, low_text, top-10 % mean, scaling factor).

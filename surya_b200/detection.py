@@ -250,6 +250,16 @@ class DetEngine:
                                        c_int(ws), c_int(size[0]), c_int(size[1]), stream_ptr()), "sb_det_upsample")
         return out
 
+    def normalize_u8(self, pages: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """uint8 NHWC [B,H,W,3] device tensor -> normalised NCHW [B,3,H,W] in the engine dtype (sb_det_normalize_u8)."""
+        B, H, W, C = pages.shape
+        assert C == 3 and pages.dtype == torch.uint8 and pages.is_cuda
+        if out is None:
+            out = torch.empty((B, 3, H, W), dtype=self.dtype, device=pages.device)
+        check(self.lib.sb_det_normalize_u8(c_int(dt_code(self.dtype)), ptr(pages.contiguous()), ptr(out), c_int(B), c_int(H),
+                                           c_int(W), stream_ptr()), "sb_det_normalize_u8")
+        return out
+
     def text_front(self, logits: torch.Tensor, size: Tuple[int, int], text_threshold: float = 0.6, low_text: float = 0.35,
                    out: Dict[str, torch.Tensor] | None = None) -> Dict[str, torch.Tensor]:
         """Device-side front half of the detection post-processing for the TEXT channel (sb_det_text_front): the x4 bilinear map
@@ -385,7 +395,11 @@ def detect_text_front_host(engine: DetEngine, pages_host: torch.Tensor, chunk: i
     map, the binarised mask and the dynamic thresholds out (3 bytes per pixel over PCIe instead of the 8 of two fp32 heat maps;
     same three-stream pipeline as detect_pages_host).  Returns pinned tensors {"map": [B,H,W], "mask": [B,H,W] u8, "thr": [B,4]};
     feed them to text_boxes_from_front()."""
-    B, _, H, W = pages_host.shape
+    u8 = pages_host.dtype == torch.uint8        # raw pages [B,H,W,3]: normalised on the device (3 bytes per pixel over PCIe)
+    if u8:
+        B, H, W, _ = pages_host.shape
+    else:
+        B, _, H, W = pages_host.shape
     size = out_size or (H, W)
     dev = engine.device
     L = engine.cfg.num_labels
@@ -393,7 +407,8 @@ def detect_text_front_host(engine: DetEngine, pages_host: torch.Tensor, chunk: i
     st = getattr(engine, "_pipe_front", None)
     if st is None or st["key"] != key:
         st = {"key": key, "s_in": torch.cuda.Stream(dev), "s_c": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
-              "x": [torch.empty((chunk, 3, H, W), dtype=pages_host.dtype, device=dev) for _ in range(2)],
+              "x": [torch.empty((chunk, H, W, 3) if u8 else (chunk, 3, H, W), dtype=pages_host.dtype, device=dev) for _ in range(2)],
+              "xn": [torch.empty((chunk, 3, H, W), dtype=engine.dtype, device=dev) for _ in range(2)] if u8 else None,
               "lg": [torch.empty((chunk, L, H // 4, W // 4), dtype=engine.dtype, device=dev) for _ in range(2)],
               "o": [{"map": torch.empty((chunk, size[0], size[1]), dtype=engine.dtype, device=dev),
                      "mask": torch.empty((chunk, size[0], size[1]), dtype=torch.uint8, device=dev),
@@ -421,7 +436,8 @@ def detect_text_front_host(engine: DetEngine, pages_host: torch.Tensor, chunk: i
             s_c.wait_event(ev_in)
             if ev_o[k] is not None:
                 s_c.wait_event(ev_o[k])
-            engine.forward(st["x"][k][:n], out=st["lg"][k][:n])
+            xin = engine.normalize_u8(st["x"][k][:n], out=st["xn"][k][:n]) if u8 else st["x"][k][:n]
+            engine.forward(xin, out=st["lg"][k][:n])
             o = st["o"][k]
             engine.text_front(st["lg"][k][:n], size, text_threshold, low_text,
                               out={"map": o["map"][:n], "mask": o["mask"][:n], "thr": o["thr"][:n]})

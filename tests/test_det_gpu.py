@@ -294,3 +294,44 @@ def test_pipelined_host_path_equals_single_shot(built_lib):
         torch.cuda.synchronize()
         assert got.is_pinned() and torch.equal(got, ref)
     eng.close()
+
+
+def test_ocr_pipeline_end_to_end_tiny(built_lib):
+    """BASELINE config 5 data flow on small engines: uint8 pages -> device normalisation + detection + post-processing front half
+    -> host boxes -> polygon crops -> width-sorted recognition.  Stage by stage against independent computations: polygons from
+    the oracle's detect_boxes on the engine's own fp32 maps, crops re-sliced here, tokens from a separate runner call per crop."""
+    import numpy as np
+
+    from surya_b200.config import det_tiny, tiny_rec
+    from surya_b200.detection import DetEngine
+    from surya_b200.pipeline import OcrPipeline, page_polygons, slice_polygon
+    from surya_b200.recognition import RecEngine, RecognitionRunner
+    from surya_b200.synth import det_normalize, det_state_dict, det_synthetic_pages, rec_state_dict
+
+    S = 256
+    dcfg, rcfg = det_tiny(), tiny_rec()
+    det = DetEngine(dcfg, det_state_dict(dcfg, 0), torch.float16, max_batch=4, max_hw=(S, S))
+    rec = RecEngine(rcfg, rec_state_dict(rcfg, 0), dtype=torch.float16, max_slots=9, s_max=256, max_patches=8192, max_tokens=2048)
+    pages = det_synthetic_pages(5, S, seed=77, text_like=True)
+    pipe = OcrPipeline(det, rec, rec_batch=8, max_tokens=6, det_chunk=2, workers=2)
+    per_page, timings = pipe.run(pages, fixed_steps=True)
+    assert len(per_page) == 5 and sum(len(p) for p in per_page) >= 5
+    # device normalisation == host normalisation
+    xn = det.normalize_u8(torch.from_numpy(pages).cuda())
+    assert torch.equal(xn.cpu(), det_normalize(pages).half())
+    up = det.upsample(det.forward(xn), (S, S)).cpu()
+    runner = RecognitionRunner(rec, batch_size=8, max_tokens=6)
+    n_lines = 0
+    for pg in range(5):
+        boxes, conf = D.detect_boxes(up[pg, 0].numpy())
+        polys, pconf = page_polygons(boxes, conf, (S, S), (S, S))
+        assert [ln.polygon for ln in per_page[pg]] == polys
+        assert np.allclose([ln.confidence for ln in per_page[pg]], pconf, atol=1e-6)
+        for ln in per_page[pg]:
+            crop = slice_polygon(pages[pg].astype(np.float32), ln.polygon)
+            tok, sc, bb = runner.run([crop], fixed_steps=True)
+            assert ln.tokens == tok[0] and np.array_equal(ln.boxes, bb[0]), (pg, ln.polygon)
+            n_lines += 1
+    _report("ocr_pipeline_tiny", {"pages": 5, "lines": n_lines, "timings_s": {k: round(v, 4) for k, v in timings.items()}})
+    rec.close()
+    det.close()

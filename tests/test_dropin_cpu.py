@@ -213,3 +213,50 @@ def test_det_postprocess_oracle_pinned_to_reference():
         for a, b, c in zip(ref_boxes, boxes, pboxes):
             assert np.array_equal(a, b) and np.array_equal(a, c)
         assert np.allclose(ref_conf, conf, atol=0) and np.allclose(ref_conf, pconf, atol=1e-7)
+
+
+@needs_reference
+def test_pipeline_host_stages_pinned_to_reference():
+    """surya_b200.pipeline.page_polygons / slice_polygon against the reference's get_and_clean_boxes + parallel_get_boxes expansion
+    (surya/detection/heatmap.py:125-175) and slice_polys_from_image (surya/input/processing.py:57-101) on synthetic heat maps."""
+    import cv2
+
+    from oracle import det_oracle as D
+    from oracle import ref_predictors as RP
+    from surya_b200.detection import text_boxes_from_front
+    from surya_b200.pipeline import page_polygons, slice_polygon
+
+    RP.install_predictors()
+    from surya.detection.heatmap import get_and_clean_boxes
+    from surya.input.processing import slice_polys_from_image
+    from surya.settings import settings
+
+    rng = np.random.default_rng(9)
+    for trial in range(3):
+        H, W = 512, 640
+        m = np.zeros((H, W), np.float32)
+        for _ in range(20):
+            x, y = int(rng.integers(0, W - 60)), int(rng.integers(0, H - 30))
+            w, h = int(rng.integers(30, 220)), int(rng.integers(6, 30))
+            m[y:y + h, x:x + w] = rng.uniform(0.3, 1.0)
+        m[40:60, 100:300] = 0.9
+        m[44:56, 150:250] = 0.95                                   # a box contained in another one
+        m = cv2.GaussianBlur(m, (0, 0), 1.5).astype(np.float16).astype(np.float32)
+        img_size = (W * 2, H * 2) if trial == 1 else (W, H)       # also exercise the rescale path
+        ref = get_and_clean_boxes(m, [W, H], img_size)
+        for box in ref:
+            if box.height < 3 * box.width:
+                box.expand(x_margin=0, y_margin=settings.DETECTOR_BOX_Y_EXPAND_MARGIN)
+                box.fit_to_bounds([0, 0, img_size[0], img_size[1]])
+        tt, low, _ = D.dynamic_thresholds(m)
+        boxes, conf = text_boxes_from_front(m, (m > low).astype(np.uint8), float(tt), float(low))
+        polys, pconf = page_polygons(boxes, conf, img_size, (W, H))
+        assert len(polys) == len(ref) and len(polys) > 3
+        for p, r, c in zip(polys, ref, pconf):
+            assert [[float(v) for v in pt] for pt in p] == [[float(v) for v in pt] for pt in r.polygon], (p, r.polygon)
+            assert abs(c - r.confidence) < 1e-6
+        if trial != 1:
+            page = rng.integers(0, 256, size=(H, W, 3)).astype(np.float32)
+            ref_slices = slice_polys_from_image(page, [[[int(v) for v in pt] for pt in r.polygon] for r in ref])
+            for p, rs in zip(polys, ref_slices):
+                assert np.array_equal(slice_polygon(page, p), rs)

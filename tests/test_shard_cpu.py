@@ -106,3 +106,50 @@ def test_page_slices_and_sharded_pages_world2():
         for _, out in res:
             assert out.shape == (n_pages, 2, 3)
             assert torch.equal(out, ref[:n_pages])
+
+
+def _ocr_worker(rank, world, port, n_pages, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from surya_b200.pipeline import Line, sharded_ocr
+
+    class FakePipe:
+        """Stands in for OcrPipeline: page p (global id carried in the pixel data) has p % 3 lines with deterministic content."""
+
+        def run(self, pages, fixed_steps=False):
+            out = []
+            for i, pg in enumerate(pages):
+                gid = int(pg[0, 0, 0])
+                out.append([Line(page=i, polygon=[[gid, j], [gid + 5, j], [gid + 5, j + 2], [gid, j + 2]], confidence=0.5 + 0.1 * j,
+                                 tokens=[gid, j, 7][: 1 + (gid + j) % 3], scores=[0.25, 0.5, 0.75][: 1 + (gid + j) % 3])
+                            for j in range(gid % 3)])
+            return out, {"fake": 0.0}
+
+    pages = np.zeros((n_pages, 4, 4, 3), dtype=np.uint8)
+    pages[:, 0, 0, 0] = np.arange(n_pages)
+    res, _ = sharded_ocr(FakePipe(), pages, max_tokens=4)
+    q.put((rank, [[(ln.page, ln.polygon, round(ln.confidence, 4), ln.tokens, [round(s, 4) for s in ln.scores]) for ln in pg] for pg in res]))
+    dist.destroy_process_group()
+
+
+def test_sharded_ocr_world2():
+    """BASELINE config 5 sharding: every rank runs the pipeline on its page share, lines of ALL pages come back on every rank in
+    page order (gloo, world size 2; 7 pages so the shares are uneven and one page has no line)."""
+    n_pages = 7
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ocr_worker, args=(r, 2, port, n_pages, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1] == res[1][1]
+    pages = res[0][1]
+    assert len(pages) == n_pages
+    for gid, pg in enumerate(pages):
+        assert len(pg) == gid % 3
+        for j, (page, poly, conf, toks, scs) in enumerate(pg):
+            assert page == gid and poly[0] == [gid, j] and conf == round(0.5 + 0.1 * j, 4)
+            assert toks == [gid, j, 7][: 1 + (gid + j) % 3] and len(scs) == len(toks)
