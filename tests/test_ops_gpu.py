@@ -536,3 +536,18 @@ def test_errors_are_loud(built_lib):
     out = ops.gemm(a, w)
     torch.cuda.synchronize()
     _close(out, (a.float() @ w.float().t()).to(dt), dt, what="gemm after errors")
+
+
+def test_decode_attn_v2_variant_in_subprocess(built_lib):
+    """The shared-memory-V variant of decode attention (off by default, $SB_DECODE_ATTN_V2=1) must pass the same op-level parity
+    test; the switch is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+
+    if os.environ.get("SB_DECODE_ATTN_V2") == "1":
+        pytest.skip("already inside the variant run")
+    env = dict(os.environ, SB_DECODE_ATTN_V2="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-m", "gpu", "-q", "-x", "-k", "test_decode_attn_and_rope_append"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
