@@ -47,6 +47,9 @@ struct GemmArgs {
   int am_ld = 0;
   int store_c = 1;
 };
+// M <= 16 rows: mma.sync kernel without the tcgen05 set-up costs (gemm_skinny.cu); gemm_launch routes to it when it applies.
+bool gemm_skinny_ok(const GemmArgs& a);
+int gemm_skinny_launch(const GemmArgs& a, cudaStream_t stream);
 // Several dependent skinny GEMMs in one persistent launch with grid-wide barriers between them (gemm_chain.cu); `bar` = 3
 // zero-initialised uint32 owned by the caller (re-armed by the kernel).  phases[i].force_bn > 0 fixes that phase's tile width.
 int gemm_chain_launch(const GemmArgs* phases, int n, unsigned int* bar, cudaStream_t stream);

@@ -485,10 +485,10 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     set_error("swiglu epilogue needs an even N");
     return -13;
   }
+  if (a.dtype != DT_BF16 && a.dtype != DT_F16) { set_error("unsupported dtype %d", a.dtype); return -14; }
+  if (gemm_skinny_ok(a)) return gemm_skinny_launch(a, stream);
   if (a.dtype == DT_BF16) return launch_typed<__nv_bfloat16>(a, stream);
-  if (a.dtype == DT_F16) return launch_typed<__half>(a, stream);
-  set_error("unsupported dtype %d", a.dtype);
-  return -14;
+  return launch_typed<__half>(a, stream);
 }
 
 }  // namespace sb

@@ -551,3 +551,34 @@ def test_decode_attn_v2_variant_in_subprocess(built_lib):
     r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-m", "gpu", "-q", "-x", "-k", "test_decode_attn_and_rope_append"],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("M,N,K,epi", [(16, 1024, 1024, "bias"), (16, 8192, 1024, "geglu"), (16, 1024, 4096, "res"), (3, 520, 320, "gelu"),
+                                       (16, 1536, 1024, "none"), (1, 20, 1024, "none")])
+def test_gemm_skinny_path(built_lib, dtype, M, N, K, epi):
+    """M <= 16 routes to the mma.sync kernel (gemm_skinny.cu): against the fp32 restatement with the output roundings, and
+    against the tcgen05 kernel (forced tile width) to a few ulp — the two paths sum in different orders."""
+    from surya_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(dtype)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(dtype)
+    bias = (torch.randn(N, device="cuda", generator=g) * 0.1).to(dtype).float() if epi in ("bias", "gelu") else None
+    res = (torch.randn(M, N, device="cuda", generator=g)).to(dtype) if epi == "res" else None
+    act = {"gelu": "gelu", "geglu": "gelu_tanh"}.get(epi, "none")
+    got = ops.gemm(a, w, bias=bias, residual=res, act=act, swiglu=(epi == "geglu"))
+    lin = a.float() @ w.float().t()
+    if bias is not None:
+        lin = lin + bias
+    lin = lin.to(dtype).float()
+    if epi == "geglu":
+        gt, up = lin[:, 0::2], lin[:, 1::2]
+        ref = (_act_ref(gt, "gelu_tanh").to(dtype).float() * up).to(dtype)
+    else:
+        y = _act_ref(lin, act).to(dtype).float() if act != "none" else lin
+        ref = (y + res.float()).to(dtype) if res is not None else y.to(dtype)
+    _close(got, ref, dtype, ulps=2.0, what="skinny gemm", scale=lin if res is not None else None)
+    if N % 8 == 0 and epi != "geglu":
+        tc = ops.gemm(a, w, bias=bias, residual=res, act=act, force_bn=32)
+        _close(got, tc, dtype, ulps=2.0, what="skinny vs tcgen05", scale=lin if res is not None else None)
