@@ -46,11 +46,6 @@ struct GemmArgs {
   float* am_sum = nullptr;
   int am_ld = 0;
   int store_c = 1;
-  // M <= 16 only (gemm_skinny.cu): RMSNorm of A applied on the fly, bit-identical to ops.cu's rmsnorm kernel followed by the
-  // plain GEMM: norm_mode 0 = Qwen2RMSNorm (w * T(x * rsqrt(mean + eps))), 1 = ADETR ((1 + w), clamp, NaN -> 0)
-  const void* norm_w = nullptr;
-  float norm_eps = 0.f;
-  int norm_mode = 0;
 };
 // M <= 16 rows: mma.sync kernel without the tcgen05 set-up costs (gemm_skinny.cu); gemm_launch routes to it when it applies.
 bool gemm_skinny_ok(const GemmArgs& a);

@@ -28,7 +28,6 @@ struct SkinnyParams {
   const float* bias;
   const void* residual; int ldr;
   int act, swiglu;
-  const void* norm_w; float norm_eps; int norm_mode;
 };
 
 template <typename T> struct MmaSkinny;
@@ -53,7 +52,6 @@ constexpr int SK_UNROLL = 4;     // 32-wide k blocks whose loads are issued befo
 template <typename T>
 __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(const SkinnyParams p) {
   __shared__ float part[SK_WARPS][16 * 8];
-  __shared__ float s_inv[16];
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * 8;
@@ -75,50 +73,6 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(const Skinny
   for (int u = 0; u < SK_UNROLL; ++u)
     w[u] = (n_ok && kb + u < kb1) ? *reinterpret_cast<const uint4*>(Wrow + static_cast<size_t>(kb + u) * 32) : make_uint4(0u, 0u, 0u, 0u);
   pdl_wait();
-  if (p.norm_w) {
-    // 1/rms of the 16 rows, summed exactly like rmsnorm_kernel (ops.cu): one warp per row, lanes stride over 16-byte vectors,
-    // xor-butterfly reduction — so the fused path reproduces rmsnorm -> GEMM bit for bit
-    for (int rr = warp; rr < 16; rr += SK_WARPS) {
-      float ss = 0.f;
-      if (rr < p.M) {
-        const T* xr = reinterpret_cast<const T*>(p.A) + static_cast<size_t>(rr) * p.lda;
-        for (int i = lane; i < (p.K >> 3); i += 32) {
-          const uint4 u = *reinterpret_cast<const uint4*>(xr + i * 8);
-          const T* e = reinterpret_cast<const T*>(&u);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float f = to_f<T>(e[j]);
-            ss += f * f;
-          }
-        }
-      }
-      ss = warp_sum(ss);
-      if (lane == 0)
-        s_inv[rr] = p.norm_mode ? rsqrtf(fmaxf(ss / static_cast<float>(p.K), p.norm_eps)) : rsqrtf(ss / static_cast<float>(p.K) + p.norm_eps);
-    }
-    __syncthreads();
-  }
-  const float inv0 = p.norm_w ? s_inv[r] : 1.f, inv1 = p.norm_w ? s_inv[r + 8] : 1.f;
-  const float tmax = sizeof(T) == 2 && TypeInfo<T>::umma_fmt == 0 ? 65504.f : 3.3895313892515355e38f;
-  auto normed = [&](uint4 x, uint4 wv, float inv) -> uint4 {
-    const T* xe = reinterpret_cast<const T*>(&x);
-    const T* we = reinterpret_cast<const T*>(&wv);
-    uint4 o;
-    T* oe = reinterpret_cast<T*>(&o);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (p.norm_mode) {
-        float v = to_f<T>(xe[j]) * inv * (1.0f + to_f<T>(we[j]));
-        v = fminf(fmaxf(v, -tmax), tmax);
-        oe[j] = from_f<T>(v != v ? 0.f : v);
-      } else {
-        const float nrm = rnd<T>(to_f<T>(xe[j]) * inv);
-        oe[j] = from_f<T>(to_f<T>(we[j]) * nrm);
-      }
-    }
-    return o;
-  };
-  const T* NW = reinterpret_cast<const T*>(p.norm_w) + q * 8;
   for (; kb < kb1; kb += SK_UNROLL) {
     uint4 a0[SK_UNROLL], a1[SK_UNROLL];
 #pragma unroll
@@ -126,15 +80,6 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(const Skinny
       const bool ok = kb + u < kb1;
       a0[u] = (ok && a0_ok) ? *reinterpret_cast<const uint4*>(A0 + static_cast<size_t>(kb + u) * 32) : make_uint4(0u, 0u, 0u, 0u);
       a1[u] = (ok && a1_ok) ? *reinterpret_cast<const uint4*>(A1 + static_cast<size_t>(kb + u) * 32) : make_uint4(0u, 0u, 0u, 0u);
-    }
-    if (p.norm_w) {
-#pragma unroll
-      for (int u = 0; u < SK_UNROLL; ++u) {
-        if (kb + u >= kb1) break;
-        const uint4 nw = *reinterpret_cast<const uint4*>(NW + static_cast<size_t>(kb + u) * 32);
-        if (a0_ok) a0[u] = normed(a0[u], nw, inv0);
-        if (a1_ok) a1[u] = normed(a1[u], nw, inv1);
-      }
     }
     uint4 wn[SK_UNROLL];
 #pragma unroll
@@ -194,7 +139,6 @@ bool gemm_skinny_ok(const GemmArgs& a) {
   if (en < 0) { const char* e = getenv("SB_SKINNY"); en = (e && e[0] == '0') ? 0 : 1; }
   if (!en) return false;
   if (a.M > 16 || a.M <= 0 || a.out_f32 || a.group_k || a.rowscale || a.ssq_inline || a.am_val || a.force_bn > 0) return false;
-  if (a.norm_w && (reinterpret_cast<uintptr_t>(a.norm_w) & 15)) return false;
   if (a.K % 32 || a.lda % 8 || a.ldw % 8) return false;
   if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.W)) & 15) return false;
   if (a.swiglu && (a.N % 2)) return false;
@@ -205,7 +149,6 @@ int gemm_skinny_launch(const GemmArgs& a, cudaStream_t stream) {
   SkinnyParams p;
   p.A = a.A; p.lda = a.lda; p.W = a.W; p.ldw = a.ldw; p.C = a.C; p.ldc = a.ldc;
   p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.residual = a.residual; p.ldr = a.ldr; p.act = a.act; p.swiglu = a.swiglu;
-  p.norm_w = a.norm_w; p.norm_eps = a.norm_eps; p.norm_mode = a.norm_mode;
   const dim3 grid((a.N + 7) / 8), block(SK_WARPS * 32);
   if (a.dtype == DT_BF16) launch_pdl(gemm_skinny_kernel<__nv_bfloat16>, grid, block, 0, stream, p);
   else launch_pdl(gemm_skinny_kernel<__half>, grid, block, 0, stream, p);

@@ -487,7 +487,6 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   }
   if (a.dtype != DT_BF16 && a.dtype != DT_F16) { set_error("unsupported dtype %d", a.dtype); return -14; }
   if (gemm_skinny_ok(a)) return gemm_skinny_launch(a, stream);
-  if (a.norm_w) { set_error("gemm: norm_w (on-the-fly RMSNorm of A) exists on the M <= 16 path only; run rmsnorm first"); return -16; }
   if (a.dtype == DT_BF16) return launch_typed<__nv_bfloat16>(a, stream);
   return launch_typed<__half>(a, stream);
 }

@@ -54,7 +54,6 @@ struct sb_layout_engine {
   cudaGraphExec_t g_group = nullptr, g_one = nullptr;
   const void* graph_key[8] = {nullptr};
   int graph_batch = 0;
-  long long launches_per_step = 0;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 
@@ -89,22 +88,6 @@ static int lin(const sb_layout_engine* e, const void* A, int lda, const void* Wt
   a.w_constant = 1;
   a.allow_splitk = allow_splitk;
   return gemm_launch(a, st);
-}
-
-// RMSNorm (ADETR variant) followed by a Linear: one launch when the batch fits the M <= 16 kernel (the norm is applied to the A
-// fragments on the fly, bit-identical to the two-kernel sequence), else rmsnorm into `scratch` + the plain GEMM.
-static int norm_lin(const sb_layout_engine* e, const void* x, int ldx, const void* norm_w, void* scratch, const void* Wt, int ldw,
-                    void* C, int ldc, int M, int N, int K, int act, int swiglu, cudaStream_t st) {
-  GemmArgs a;
-  a.dtype = e->c.dtype;
-  a.A = x; a.lda = ldx; a.W = Wt; a.ldw = ldw; a.C = C; a.ldc = ldc;
-  a.M = M; a.N = N; a.K = K;
-  a.act = act; a.swiglu = swiglu;
-  a.w_constant = 1;
-  a.norm_w = norm_w; a.norm_eps = e->c.rms_eps; a.norm_mode = 1;
-  if (gemm_skinny_ok(a)) return gemm_skinny_launch(a, st);
-  CK(rmsnorm(e->c.dtype, x, ldx, norm_w, scratch, K, M, K, e->c.rms_eps, nullptr, st, 1));
-  return lin(e, scratch, K, Wt, ldw, C, ldc, M, N, K, nullptr, nullptr, 0, act, swiglu, st);
 }
 
 // ------------------------------------------------------------------------------------------------ Swin encoder
@@ -173,14 +156,16 @@ static int run_token(sb_layout_engine* e, const long long* tok, const int* pos, 
   const int QW = (nh + 2 * nkv) * hd, KVW = 2 * nkv * hd;
   for (int l = 0; l < c.dec_layers; ++l) {
     // cross attention over the cached encoder K/V
-    CK(norm_lin(e, e->dx, Hd, e->WD(l, SB_LWD_CROSS_NORM), e->dn, e->WD(l, SB_LWD_CQ_W), Hd, e->dq, nh * hd, B, nh * hd, Hd, ACT_NONE, 0, st));
+    CK(rmsnorm(dt, e->dx, Hd, e->WD(l, SB_LWD_CROSS_NORM), e->dn, Hd, B, Hd, c.rms_eps, nullptr, st, 1));
+    CK(lin(e, e->dn, Hd, e->WD(l, SB_LWD_CQ_W), Hd, e->dq, nh * hd, B, nh * hd, Hd, nullptr, nullptr, 0, ACT_NONE, 0, st));
     const uint8_t* kv = static_cast<const uint8_t*>(e->ckv[l]);
     CK(attn_single_query(dt, e->dq, nh * hd, kv, kv + static_cast<size_t>(nkv) * hd * e->esz, static_cast<long long>(e->Lk) * KVW, hd,
                          KVW, e->da, nh * hd, B, nh, nkv, hd, e->Lk, scale, st));
     CK(lin(e, e->da, nh * hd, e->WD(l, SB_LWD_CO_W), nh * hd, e->dcross, Hd, B, Hd, nh * hd, e->WD(l, SB_LWD_CO_B), e->dx, Hd, ACT_NONE,
            0, st));
     // causal self attention (RoPE + cache append fused into the attention kernel)
-    CK(norm_lin(e, e->dcross, Hd, e->WD(l, SB_LWD_SELF_NORM), e->dn, e->WD(l, SB_LWD_SQKV_W), Hd, e->dqkv, QW, B, QW, Hd, ACT_NONE, 0, st));
+    CK(rmsnorm(dt, e->dcross, Hd, e->WD(l, SB_LWD_SELF_NORM), e->dn, Hd, B, Hd, c.rms_eps, nullptr, st, 1));
+    CK(lin(e, e->dn, Hd, e->WD(l, SB_LWD_SQKV_W), Hd, e->dqkv, QW, B, QW, Hd, nullptr, nullptr, 0, ACT_NONE, 0, st));
     DecodeAttnArgs a;
     a.dtype = dt; a.qkv = e->dqkv; a.ld = QW; a.kcache = e->kc[l]; a.vcache = e->vc[l]; a.slot = e->slot; a.pos = pos;
     a.inv_freq = static_cast<const float*>(e->WX(SB_LWX_INV_FREQ));
@@ -191,8 +176,8 @@ static int run_token(sb_layout_engine* e, const long long* tok, const int* pos, 
     CK(lin(e, e->da, nh * hd, e->WD(l, SB_LWD_SO_W), nh * hd, e->dres, Hd, B, Hd, nh * hd, e->WD(l, SB_LWD_SO_B), res_src, Hd, ACT_NONE,
            0, st));
     // GeGLU MLP
-    CK(norm_lin(e, e->dres, Hd, e->WD(l, SB_LWD_MLP_NORM), e->dn, e->WD(l, SB_LWD_GU_W), Hd, e->dm, c.inter, B, 2 * c.inter, Hd,
-                ACT_GELU_TANH, 1, st));
+    CK(rmsnorm(dt, e->dres, Hd, e->WD(l, SB_LWD_MLP_NORM), e->dn, Hd, B, Hd, c.rms_eps, nullptr, st, 1));
+    CK(lin(e, e->dn, Hd, e->WD(l, SB_LWD_GU_W), Hd, e->dm, c.inter, B, 2 * c.inter, Hd, nullptr, nullptr, 0, ACT_GELU_TANH, 1, st));
     CK(lin(e, e->dm, c.inter, e->WD(l, SB_LWD_DOWN_W), c.inter, e->dx, Hd, B, Hd, c.inter, nullptr, e->dres, Hd, ACT_NONE, 0, st, 1));
   }
   CK(rmsnorm(dt, e->dx, Hd, e->WX(SB_LWX_FINAL_NORM), e->dn, Hd, B, Hd, c.rms_eps, nullptr, st, 1));
@@ -396,7 +381,6 @@ int sb_layout_decode(sb_layout_engine* e, const void* enc, int batch, const long
       const long long before = launch_count();
       int rc = 0;
       for (int i = 0; i < k && !rc; ++i) rc = body(st);
-      e->launches_per_step = (launch_count() - before) / k;
       count_launches(before - launch_count());   // captured, not executed
       cudaError_t ce = cudaStreamEndCapture(st, &graph);
       if (rc || ce != cudaSuccess) { cudaGetLastError(); set_error("sb_layout_decode: capture failed: rc=%d %s", rc, cudaGetErrorString(ce)); return -6; }
@@ -407,7 +391,7 @@ int sb_layout_decode(sb_layout_engine* e, const void* enc, int batch, const long
     e->graph_batch = B;
     std::memcpy(e->graph_key, key, sizeof(key));
   }
-  const long long per_step = e->launches_per_step;   // kernels per step as counted while capturing (launch accounting)
+  const long long per_step = 1 + 11LL * c.dec_layers + 2 + (c.kind == 1 ? 5 : 2) + 1;   // kernels per step (launch accounting)
   while (left >= GRAPH_GROUP) {
     if (cudaGraphLaunch(e->g_group, st) != cudaSuccess) { cudaGetLastError(); set_error("sb_layout_decode: graph launch failed"); return -9; }
     count_launches(per_step * GRAPH_GROUP);
