@@ -54,6 +54,7 @@ struct sb_layout_engine {
   cudaGraphExec_t g_group = nullptr, g_one = nullptr;
   const void* graph_key[8] = {nullptr};
   int graph_batch = 0;
+  long long launches_per_step = 0;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 
@@ -381,6 +382,7 @@ int sb_layout_decode(sb_layout_engine* e, const void* enc, int batch, const long
       const long long before = launch_count();
       int rc = 0;
       for (int i = 0; i < k && !rc; ++i) rc = body(st);
+      e->launches_per_step = (launch_count() - before) / k;
       count_launches(before - launch_count());   // captured, not executed
       cudaError_t ce = cudaStreamEndCapture(st, &graph);
       if (rc || ce != cudaSuccess) { cudaGetLastError(); set_error("sb_layout_decode: capture failed: rc=%d %s", rc, cudaGetErrorString(ce)); return -6; }
@@ -391,7 +393,7 @@ int sb_layout_decode(sb_layout_engine* e, const void* enc, int batch, const long
     e->graph_batch = B;
     std::memcpy(e->graph_key, key, sizeof(key));
   }
-  const long long per_step = 1 + 11LL * c.dec_layers + 2 + (c.kind == 1 ? 5 : 2) + 1;   // kernels per step (launch accounting)
+  const long long per_step = e->launches_per_step;   // kernels per step as counted while capturing (launch accounting)
   while (left >= GRAPH_GROUP) {
     if (cudaGraphLaunch(e->g_group, st) != cudaSuccess) { cudaGetLastError(); set_error("sb_layout_decode: graph launch failed"); return -9; }
     count_launches(per_step * GRAPH_GROUP);

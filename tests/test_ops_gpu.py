@@ -578,7 +578,7 @@ def test_gemm_skinny_path(built_lib, dtype, M, N, K, epi):
     else:
         y = _act_ref(lin, act).to(dtype).float() if act != "none" else lin
         ref = (y + res.float()).to(dtype) if res is not None else y.to(dtype)
-    _close(got, ref, dtype, ulps=2.0, what="skinny gemm", scale=lin if res is not None else None)
+    _close(got, ref, dtype, ulps=4.0 if epi == "geglu" else 2.0, what="skinny gemm", scale=lin if res is not None else None)
     if N % 8 == 0 and epi != "geglu":
         tc = ops.gemm(a, w, bias=bias, residual=res, act=act, force_bn=32)
         _close(got, tc, dtype, ulps=2.0, what="skinny vs tcgen05", scale=lin if res is not None else None)
