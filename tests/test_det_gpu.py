@@ -53,13 +53,14 @@ def test_conv3x3_igemm(built_lib, cin, cout, stride, hw, act, res):
     assert err < 8e-3, f"conv3x3 cin={cin} cout={cout} s={stride}: max err {err}"
 
 
-@pytest.mark.parametrize("ks,stride,C", [(3, 1, 64), (3, 2, 2048), (5, 1, 1536)])
-def test_dwconv(built_lib, ks, stride, C):
+@pytest.mark.parametrize("ks,stride,C,hw", [(3, 1, 64, (20, 28)), (3, 2, 2048, (20, 28)), (5, 1, 1536, (20, 28)),
+                                            (3, 1, 1024, (64, 64)), (3, 1, 72, (37, 45)), (3, 1, 3072, (32, 32)), (3, 1, 8, (5, 3))])
+def test_dwconv(built_lib, ks, stride, C, hw):
     from surya_b200 import ops
 
     dtype = torch.float16
     g = torch.Generator(device="cuda").manual_seed(ks + C)
-    x = torch.randn(2, 20, 28, C, device="cuda", generator=g).to(dtype)
+    x = torch.randn(3, hw[0], hw[1], C, device="cuda", generator=g).to(dtype)
     w = (torch.randn(C, 1, ks, ks, device="cuda", generator=g) / ks).to(dtype)
     b = torch.randn(C, device="cuda", generator=g) * 0.1
     pad = ks // 2
