@@ -273,8 +273,8 @@ template <typename T, int HD, int G>
 __global__ void __launch_bounds__(128) decode_attn_kernel(const DecodeKParams p) {
   constexpr int HALF = HD / 2, VPR = HD / 8, NKG = 128 / VPR;
   extern __shared__ __align__(16) uint8_t smem_dec[];
-  float* q_s = reinterpret_cast<float*>(smem_dec);          // [G][HD]
-  float* red = q_s + G * HD;                                // [NKG][G][HD]
+  T* q_t = reinterpret_cast<T*>(smem_dec);                  // [G][HD] rotated queries (in T; the first G*HD floats' worth of space)
+  float* red = reinterpret_cast<float*>(smem_dec) + G * HD;  // [NKG][G][HD]
   float* sc = red + NKG * G * HD;                           // [G][s_max]
   __shared__ float s_red[4][G];
   __shared__ float s_max_g[G], s_sum_g[G];
@@ -307,8 +307,8 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const DecodeKParams p)
     float o1 = rnd<T>(rnd<T>(x1 * c) + rnd<T>(-x2 * s));
     float o2 = rnd<T>(rnd<T>(x2 * c) + rnd<T>(x1 * s));
     if (hh < G) {
-      q_s[hh * HD + i] = o1;
-      q_s[hh * HD + i + HALF] = o2;
+      q_t[hh * HD + i] = from_f<T>(o1);          // exactly representable: o1 / o2 are already rounded to T
+      q_t[hh * HD + i + HALF] = from_f<T>(o2);
     } else {
       kc[static_cast<size_t>(pos) * HD + i] = from_f<T>(o1);
       kc[static_cast<size_t>(pos) * HD + i + HALF] = from_f<T>(o2);
@@ -334,22 +334,15 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const DecodeKParams p)
     for (int c = 0; c < VPR; ++c) {
       uint4 u = kr[c];
       const T* e = reinterpret_cast<const T*>(&u);
-      float kf[8];
-#pragma unroll
-      for (int x = 0; x < 8; ++x) kf[x] = to_f<T>(e[x]);
+      const unsigned short* kb = reinterpret_cast<const unsigned short*>(e);
 #pragma unroll
       for (int gq = 0; gq < G; ++gq) {
-        // two 16-byte broadcast reads of q per 8 dims instead of eight 4-byte ones: the loop was shared-memory-issue bound
-        const float4 q0 = *reinterpret_cast<const float4*>(q_s + gq * HD + c * 8);
-        const float4 q1 = *reinterpret_cast<const float4*>(q_s + gq * HD + c * 8 + 4);
-        acc[gq] += q0.x * kf[0];
-        acc[gq] += q0.y * kf[1];
-        acc[gq] += q0.z * kf[2];
-        acc[gq] += q0.w * kf[3];
-        acc[gq] += q1.x * kf[4];
-        acc[gq] += q1.y * kf[5];
-        acc[gq] += q1.z * kf[6];
-        acc[gq] += q1.w * kf[7];
+        // one 16-byte broadcast read of 8 q values (kept in T: they are rounded to T anyway) and 8 mixed-precision FMAs
+        // (FHFMA: 16-bit operands, fp32 accumulate, no conversion instructions) — bit-identical to fmaf(float(q), float(k), acc)
+        const uint4 qv = *reinterpret_cast<const uint4*>(q_t + gq * HD + c * 8);
+        const unsigned short* qb = reinterpret_cast<const unsigned short*>(&qv);
+#pragma unroll
+        for (int x = 0; x < 8; ++x) acc[gq] = fma16<T>(qb[x], kb[x], acc[gq]);
       }
     }
 #pragma unroll
@@ -410,15 +403,12 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const DecodeKParams p)
       for (int t = 0; t < PVU; ++t) {
         const int j = j0 + t * NKG;
         if (j >= n_keys) break;
-        const T* e = reinterpret_cast<const T*>(&u[t]);
-        float vf[8];
-#pragma unroll
-        for (int x = 0; x < 8; ++x) vf[x] = to_f<T>(e[x]);
+        const unsigned short* vb = reinterpret_cast<const unsigned short*>(&u[t]);
 #pragma unroll
         for (int gq = 0; gq < G; ++gq) {
-          float pj = sc[gq * p.s_max + j];
+          const unsigned short pb = bits_of<T>(from_f<T>(sc[gq * p.s_max + j]));     // p was rounded to T after the softmax
 #pragma unroll
-          for (int x = 0; x < 8; ++x) acc[gq][x] += pj * vf[x];
+          for (int x = 0; x < 8; ++x) acc[gq][x] = fma16<T>(pb, vb[x], acc[gq][x]);
         }
       }
     }

@@ -154,11 +154,11 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const T* __restrict__ in
         if (r < 0 || r >= KS) continue;
 #pragma unroll
         for (int s_ = 0; s_ < KS; ++s_) {
-          const T* xe = reinterpret_cast<const T*>(&xv[PRELOAD ? rr : 0][s_]);
+          const unsigned short* xe = reinterpret_cast<const unsigned short*>(&xv[PRELOAD ? rr : 0][s_]);
           const uint4 wq = wsm[r * KS + s_][cvec];
-          const T* we = reinterpret_cast<const T*>(&wq);
+          const unsigned short* we = reinterpret_cast<const unsigned short*>(&wq);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[y][j] += to_f<T>(xe[j]) * to_f<T>(we[j]);
+          for (int j = 0; j < 8; ++j) acc[y][j] = fma16<T>(xe[j], we[j], acc[y][j]);    // FHFMA: no conversions
         }
       }
     }
@@ -247,14 +247,9 @@ __global__ void __launch_bounds__(256, 2) dwconv_tile_kernel(const T* __restrict
         for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
 #pragma unroll
       for (int rr = 0; rr < RH; ++rr) {
-        float xf[KS][8];
+        uint4 xq[KS];
 #pragma unroll
-        for (int s_ = 0; s_ < KS; ++s_) {
-          const uint4 u = tl[(rr * RW + xl + s_) * 8 + cvec];
-          const T* xe = reinterpret_cast<const T*>(&u);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) xf[s_][j] = to_f<T>(xe[j]);
-        }
+        for (int s_ = 0; s_ < KS; ++s_) xq[s_] = tl[(rr * RW + xl + s_) * 8 + cvec];
         // input row rr is tap row r of output row y = rr - r (all indices are compile-time after unrolling)
 #pragma unroll
         for (int r = KS - 1; r >= 0; --r) {
@@ -262,9 +257,10 @@ __global__ void __launch_bounds__(256, 2) dwconv_tile_kernel(const T* __restrict
           if (y < 0 || y >= TH) continue;
 #pragma unroll
           for (int s_ = 0; s_ < KS; ++s_) {
-            const T* we = reinterpret_cast<const T*>(&wq[r * KS + s_]);
+            const unsigned short* xe = reinterpret_cast<const unsigned short*>(&xq[s_]);
+            const unsigned short* we = reinterpret_cast<const unsigned short*>(&wq[r * KS + s_]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[y % KS][j] += xf[s_][j] * to_f<T>(we[j]);
+            for (int j = 0; j < 8; ++j) acc[y % KS][j] = fma16<T>(xe[j], we[j], acc[y % KS][j]);
           }
         }
         const int yd = rr - (KS - 1);       // the output row that just received its last tap row

@@ -177,6 +177,22 @@ template <typename T> __device__ __forceinline__ T from_f(float v) { return Type
 // Round an fp32 value to storage type T and back (an eager-PyTorch op boundary).
 template <typename T> __device__ __forceinline__ float rnd(float v) { return to_f<T>(from_f<T>(v)); }
 
+// Mixed-precision FMA (PTX ISA 8.6, sm_100+): d = a * b + c with 16-bit a, b and fp32 c, d — ONE instruction (SASS FHFMA /
+// FHFMA.BF16, operands taken from register halves) instead of two conversions + FFMA.  The product of two 16-bit floats is
+// exact in fp32 and the sum is rounded once, so the result equals fmaf(float(a), float(b), c) bit for bit.
+template <typename T> __device__ __forceinline__ float fma16(unsigned short a, unsigned short b, float c);
+template <> __device__ __forceinline__ float fma16<__half>(unsigned short a, unsigned short b, float c) {
+  float d;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+  return d;
+}
+template <> __device__ __forceinline__ float fma16<__nv_bfloat16>(unsigned short a, unsigned short b, float c) {
+  float d;
+  asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+  return d;
+}
+template <typename T> __device__ __forceinline__ unsigned short bits_of(T v) { return *reinterpret_cast<unsigned short*>(&v); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
