@@ -538,13 +538,13 @@ __global__ void __launch_bounds__(256) classifier_kernel(const T* __restrict__ x
   for (int o = 0; o < NOUT; ++o) acc[o] = 0.f;
   for (int c = lane * 8; c < C; c += 256) {
     const uint4 xv = *reinterpret_cast<const uint4*>(xr + c);
-    const T* xe = reinterpret_cast<const T*>(&xv);
+    const unsigned short* xe = reinterpret_cast<const unsigned short*>(&xv);
 #pragma unroll
     for (int o = 0; o < NOUT; ++o) {
       const uint4 wv = *reinterpret_cast<const uint4*>(w + static_cast<size_t>(o) * C + c);
-      const T* we = reinterpret_cast<const T*>(&wv);
+      const unsigned short* we = reinterpret_cast<const unsigned short*>(&wv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[o] += to_f<T>(xe[j]) * to_f<T>(we[j]);
+      for (int j = 0; j < 8; ++j) acc[o] = fma16<T>(xe[j], we[j], acc[o]);
     }
   }
 #pragma unroll

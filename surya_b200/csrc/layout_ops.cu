@@ -461,14 +461,14 @@ __global__ void __launch_bounds__(128) attn_single_query_kernel(const T* __restr
                                                                 float scale) {
   constexpr int VPR = HD / 8, NKG = 128 / VPR;
   extern __shared__ __align__(16) uint8_t smem_sq[];
-  float* q_s = reinterpret_cast<float*>(smem_sq);   // [G][HD]
-  float* red = q_s + G * HD;                         // [NKG][G][HD]
+  T* q_t = reinterpret_cast<T*>(smem_sq);            // [G][HD] query rows, kept in T (first G*HD floats' worth of space)
+  float* red = reinterpret_cast<float*>(smem_sq) + G * HD;   // [NKG][G][HD]
   float* sc = red + NKG * G * HD;                    // [G][n_keys]
   __shared__ float s_red[4][G];
   __shared__ float s_m[G], s_l[G];
   const int b = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const T* qr = q + static_cast<size_t>(b) * ldq + kvh * G * HD;
-  for (int i = tid; i < G * HD; i += 128) q_s[i] = to_f<T>(qr[i]);
+  for (int i = tid; i < G * HD; i += 128) q_t[i] = qr[i];
   const T* kb = K + b * bs + kvh * hs;
   const T* vb = V + b * bs + kvh * hs;
   __syncthreads();
@@ -483,12 +483,13 @@ __global__ void __launch_bounds__(128) attn_single_query_kernel(const T* __restr
 #pragma unroll
     for (int c = 0; c < VPR; ++c) {
       const uint4 u = kr[c];
-      const T* e = reinterpret_cast<const T*>(&u);
+      const unsigned short* kb16 = reinterpret_cast<const unsigned short*>(&u);
 #pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        const float kf = to_f<T>(e[x]);
+      for (int gq = 0; gq < G; ++gq) {      // FHFMA: 16-bit q and k, fp32 accumulate, no conversions (bit-identical to fmaf on floats)
+        const uint4 qv = *reinterpret_cast<const uint4*>(q_t + gq * HD + c * 8);
+        const unsigned short* qb = reinterpret_cast<const unsigned short*>(&qv);
 #pragma unroll
-        for (int gq = 0; gq < G; ++gq) acc[gq] += q_s[gq * HD + c * 8 + x] * kf;
+        for (int x = 0; x < 8; ++x) acc[gq] = fma16<T>(qb[x], kb16[x], acc[gq]);
       }
     }
 #pragma unroll
@@ -528,12 +529,12 @@ __global__ void __launch_bounds__(128) attn_single_query_kernel(const T* __restr
       for (int x = 0; x < 8; ++x) acc[gq][x] = 0.f;
     for (int j = kg; j < n_keys; j += NKG) {
       const uint4 u = *reinterpret_cast<const uint4*>(vb + j * ts + chunk * 8);
-      const T* e = reinterpret_cast<const T*>(&u);
+      const unsigned short* vb16 = reinterpret_cast<const unsigned short*>(&u);
 #pragma unroll
       for (int gq = 0; gq < G; ++gq) {
-        const float pj = rnd<T>(sc[gq * n_keys + j] / s_l[gq]);
+        const unsigned short pb = bits_of<T>(from_f<T>(sc[gq * n_keys + j] / s_l[gq]));
 #pragma unroll
-        for (int x = 0; x < 8; ++x) acc[gq][x] += pj * to_f<T>(e[x]);
+        for (int x = 0; x < 8; ++x) acc[gq][x] = fma16<T>(pb, vb16[x], acc[gq][x]);
       }
     }
 #pragma unroll
