@@ -97,7 +97,10 @@ int det_stem_conv(int dtype, const void* in, int in_f32, const float* w, const f
 // CTA = 32 output columns x 8 channel vectors (64 channels = one 128 B line per pixel); every thread owns 8 channels of one
 // output column and walks TY output rows with the k x k weights in registers, so each input row it touches is loaded once per
 // column instead of once per tap row (L1 absorbs the overlap between neighbouring columns).  fp32 accumulation in tap order
-// (r, s) — the same order as a direct per-pixel loop.
+// (r, s) — the same order as a direct per-pixel loop.  Round 2: the multiply-adds are FHFMA (16-bit operands, fp32 accumulate,
+// sb_ptx.cuh fma16): 322 -> 285 us for the 64x64x1024 stage-2 layer at B = 32, 202 -> 159 us for the 5x5.  A shared-memory-tiled,
+// double-buffered persistent variant (cp.async halo tiles, 2 CTAs/SM) was measured at 356 us and dropped (git history:
+// "shared-memory tiled ... depthwise 3x3"): the kernel is not bound by the L1 re-fetch of neighbouring columns.
 template <typename T, int KS, int STRIDE, int TY>
 __global__ void __launch_bounds__(256, 2) dwconv_kernel(const T* __restrict__ in, const T* __restrict__ w,
                                                         const float* __restrict__ bias, T* __restrict__ out, int H, int W, int C,
@@ -184,131 +187,6 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const T* __restrict__ in
   }
 }
 
-// Stride-1 variant with the input tile staged in shared memory (round 2).  The kernel above fetches every input vector once
-// per tap column from L1 (4.5 16-byte loads per output vector) and ran at 0.75 - 1.4 TB/s of DRAM traffic
-// (profiles/r02_det_launch_summary.md: 15 % + 5 % of the detection forward).  Here a CTA copies the (TH + KS - 1) x (32 + KS - 1)
-// pixel x 64 channel halo tile with cp.async (every input byte leaves L2 once per tile, 1.33x / 1.69x halo overhead), then each
-// thread — one output column x 8 channels — slides a KS-row window down the tile out of shared memory.  Accumulation order
-// per output is tap order (r, s), identical to the direct kernel, so results are bit-identical.
-template <typename T, int KS, int TH>
-__global__ void __launch_bounds__(256, 2) dwconv_tile_kernel(const T* __restrict__ in, const T* __restrict__ w,
-                                                             const float* __restrict__ bias, T* __restrict__ out, int H, int W, int C,
-                                                             int pad, int act, int c_blocks, int x_blocks, int y_blocks, int n_tiles) {
-  constexpr int TW = 32, RH = TH + KS - 1, RW = TW + KS - 1, TILE_VECS = RH * RW * 8;
-  extern __shared__ __align__(16) uint8_t dw_smem[];
-  uint4* tiles = reinterpret_cast<uint4*>(dw_smem);                      // 2 x [RH][RW][8]: the next tile loads while this one computes
-  const int cvec = threadIdx.x & 7, xl = threadIdx.x >> 3;
-  auto decode = [&](int tile, int& b, int& oy0, int& ox0, int& cb) {
-    cb = tile % c_blocks; tile /= c_blocks;
-    ox0 = (tile % x_blocks) * TW; tile /= x_blocks;
-    oy0 = (tile % y_blocks) * TH;
-    b = tile / y_blocks;
-  };
-  auto issue = [&](int tile, int buf) {
-    int b, oy0, ox0, cb;
-    decode(tile, b, oy0, ox0, cb);
-    const T* img = in + static_cast<size_t>(b) * H * W * C;
-    uint4* dst = tiles + buf * TILE_VECS;
-    for (int i = threadIdx.x; i < TILE_VECS; i += 256) {
-      const int cv = i & 7, px = i >> 3;
-      const int rx = px % RW, ry = px / RW;
-      const int iy = oy0 - pad + ry, ix = ox0 - pad + rx, cc = (cb * 8 + cv) * 8;
-      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W && cc < C;
-      const T* src = ok ? img + (static_cast<size_t>(iy) * W + ix) * C + cc : img;
-      const int nbytes = ok ? 16 : 0;    // src-size 0 -> zero fill (= the convolution's zero padding)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst + i)), "l"(src), "r"(nbytes) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  int tile = blockIdx.x, buf = 0;
-  if (tile < n_tiles) issue(tile, 0);
-  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
-    const int next = tile + gridDim.x;
-    if (next < n_tiles) {
-      issue(next, buf ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    int b, oy0, ox0, cb;
-    decode(tile, b, oy0, ox0, cb);
-    const int c8 = (cb * 8 + cvec) * 8;
-    const int ox = ox0 + xl;
-    if (c8 < C && ox < W) {
-      const uint4* tl = tiles + buf * TILE_VECS;
-      uint4 wq[KS * KS];                    // this thread's 8 channels of every tap (L1-resident after the first tile)
-#pragma unroll
-      for (int t = 0; t < KS * KS; ++t) wq[t] = __ldg(reinterpret_cast<const uint4*>(w + static_cast<size_t>(t) * C + c8));
-      float acc[KS][8];                     // ring of the KS output rows currently receiving input rows
-#pragma unroll
-      for (int r = 0; r < KS; ++r)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
-#pragma unroll
-      for (int rr = 0; rr < RH; ++rr) {
-        uint4 xq[KS];
-#pragma unroll
-        for (int s_ = 0; s_ < KS; ++s_) xq[s_] = tl[(rr * RW + xl + s_) * 8 + cvec];
-        // input row rr is tap row r of output row y = rr - r (all indices are compile-time after unrolling)
-#pragma unroll
-        for (int r = KS - 1; r >= 0; --r) {
-          const int y = rr - r;
-          if (y < 0 || y >= TH) continue;
-#pragma unroll
-          for (int s_ = 0; s_ < KS; ++s_) {
-            const unsigned short* xe = reinterpret_cast<const unsigned short*>(&xq[s_]);
-            const unsigned short* we = reinterpret_cast<const unsigned short*>(&wq[r * KS + s_]);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[y % KS][j] = fma16<T>(xe[j], we[j], acc[y % KS][j]);
-          }
-        }
-        const int yd = rr - (KS - 1);       // the output row that just received its last tap row
-        if (yd >= 0 && yd < TH) {
-          const int oy = oy0 + yd;
-          if (oy < H) {
-            uint4 pack;
-            T* pe = reinterpret_cast<T*>(&pack);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float v = rnd<T>(acc[yd % KS][j] + (bias ? __ldg(bias + c8 + j) : 0.f));
-              if (act == ACT_HARDSWISH) v = hardswish_f(v);
-              pe[j] = from_f<T>(v);
-            }
-            *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * H + oy) * W + ox) * C + c8) = pack;
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[yd % KS][j] = 0.f;
-        }
-      }
-    }
-    __syncthreads();                        // everybody is done with `buf` before the loads two tiles ahead overwrite it
-  }
-}
-
-template <typename T, int KS, int TH>
-static bool launch_dw_tile(const void* in, const void* w, const float* bias, void* out, int B, int H, int W, int C, int pad, int act,
-                           cudaStream_t st) {
-  static int en = -1;
-  if (en < 0) { const char* e = getenv("SB_DW_TILE"); en = (e && e[0] == '0') ? 0 : 1; }
-  if (!en || pad != (KS - 1) / 2) return false;
-  constexpr int RH = TH + KS - 1, RW = 32 + KS - 1;
-  constexpr size_t SMEM = 2 * static_cast<size_t>(RH) * RW * 8 * sizeof(uint4);
-  auto kern = dwconv_tile_kernel<T, KS, TH>;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM) != cudaSuccess) { cudaGetLastError(); return false; }
-    attr = true;
-  }
-  const int c_blocks = (C + 63) / 64, x_blocks = (W + 31) / 32, y_blocks = (H + TH - 1) / TH;
-  const long long n_tiles = static_cast<long long>(B) * y_blocks * x_blocks * c_blocks;
-  if (n_tiles > 0x7fffffffLL) return false;
-  const int grid = static_cast<int>(n_tiles < 2LL * num_sms() ? n_tiles : 2LL * num_sms());
-  kern<<<grid, 256, SMEM, st>>>((const T*)in, (const T*)w, bias, (T*)out, H, W, C, pad, act, c_blocks, x_blocks, y_blocks,
-                                static_cast<int>(n_tiles));
-  return true;
-}
-
 template <typename T, int KS, int STRIDE, int TY>
 static void launch_dw(const void* in, const void* w, const float* bias, void* out, int B, int H, int W, int C, int Ho, int Wo,
                       int pad, int act, cudaStream_t st) {
@@ -331,7 +209,6 @@ int det_dwconv(int dtype, const void* in, const void* w, const float* bias, void
   if (Ho <= 0 || Wo <= 0) return 0;
 #define DW(T_) \
   do { \
-    if (ks == 3 && stride == 1 && launch_dw_tile<T_, 3, 8>(in, w, bias, out, B, H, W, C, pad, act, st)) break; \
     if (ks == 3 && stride == 1) launch_dw<T_, 3, 1, 4>(in, w, bias, out, B, H, W, C, Ho, Wo, pad, act, st); \
     else if (ks == 3 && stride == 2) launch_dw<T_, 3, 2, 2>(in, w, bias, out, B, H, W, C, Ho, Wo, pad, act, st); \
     else if (ks == 5 && stride == 1) launch_dw<T_, 5, 1, 2>(in, w, bias, out, B, H, W, C, Ho, Wo, pad, act, st); \
