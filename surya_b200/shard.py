@@ -145,13 +145,16 @@ def gather_step_results(tok: torch.Tensor, score: torch.Tensor, bbox: torch.Tens
     [T, B], scores fp32 [T, B], boxes int16 [T, B, 6] (boxes are < 1025).  Returns per-rank lists in rank order; a no-op list of
     the local tensors for world size 1.  ~2.6 KB per crop on the wire."""
     rank, n = world()
-    parts = (tok.to(torch.int32), score.to(torch.float32), bbox.to(torch.int16))
+    box16 = bbox.to(torch.int16).contiguous()
     if n == 1:
-        return tuple([p] for p in parts)
+        return [tok.to(torch.int32)], [score.to(torch.float32)], [box16]
+    # NCCL has no 16-bit integer type: the six int16 coordinates of a box travel as three int32 words
+    parts = (tok.to(torch.int32), score.to(torch.float32), box16.view(torch.int32))
     out = []
     for p in parts:
         p = p.contiguous()
         bufs = [torch.empty_like(p) for _ in range(n)]
         dist.all_gather(bufs, p)
         out.append(bufs)
+    out[2] = [b.view(torch.int16) for b in out[2]]
     return tuple(out)

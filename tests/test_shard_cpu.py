@@ -153,3 +153,33 @@ def test_sharded_ocr_world2():
         for j, (page, poly, conf, toks, scs) in enumerate(pg):
             assert page == gid and poly[0] == [gid, j] and conf == round(0.5 + 0.1 * j, 4)
             assert toks == [gid, j, 7][: 1 + (gid + j) % 3] and len(scs) == len(toks)
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from surya_b200.shard import gather_step_results
+
+    T, B = 5, 4
+    tok = torch.arange(T * B, dtype=torch.int64).reshape(T, B) + 1000 * rank
+    score = torch.full((T, B), 0.25 * (rank + 1))
+    bbox = (torch.arange(T * B * 6, dtype=torch.int64).reshape(T, B, 6) % 1025) + rank
+    toks, scores, boxes = gather_step_results(tok, score, bbox)
+    ok = all(torch.equal(toks[r].long(), torch.arange(T * B).reshape(T, B) + 1000 * r) for r in range(world))
+    ok &= all(torch.equal(boxes[r].long(), (torch.arange(T * B * 6).reshape(T, B, 6) % 1025) + r) for r in range(world))
+    ok &= all(float(scores[r][0, 0]) == 0.25 * (r + 1) for r in range(world)) and boxes[0].dtype == torch.int16
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gather_step_results_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res)
