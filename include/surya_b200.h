@@ -296,16 +296,20 @@ int sb_rmsnorm_adetr(int dtype, const void* x, int ldx, const void* w, void* y, 
                      void* stream);
 /* nn.LayerNorm (donut/encoder.py:117,163,544-548; layout/model/decoder.py:73). */
 int sb_layernorm(int dtype, const void* x, const void* w, const void* b, void* y, int rows, int C, float eps, void* stream);
-/* im2col of the patch-embedding Conv2d(k = stride = P) (donut/encoder.py:228-230): NCHW -> [B*gh*gw, Kp], col = c*P*P+ky*P+kx. */
+/* im2col of the patch-embedding Conv2d(k = stride = P) (donut/encoder.py:228-230): NCHW -> [B*gh*gw, Kp], col = c*P*P+ky*P+kx;
+ * gh = ceil(H/P), gw = ceil(W/P), a partial last patch is zero filled (DonutSwinPatchEmbeddings.maybe_pad, :232-239). */
 int sb_patch_gather(int dtype, const void* in, int in_f32, void* out, int B, int Cin, int H, int W, int P, int Kp, void* stream);
 /* x[b, t, :] += tab[t, :] (stage sin-cos table donut/encoder.py:773-776; position_embeddings layout/model/encoder.py:76-77). */
 int sb_add_bcast_rows(int dtype, void* x, const void* tab, long long rows, int rows_per_batch, int C, void* stream);
-/* DonutSwinPatchMerging's 2x2 gather (donut/encoder.py:301-312): [B,H,W,C] -> [B,H/2,W/2,4C]. */
+/* DonutSwinPatchMerging's 2x2 gather (donut/encoder.py:301-312): [B,H,W,C] -> [B,ceil(H/2),ceil(W/2),4C]; an odd H / W is zero
+ * padded (maybe_pad, :281-287). */
 int sb_patch_merge_gather(int dtype, const void* x, void* y, int B, int H, int W, int C, void* stream);
 /* DonutSwinLayer attention core (donut/encoder.py:383-442, 562-590, 598-664): 8x8 windows, cyclic shift, relative-position
- * bias table [225, nh], -100 shift mask; qkv [B*H*W, 3C] and out [B*H*W, C] in natural token order. */
-int sb_swin_window_attn(int dtype, const void* qkv, const void* bias_table, void* out, int B, int H, int W, int C, int nh,
-                        int shift, void* stream);
+ * bias table [225, nh], -100 shift mask; qkv [B*H*W, 3C] and out [B*H*W, C] in natural token order.  H / W that are not multiples
+ * of 8 are zero padded to the window like maybe_pad (:591-596, crop :657-659): a pad token's q/k/v is the fp32 QKV bias
+ * `qkv_bias` [3C] (required then, may be NULL otherwise).  H, W < 8 is an error (the reference's own bias table breaks there). */
+int sb_swin_window_attn(int dtype, const void* qkv, const float* qkv_bias, const void* bias_table, void* out, int B, int H, int W,
+                        int C, int nh, int shift, void* stream);
 /* BboxEmbedding (layout/model/decoder.py:36-57): tables = 15 device pointers (w,h,cx,cy,xskew,yskew,x1,y1,...,y4,label). */
 int sb_bbox_embed_sum(int dtype, const long long* boxes, const void* const* tables, void* out, int n, int Hd, int bbox_size,
                       void* stream);

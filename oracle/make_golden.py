@@ -248,6 +248,28 @@ def make_predictor_trace_golden():
           f"tokens[0]={tokens[0]}")
 
 
+def make_swin_window_padding_golden():
+    """Oracle pin for DonutSwinLayer.maybe_pad (donut/encoder.py:591-596, crop :657-659): a 288x352 input gives token grids
+    72x88 / 36x44 / 18x22 / 9x11 -- every merge sees even sides (the reference's floor-sized stage position tables demand it) but
+    stages 1-3 are not multiples of the 8x8 window, so their layers run on zero-padded grids with the shift mask of the padded
+    size.  Encoder output only (1 page)."""
+    from surya_b200.config import LayoutConfig, SwinConfig, table_decoder
+    from surya_b200.synth import adetr_table_state_dict, layout_synthetic_pages, swin_state_dict
+
+    enc_cfg = SwinConfig(image_size=(288, 352), depths=(2, 2, 2, 2), encoder_length=99)
+    cfg = LayoutConfig(encoder=enc_cfg, decoder=table_decoder(2))
+    sde, sdd = swin_state_dict(enc_cfg, 5), adetr_table_state_dict(cfg.decoder, 5)
+    enc, _ = ref_shim.build_reference_table_models(cfg, sde, sdd)
+    x = layout_synthetic_pages(1, enc_cfg.image_size, seed=23)
+    with torch.inference_mode():
+        ref_enc = enc(pixel_values=x).last_hidden_state
+    g = {"encoder": ref_enc.float().clone(), "input_checksum": x.double().sum(),
+         "meta": {"kind": "swin_window_padding", "seed": 5, "page_seed": 23, "image_size": [288, 352], "torch": str(torch.__version__),
+                  "reference": "VikParuchuri/surya@80e9a7e (v0.14.6), fp32 CPU"}}
+    torch.save(g, GOLDEN / "swin_window_padding.pt")
+    print(f"[golden] swin_window_padding: enc {tuple(ref_enc.shape)} absmax {ref_enc.abs().max():.3f}")
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
@@ -257,6 +279,7 @@ def main():
     if "table" in which:
         make_table_golden()
         make_layout_variants_golden()
+        make_swin_window_padding_golden()
     if "det" in which:
         make_det_golden()
     if "trace" in which:

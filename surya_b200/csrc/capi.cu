@@ -162,9 +162,9 @@ int sb_add_bcast_rows(int dtype, void* x, const void* tab, long long rows, int r
 int sb_patch_merge_gather(int dtype, const void* x, void* y, int B, int H, int W, int C, void* stream) {
   return patch_merge_gather(dtype, x, y, B, H, W, C, static_cast<cudaStream_t>(stream));
 }
-int sb_swin_window_attn(int dtype, const void* qkv, const void* bias_table, void* out, int B, int H, int W, int C, int nh,
-                        int shift, void* stream) {
-  return swin_window_attn(dtype, qkv, bias_table, out, B, H, W, C, nh, shift, static_cast<cudaStream_t>(stream));
+int sb_swin_window_attn(int dtype, const void* qkv, const float* qkv_bias, const void* bias_table, void* out, int B, int H, int W,
+                        int C, int nh, int shift, void* stream) {
+  return swin_window_attn(dtype, qkv, qkv_bias, bias_table, out, B, H, W, C, nh, shift, static_cast<cudaStream_t>(stream));
 }
 int sb_bbox_embed_sum(int dtype, const long long* boxes, const void* const* tables, void* out, int n, int Hd, int bbox_size,
                       void* stream) {

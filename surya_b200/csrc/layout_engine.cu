@@ -115,7 +115,8 @@ static int run_encoder(sb_layout_engine* e, const void* pixels, int is_f32, int 
       CK(layernorm(dt, x, e->WL(s, l, SB_LWE_LN1_W), e->WL(s, l, SB_LWE_LN1_B), e->h, R, C, c.enc_ln_eps, st));
       CK(lin(e, e->h, C, e->WL(s, l, SB_LWE_QKV_W), C, e->qkv, 3 * C, R, 3 * C, C, e->WL(s, l, SB_LWE_QKV_B), nullptr, 0, ACT_NONE,
              0, st));
-      CK(swin_window_attn(dt, e->qkv, e->WL(s, l, SB_LWE_RPB), attn_out, B, H, W, C, nh, shift, st));
+      CK(swin_window_attn(dt, e->qkv, static_cast<const float*>(e->WL(s, l, SB_LWE_QKV_B)), e->WL(s, l, SB_LWE_RPB), attn_out, B, H, W, C, nh,
+                          shift, st));
       // x = attn_out @ Wo^T + bo + x   (written over h first, then swapped in: the GEMM must not alias its residual's rows
       // with a different pitch; here both are [R, C] so in-place on x is the same read-then-write per element)
       CK(lin(e, attn_out, C, e->WL(s, l, SB_LWE_O_W), C, x, C, R, C, C, e->WL(s, l, SB_LWE_O_B), x, C, ACT_NONE, 0, st));
@@ -125,6 +126,11 @@ static int run_encoder(sb_layout_engine* e, const void* pixels, int is_f32, int 
       CK(lin(e, e->mlp, 4 * C, e->WL(s, l, SB_LWE_FC2_W), 4 * C, x, C, R, C, 4 * C, e->WL(s, l, SB_LWE_FC2_B), x, C, ACT_NONE, 0, st));
     }
     if (s < c.n_stages - 1) {
+      if ((H | W) & 1) {
+        // the reference pads here (encoder.py:281-287) and then fails on its floor-sized stage position table (:730-735, 773-776)
+        set_error("sb_layout_encode: stage %d has an odd %dx%d token grid (the reference's stage position table cannot follow it)", s, H, W);
+        return -31;
+      }
       CK(patch_merge_gather(dt, x, e->mlp, B, H, W, C, st));
       rows /= 4;
       H /= 2; W /= 2;
@@ -216,6 +222,12 @@ int sb_layout_create(const sb_layout_config* cfg, const void* const* weights, in
   const sb_layout_config& c = e->c;
   if (c.n_stages < 1 || c.n_stages > 4 || c.n_out_heads < 1 || c.n_out_heads > 4 || c.head_dim != 64) {
     set_error("sb_layout_create: 1..4 stages, 1..4 output heads and head_dim 64 are supported");
+    delete e;
+    return -2;
+  }
+  if (c.patch <= 0 || c.img_h % c.patch || c.img_w % c.patch) {
+    // the reference would zero pad the pixels (encoder.py:232-239) and then fail on its floor-sized position tables
+    set_error("sb_layout_create: image size %dx%d is not a multiple of the patch size %d", c.img_h, c.img_w, c.patch);
     delete e;
     return -2;
   }

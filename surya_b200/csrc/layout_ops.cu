@@ -140,7 +140,7 @@ template <typename T, typename InT>
 __global__ void __launch_bounds__(256) patch_gather_kernel(const InT* __restrict__ in, T* __restrict__ out, int Cin, int H, int W,
                                                           int P, int Kp) {
   // one thread = 8 consecutive output columns of one patch (16-byte store); (patch row, image) come from the grid
-  const int gw = W / P, gh = H / P;
+  const int gw = (W + P - 1) / P, gh = (H + P - 1) / P;     // a partial last patch row / column is zero padded (maybe_pad)
   const int groups = Kp >> 3;
   const int t = blockIdx.x * 256 + threadIdx.x;
   if (t >= gw * groups) return;
@@ -156,8 +156,11 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const InT* __restrict
     if (col < K) {
       const int c = col / PP, r = col - c * PP;
       const int ky = r / P, kx = r - ky * P;
-      const InT* p = in + ((static_cast<size_t>(b) * Cin + c) * H + gy * P + ky) * W + gx * P + kx;
-      if constexpr (sizeof(InT) == 4) v = static_cast<float>(*p); else v = to_f<InT>(*p);
+      const int yy = gy * P + ky, xx = gx * P + kx;
+      if (yy < H && xx < W) {
+        const InT* p = in + ((static_cast<size_t>(b) * Cin + c) * H + yy) * W + xx;
+        if constexpr (sizeof(InT) == 4) v = static_cast<float>(*p); else v = to_f<InT>(*p);
+      }
     }
     pe[j] = from_f<T>(v);
   }
@@ -166,9 +169,10 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const InT* __restrict
 
 int patch_gather(int dtype, const void* in, int in_f32, void* out, int B, int Cin, int H, int W, int P, int Kp, cudaStream_t st) {
   if (B <= 0) return 0;
-  if (H % P || W % P || Kp % 8 || Kp < Cin * P * P) { set_error("patch_gather: H, W multiples of P and Kp >= Cin*P*P, Kp %% 8 == 0"); return -1; }
-  if (B > 65535 || H / P > 65535) { set_error("patch_gather: batch / rows too large for the grid"); return -1; }
-  dim3 grid(((W / P) * (Kp / 8) + 255) / 256, H / P, B);
+  if (P <= 0 || Kp % 8 || Kp < Cin * P * P) { set_error("patch_gather: Kp >= Cin*P*P and Kp %% 8 == 0"); return -1; }
+  const int gh = (H + P - 1) / P, gw = (W + P - 1) / P;
+  if (B > 65535 || gh > 65535) { set_error("patch_gather: batch / rows too large for the grid"); return -1; }
+  dim3 grid((gw * (Kp / 8) + 255) / 256, gh, B);
 #define PG(T_, I_) patch_gather_kernel<T_, I_><<<grid, 256, 0, st>>>((const I_*)in, (T_*)out, Cin, H, W, P, Kp)
   if (dtype == DT_F16) { if (in_f32) PG(__half, float); else PG(__half, __half); }
   else { if (in_f32) PG(__nv_bfloat16, float); else PG(__nv_bfloat16, __nv_bfloat16); }
@@ -206,10 +210,11 @@ int add_bcast_rows(int dtype, void* x, const void* tab, long long rows, int rows
 }
 
 // ------------------------------------------------------------------------------------------------ 2x2 patch-merging gather
-// x [B, H, W, C] -> y [B, H/2, W/2, 4C], channel blocks (dy,dx) = (0,0), (1,0), (0,1), (1,1)
+// x [B, H, W, C] -> y [B, ceil(H/2), ceil(W/2), 4C], channel blocks (dy,dx) = (0,0), (1,0), (0,1), (1,1); an odd H / W is zero
+// padded by one row / column (DonutSwinPatchMerging.maybe_pad, encoder.py:281-287)
 template <typename T>
 __global__ void patch_merge_gather_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C) {
-  const int cv = C >> 3, Ho = H / 2, Wo = W / 2;
+  const int cv = C >> 3, Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const long long total = static_cast<long long>(B) * Ho * Wo * 4 * cv;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -220,14 +225,16 @@ __global__ void patch_merge_gather_kernel(const T* __restrict__ x, T* __restrict
     const int ox = r % Wo, oy = (r / Wo) % Ho;
     const int b = r / (static_cast<long long>(Wo) * Ho);
     const int dy = blk & 1, dx = blk >> 1;
-    const uint4 v = *reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + 2 * oy + dy) * W + 2 * ox + dx) * C + c8);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (2 * oy + dy < H && 2 * ox + dx < W)
+      v = *reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + 2 * oy + dy) * W + 2 * ox + dx) * C + c8);
     *reinterpret_cast<uint4*>(y + (((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * 4 + blk) * C + c8) = v;
   }
 }
 
 int patch_merge_gather(int dtype, const void* x, void* y, int B, int H, int W, int C, cudaStream_t st) {
-  if (C % 8 || H % 2 || W % 2) { set_error("patch_merge_gather: C %% 8, even H and W"); return -1; }
-  const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * 4 * (C / 8);
+  if (C % 8) { set_error("patch_merge_gather: C must be a multiple of 8"); return -1; }
+  const long long total = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2) * 4 * (C / 8);
   int grid = static_cast<int>((total + 255) / 256);
   if (grid > num_sms() * 32) grid = num_sms() * 32;
   if (dtype == DT_F16) patch_merge_gather_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, (__half*)y, B, H, W, C);
@@ -254,10 +261,13 @@ template <> struct MmaS<__half> {
 
 // qkv [B*H*W, 3C] natural token order (q | k | v, head h at h*32); bias_table T [225, nh]; out [B*H*W, C].
 // One CTA = one 8x8 window x 4 heads (128 contiguous channels per token); warp w owns query rows 16w..16w+15.
+// H, W that are not multiples of the window are handled like DonutSwinLayer.maybe_pad (encoder.py:591-596): the token grid is
+// padded with ZERO rows (after layernorm_before) to Hp x Wp, so a pad token's q / k / v is the QKV bias; windows, the cyclic shift
+// and the shift mask live on the padded grid and pad query rows are dropped (the reference crops them, encoder.py:657-659).
 template <typename T>
-__global__ void __launch_bounds__(128) swin_window_attn_kernel(const T* __restrict__ qkv, const T* __restrict__ bias_table,
-                                                               T* __restrict__ out, int H, int W, int C, int nh, int shift,
-                                                               float scale) {
+__global__ void __launch_bounds__(128) swin_window_attn_kernel(const T* __restrict__ qkv, const float* __restrict__ qkv_bias,
+                                                               const T* __restrict__ bias_table, T* __restrict__ out, int Hr,
+                                                               int Wr, int H, int W, int C, int nh, int shift, float scale) {
   constexpr int WS = 8, NT = 64, HD = 32, HG = 4, LDS = HG * HD + 8;
   extern __shared__ __align__(16) uint8_t smem_sw[];
   T* sQ = reinterpret_cast<T*>(smem_sw);
@@ -277,8 +287,8 @@ __global__ void __launch_bounds__(128) swin_window_attn_kernel(const T* __restri
   if (tid < NT) {
     const int py = tid / WS, px = tid % WS;
     const int ys = wy * WS + py, xs = wx * WS + px;                 // coordinates in the shifted image
-    const int y = (ys + shift) % H, x = (xs + shift) % W;           // torch.roll(-shift) source
-    s_tok[tid] = (b * H + y) * W + x;
+    const int y = (ys + shift) % H, x = (xs + shift) % W;           // torch.roll(-shift) source (H, W = padded grid)
+    s_tok[tid] = (y < Hr && x < Wr) ? (b * Hr + y) * Wr + x : -1;   // -1 = pad token
     int ry = 0, rx = 0;
     if (shift > 0) {
       ry = ys < H - WS ? 0 : (ys < H - shift ? 1 : 2);
@@ -295,10 +305,21 @@ __global__ void __launch_bounds__(128) swin_window_attn_kernel(const T* __restri
   constexpr int VPR = HG * HD / 8;  // 16
   for (int i = tid; i < NT * VPR; i += 128) {
     const int r = i / VPR, c = i % VPR;
-    const T* base = qkv + static_cast<size_t>(s_tok[r]) * (3 * C) + hg * HG * HD + c * 8;
-    *reinterpret_cast<uint4*>(sQ + r * LDS + c * 8) = *reinterpret_cast<const uint4*>(base);
-    *reinterpret_cast<uint4*>(sK + r * LDS + c * 8) = *reinterpret_cast<const uint4*>(base + C);
-    *reinterpret_cast<uint4*>(sV + r * LDS + c * 8) = *reinterpret_cast<const uint4*>(base + 2 * C);
+    if (s_tok[r] >= 0) {
+      const T* base = qkv + static_cast<size_t>(s_tok[r]) * (3 * C) + hg * HG * HD + c * 8;
+      *reinterpret_cast<uint4*>(sQ + r * LDS + c * 8) = *reinterpret_cast<const uint4*>(base);
+      *reinterpret_cast<uint4*>(sK + r * LDS + c * 8) = *reinterpret_cast<const uint4*>(base + C);
+      *reinterpret_cast<uint4*>(sV + r * LDS + c * 8) = *reinterpret_cast<const uint4*>(base + 2 * C);
+    } else {
+      // Linear(0) = bias, rounded to T like any other GEMM output row
+      const float* bq = qkv_bias + hg * HG * HD + c * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sQ[r * LDS + c * 8 + j] = from_f<T>(bq[j]);
+        sK[r * LDS + c * 8 + j] = from_f<T>(bq[C + j]);
+        sV[r * LDS + c * 8 + j] = from_f<T>(bq[2 * C + j]);
+      }
+    }
   }
   __syncthreads();
 
@@ -375,33 +396,44 @@ __global__ void __launch_bounds__(128) swin_window_attn_kernel(const T* __restri
         MmaS<T>::run(O[dn + 1], aP, bv[2], bv[3]);
       }
     }
-    T* o0 = out + static_cast<size_t>(s_tok[q0]) * C + (hg * HG + hh) * HD;
-    T* o1 = out + static_cast<size_t>(s_tok[q1]) * C + (hg * HG + hh) * HD;
+    const int tk0 = s_tok[q0], tk1 = s_tok[q1];
+    T* o0 = out + static_cast<size_t>(tk0 < 0 ? 0 : tk0) * C + (hg * HG + hh) * HD;
+    T* o1 = out + static_cast<size_t>(tk1 < 0 ? 0 : tk1) * C + (hg * HG + hh) * HD;
 #pragma unroll
     for (int dn = 0; dn < 4; ++dn) {
-      *reinterpret_cast<uint32_t*>(o0 + dn * 8 + 2 * t) = MmaS<T>::pack(O[dn][0], O[dn][1]);
-      *reinterpret_cast<uint32_t*>(o1 + dn * 8 + 2 * t) = MmaS<T>::pack(O[dn][2], O[dn][3]);
+      if (tk0 >= 0) *reinterpret_cast<uint32_t*>(o0 + dn * 8 + 2 * t) = MmaS<T>::pack(O[dn][0], O[dn][1]);
+      if (tk1 >= 0) *reinterpret_cast<uint32_t*>(o1 + dn * 8 + 2 * t) = MmaS<T>::pack(O[dn][2], O[dn][3]);
     }
   }
 }
 
-int swin_window_attn(int dtype, const void* qkv, const void* bias_table, void* out, int B, int H, int W, int C, int nh, int shift,
-                     cudaStream_t st) {
-  if (H % 8 || W % 8 || nh % 4 || C != nh * 32) {
-    set_error("swin_window_attn: needs H, W multiples of the 8x8 window, head_dim 32 and heads in groups of 4 (H=%d W=%d C=%d nh=%d)", H, W, C, nh);
+int swin_window_attn(int dtype, const void* qkv, const float* qkv_bias, const void* bias_table, void* out, int B, int H, int W, int C,
+                     int nh, int shift, cudaStream_t st) {
+  if (nh % 4 || C != nh * 32) {
+    set_error("swin_window_attn: needs head_dim 32 and heads in groups of 4 (C=%d nh=%d)", C, nh);
+    return -1;
+  }
+  if (H < 8 || W < 8) {
+    // the reference shrinks the window to min(H, W) here (encoder.py:550-558) and then fails on its own 8x8 relative-position bias
+    set_error("swin_window_attn: token grid %dx%d is smaller than the 8x8 window", H, W);
+    return -1;
+  }
+  const int Hp = (H + 7) / 8 * 8, Wp = (W + 7) / 8 * 8;
+  if ((Hp != H || Wp != W) && !qkv_bias) {
+    set_error("swin_window_attn: a %dx%d grid needs window padding, which needs the QKV bias (pad tokens are Linear(0))", H, W);
     return -1;
   }
   constexpr size_t SMEM = 3 * 64 * (128 + 8) * 2 + 225 * 4 * 4;
-  dim3 grid(B * (H / 8) * (W / 8), nh / 4), block(128);
+  dim3 grid(B * (Hp / 8) * (Wp / 8), nh / 4), block(128);
   const float scale = 0.17677669529663687f;  // 32^-0.5
   if (dtype == DT_F16) {
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(swin_window_attn_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM); set = true; }
-    swin_window_attn_kernel<__half><<<grid, block, SMEM, st>>>((const __half*)qkv, (const __half*)bias_table, (__half*)out, H, W, C, nh, shift, scale);
+    swin_window_attn_kernel<__half><<<grid, block, SMEM, st>>>((const __half*)qkv, qkv_bias, (const __half*)bias_table, (__half*)out, H, W, Hp, Wp, C, nh, shift, scale);
   } else {
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(swin_window_attn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM); set = true; }
-    swin_window_attn_kernel<__nv_bfloat16><<<grid, block, SMEM, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)bias_table, (__nv_bfloat16*)out, H, W, C, nh, shift, scale);
+    swin_window_attn_kernel<__nv_bfloat16><<<grid, block, SMEM, st>>>((const __nv_bfloat16*)qkv, qkv_bias, (const __nv_bfloat16*)bias_table, (__nv_bfloat16*)out, H, W, Hp, Wp, C, nh, shift, scale);
   }
   return launch_ok();
 }

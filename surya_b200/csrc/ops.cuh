@@ -96,8 +96,8 @@ int layernorm(int dtype, const void* x, const void* w, const void* b, void* y, i
 int patch_gather(int dtype, const void* in, int in_f32, void* out, int B, int Cin, int H, int W, int P, int Kp, cudaStream_t st);
 int add_bcast_rows(int dtype, void* x, const void* tab, long long rows, int rows_per_batch, int C, cudaStream_t st);
 int patch_merge_gather(int dtype, const void* x, void* y, int B, int H, int W, int C, cudaStream_t st);
-int swin_window_attn(int dtype, const void* qkv, const void* bias_table, void* out, int B, int H, int W, int C, int nh, int shift,
-                     cudaStream_t st);
+int swin_window_attn(int dtype, const void* qkv, const float* qkv_bias, const void* bias_table, void* out, int B, int H, int W, int C,
+                     int nh, int shift, cudaStream_t st);
 int bbox_embed_sum(int dtype, const long long* boxes, const void* const* tables, void* out, int n, int Hd, int bbox_size,
                    cudaStream_t st);
 int attn_single_query(int dtype, const void* q, int ldq, const void* K, const void* V, long long bs, long long hs, long long ts,

@@ -258,7 +258,7 @@ class LayoutEngine:
             for L in st["layers"]:
                 h = ops.layernorm(x, *L["ln1"], eps=e.layer_norm_eps)
                 qkv = ops.gemm(h, L["qkv_w"], bias=L["qkv_b"])
-                a = ops.swin_window_attn(qkv, L["rpb"], B, H, W, nh, L["shift"] if min(H, W) > e.window_size else 0)
+                a = ops.swin_window_attn(qkv, L["rpb"], B, H, W, nh, L["shift"] if min(H, W) > e.window_size else 0, qkv_bias=L["qkv_b"])
                 x = ops.gemm(a, L["o_w"], bias=L["o_b"], residual=x)
                 h = ops.layernorm(x, *L["ln2"], eps=e.layer_norm_eps)
                 h = ops.gemm(h, L["fc1_w"], bias=L["fc1_b"], act="gelu")

@@ -292,7 +292,7 @@ def patch_gather(pixels, P, Kp, dtype):
     lib = _lib.load()
     B, C, H, W = pixels.shape
     pixels = pixels.contiguous()
-    out = torch.empty((B * (H // P) * (W // P), Kp), device=pixels.device, dtype=dtype)
+    out = torch.empty((B * (-(-H // P)) * (-(-W // P)), Kp), device=pixels.device, dtype=dtype)
     check(lib.sb_patch_gather(dt_code(dtype), ptr(pixels), c_int(1 if pixels.dtype == torch.float32 else 0), ptr(out), c_int(B),
                               c_int(C), c_int(H), c_int(W), c_int(P), c_int(Kp), stream_ptr()), "sb_patch_gather")
     return out
@@ -308,18 +308,20 @@ def add_bcast_rows_(x, tab):
 def patch_merge_gather(x, B, H, W):
     lib = _lib.load()
     C = x.shape[1]
-    out = torch.empty((B * (H // 2) * (W // 2), 4 * C), device=x.device, dtype=x.dtype)
+    out = torch.empty((B * ((H + 1) // 2) * ((W + 1) // 2), 4 * C), device=x.device, dtype=x.dtype)
     check(lib.sb_patch_merge_gather(dt_code(x.dtype), ptr(x), ptr(out), c_int(B), c_int(H), c_int(W), c_int(C), stream_ptr()),
           "sb_patch_merge_gather")
     return out
 
 
-def swin_window_attn(qkv, bias_table, B, H, W, nh, shift):
+def swin_window_attn(qkv, bias_table, B, H, W, nh, shift, qkv_bias=None):
+    """qkv_bias (fp32 [3C]) is needed when H or W is not a multiple of the 8x8 window: pad tokens are Linear(0) = bias."""
     lib = _lib.load()
     C = qkv.shape[1] // 3
     out = torch.empty((qkv.shape[0], C), device=qkv.device, dtype=qkv.dtype)
-    check(lib.sb_swin_window_attn(dt_code(qkv.dtype), ptr(qkv), ptr(bias_table), ptr(out), c_int(B), c_int(H), c_int(W), c_int(C),
-                                  c_int(nh), c_int(shift), stream_ptr()), "sb_swin_window_attn")
+    check(lib.sb_swin_window_attn(dt_code(qkv.dtype), ptr(qkv), ptr(qkv_bias) if qkv_bias is not None else None, ptr(bias_table),
+                                  ptr(out), c_int(B), c_int(H), c_int(W), c_int(C), c_int(nh), c_int(shift), stream_ptr()),
+          "sb_swin_window_attn")
     return out
 
 

@@ -384,6 +384,22 @@ def test_oracle_pinned_nonsquare_swin_and_cellpass_prompt():
     assert torch.equal(tok, g["tokens"])
 
 
+def test_oracle_pinned_swin_window_padding():
+    """Oracle's maybe_pad branch (zero-padded windows, padded-size shift mask, crop) vs the reference's Swin encoder on a 288x352
+    input whose later stages (36x44, 18x22, 9x11 tokens) are not multiples of the 8x8 window."""
+    from oracle import layout_oracle as L
+    from surya_b200.config import SwinConfig
+    from surya_b200.synth import layout_synthetic_pages, swin_state_dict
+
+    g = torch.load(GOLDEN / "swin_window_padding.pt")
+    enc_cfg = SwinConfig(image_size=tuple(g["meta"]["image_size"]), depths=(2, 2, 2, 2), encoder_length=99)
+    sde = swin_state_dict(enc_cfg, g["meta"]["seed"])
+    x = layout_synthetic_pages(1, enc_cfg.image_size, seed=g["meta"]["page_seed"])
+    enc = L.swin_forward(sde, enc_cfg, x)
+    assert enc.shape == g["encoder"].shape == (1, 99, 1024)
+    assert (enc - g["encoder"]).abs().max().item() < 1e-5
+
+
 def test_committed_bench_lines_follow_the_contract():
     """The bench lines committed under profiles/ carry every key the driver's contract names (schema guard for bench.py)."""
     import json

@@ -106,6 +106,48 @@ def test_swin_window_attn(built_lib, dtype, shift, nh, H, W):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shift,H,W", [(0, 9, 11), (4, 18, 22), (4, 12, 40), (0, 36, 44)])
+def test_swin_window_attn_zero_padded_windows(built_lib, dtype, shift, H, W):
+    """DonutSwinLayer.maybe_pad (donut/encoder.py:591-596) + crop (:657-659): grids that are not multiples of the window run on a
+    zero-padded grid — pad tokens are Linear(0) = the QKV bias, the shift mask is the padded grid's, pad query rows are dropped."""
+    from oracle.layout_oracle import relative_position_index, shift_attn_mask, window_partition, window_reverse
+    from surya_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    B, nh, hd, ws = 2, 8, 32, 8
+    C = nh * hd
+    qkv = torch.randn(B * H * W, 3 * C, generator=g).to(dtype)
+    qb = (0.3 * torch.randn(3 * C, generator=g)).to(dtype).float()
+    table = (0.5 * torch.randn((2 * ws - 1) ** 2, nh, generator=g)).to(dtype)
+    got = ops.swin_window_attn(qkv.cuda(), table.cuda(), B, H, W, nh, shift, qkv_bias=qb.cuda())
+    Hp, Wp = (H + 7) // 8 * 8, (W + 7) // 8 * 8
+    x = qb.to(dtype).expand(B, Hp, Wp, 3 * C).clone()
+    x[:, :H, :W] = qkv.view(B, H, W, 3 * C)
+    if shift:
+        x = torch.roll(x, (-shift, -shift), (1, 2))
+    win = window_partition(x, ws).view(-1, ws * ws, 3, nh, hd)
+    q, k, v = (win[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    s = (q.float() @ k.float().transpose(-1, -2)).to(dtype)
+    s = (s.float() / math.sqrt(hd)).to(dtype)
+    bias = table[relative_position_index(ws).view(-1)].view(ws * ws, ws * ws, nh).permute(2, 0, 1)
+    s = (s.float() + bias.float()).to(dtype)
+    if shift:
+        mask = shift_attn_mask(Hp, Wp, ws, shift, dtype)
+        s = (s.view(B, -1, nh, 64, 64).float() + mask.float()[None, :, None]).to(dtype).view(-1, nh, 64, 64)
+    p = torch.softmax(s.float(), -1).to(dtype)
+    ctx = (p.float() @ v.float()).to(dtype).permute(0, 2, 1, 3).reshape(-1, ws, ws, C)
+    ref = window_reverse(ctx, ws, Hp, Wp)
+    if shift:
+        ref = torch.roll(ref, (shift, shift), (1, 2))
+    ref = ref[:, :H, :W].reshape(B * H * W, C)
+    _close(got, ref, dtype, scale=1.0, n_ulp=6.0)
+    with pytest.raises(Exception, match="QKV bias"):
+        ops.swin_window_attn(qkv.cuda(), table.cuda(), B, H, W, nh, shift)
+    with pytest.raises(Exception, match="smaller than the 8x8 window"):
+        ops.swin_window_attn(qkv[: B * 6 * 16].cuda(), table.cuda(), B, 6, 16, nh, 0, qkv_bias=qb.cuda())
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_bbox_embed_sum(built_lib, dtype):
     from oracle.layout_oracle import bbox_embedding
     from surya_b200 import ops
@@ -178,6 +220,36 @@ def test_swin_encoder_vs_reference_golden(built_lib, dtype, tol):
     rel = ((enc - ref).norm() / ref.norm()).item()
     print(f"swin encoder {dtype}: max abs err {err:.4g} (ref max {ref.abs().max():.3g}), rel fro {rel:.3g}")
     assert err < tol * ref.abs().max().item() and rel < tol / 4
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 1e-2), (torch.bfloat16, 6e-2)])
+def test_swin_encoder_window_padding_vs_reference_golden(built_lib, dtype, tol):
+    """288x352 input: token grids 36x44, 18x22 and 9x11 are not multiples of the 8x8 window, so the reference pads them
+    (donut/encoder.py:591-596).  Engine (C++ loop) and the op-by-op path vs the reference's own output, and bit-identical to each
+    other."""
+    from surya_b200.config import LayoutConfig, SwinConfig, table_decoder
+    from surya_b200.layout import LayoutEngine
+    from surya_b200.synth import adetr_table_state_dict, layout_synthetic_pages, swin_state_dict
+
+    g = torch.load(GOLDEN / "swin_window_padding.pt")
+    enc_cfg = SwinConfig(image_size=tuple(g["meta"]["image_size"]), depths=(2, 2, 2, 2), encoder_length=99)
+    cfg = LayoutConfig(encoder=enc_cfg, decoder=table_decoder(2))
+    sde, sdd = swin_state_dict(enc_cfg, g["meta"]["seed"]), adetr_table_state_dict(cfg.decoder, g["meta"]["seed"])
+    x = layout_synthetic_pages(1, enc_cfg.image_size, seed=g["meta"]["page_seed"])
+    assert abs(float(x.double().sum()) - float(g["input_checksum"])) < 1e-6
+    ref = g["encoder"]
+    outs = []
+    for impl in ("native", "ops"):
+        eng = LayoutEngine(cfg, sde, sdd, dtype=dtype, impl=impl)
+        enc = eng.encode(x.cuda())
+        outs.append(enc)
+        encf = enc.float().cpu()
+        err = (encf - ref).abs().max().item()
+        rel = ((encf - ref).norm() / ref.norm()).item()
+        print(f"swin encoder with window padding, {impl}, {dtype}: max abs err {err:.4g} (ref max {ref.abs().max():.3g}), rel fro {rel:.3g}")
+        assert enc.shape == (1, 99, 1024)
+        assert err < tol * ref.abs().max().item() and rel < tol / 4
+    assert torch.equal(outs[0], outs[1])
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float16, 1e-2), (torch.bfloat16, 6e-2)])
