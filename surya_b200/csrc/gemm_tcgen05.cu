@@ -12,6 +12,10 @@
 // Rounding to the storage type happens exactly where eager PyTorch has an op boundary (after the
 // Linear, after the activation, after the residual add) so results track the reference path.
 #include "gemm.cuh"
+
+#include <mutex>
+#include <string>
+#include <unordered_map>
 #include "gemm_epilogue.cuh"
 #include "sb_ptx.cuh"
 
@@ -302,6 +306,35 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled costs 1-2 us of host time per operand; engines issue the same few hundred (pointer, shape, box)
+// combinations every forward / step, so encoded maps are memoised (key = every argument of the encode call).
+static CUresult encode_tiled_cached(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
+                                    const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr,
+                                    CUtensorMapSwizzle swz) {
+  struct Key { uint64_t v[18]; };
+  Key k{};
+  k.v[0] = reinterpret_cast<uint64_t>(base);
+  k.v[1] = (static_cast<uint64_t>(dt) << 40) | (static_cast<uint64_t>(rank) << 32) | static_cast<uint64_t>(swz);
+  for (int i = 0; i < rank; ++i) { k.v[2 + i] = dims[i]; k.v[10 + i] = (static_cast<uint64_t>(box[i]) << 32) | estr[i]; }
+  for (int i = 0; i + 1 < rank; ++i) k.v[6 + i] = strides[i];
+  const std::string key(reinterpret_cast<const char*>(&k), sizeof(k));
+  static std::mutex mu;
+  static std::unordered_map<std::string, CUtensorMap> cache;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *map = it->second; return CUDA_SUCCESS; }
+  }
+  CUresult r = get_encode_fn()(map, dt, rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 16384) cache.clear();
+    cache.emplace(key, *map);
+  }
+  return r;
+}
+
 // 2-D K-major operand map: global [rows, K] with row stride ld (elements); box = 64 x box_rows; 128B swizzle.
 int make_tma_2d(CUtensorMap* map, int dtype, const void* base, int rows, int K, int ld, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
@@ -317,9 +350,8 @@ int make_tma_2d(CUtensorMap* map, int dtype, const void* base, int rows, int K, 
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
   cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
-                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = encode_tiled_cached(map, dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base,
+                                   dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: %d (rows=%d K=%d ld=%d box_rows=%d)", (int)r, rows, K, ld, box_rows);
     return -3;
@@ -339,10 +371,10 @@ int make_tma_2d_sw(CUtensorMap* map, int dtype, const void* base, int rows, int 
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_k), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
-                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = encode_tiled_cached(map, dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base,
+                                   dims, strides, box, estr,
+                                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                        : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE));
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(2d) failed: %d", (int)r); return -3; }
   return 0;
 }
@@ -361,10 +393,10 @@ int make_tma_nhwc(CUtensorMap* map, int dtype, const void* base, int N, int H, i
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-  CUresult r = fn(map, dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
-                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = encode_tiled_cached(map, dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base,
+                                   dims, strides, box, estr,
+                                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                        : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE));
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(nhwc) failed: %d (N=%d H=%d W=%d C=%d box=%d,%d,%d stride=%d)", (int)r, N, H, W, C,
               box_c, box_w, box_h, stride);

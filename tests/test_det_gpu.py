@@ -26,7 +26,7 @@ def _report(name, payload):
 @pytest.mark.parametrize("cin,cout,stride,hw,act,res", [
     (32, 32, 1, (64, 48), "hardswish", False), (32, 512, 2, (64, 64), "hardswish", False), (64, 256, 1, (40, 56), "hardswish", False),
     (64, 1024, 2, (32, 64), "none", False), (128, 512, 1, (24, 40), "hardswish", False), (32, 32, 1, (72, 80), "none", True),
-    (64, 96, 1, (17, 23), "relu", True),
+    (64, 96, 1, (17, 23), "relu", True), (32, 32, 1, (21, 37), "hardswish", True), (32, 32, 1, (200, 176), "hardswish", False),
 ])
 def test_conv3x3_igemm(built_lib, cin, cout, stride, hw, act, res):
     from surya_b200 import ops

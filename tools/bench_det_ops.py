@@ -45,6 +45,16 @@ def main():
         b = torch.randn(C, device="cuda") * 0.1
         us = timeit(lambda i: ops.dwconv_nhwc(xs[i % 2], w, b, 3, 2, 1, "hardswish"), reps=5)
         rec(name, us, int(xs[0].numel() * 2 * 1.25))
+    for name, H, cin, cout, stride, res in (("conv3x3 32->32 s1 stem block (512x512)", 512, 32, 32, 1, True),
+                                          ("conv3x3 32->512 s2 stage 0 (512->256)", 512, 32, 512, 2, False),
+                                          ("conv3x3 64->256 s1 stage 0 (256x256)", 256, 64, 256, 1, False)):
+        xs = [torch.randn(B, H, H, cin, device="cuda").to(DT) for _ in range(2)]
+        w = (torch.randn(cout, 9 * cin, device="cuda") * (9 * cin) ** -0.5).to(DT)
+        b = torch.randn(cout, device="cuda") * 0.1
+        Ho = H // stride
+        r = torch.randn(B, Ho, Ho, cout, device="cuda").to(DT) if res else None
+        us = timeit(lambda i: ops.conv2d_nhwc(xs[i % 2], w, b, r, 3, stride, 1, "none" if res else "hardswish"), reps=5)
+        rec(name, us, (xs[0].numel() + B * Ho * Ho * cout * (2 if res else 1)) * 2)
     heads, dim, HW = 16, 32, 1024
     qa = [torch.randn(B * HW, 3 * heads * dim, device="cuda").to(DT) for _ in range(3)]
     qb = [torch.randn(B * HW, 3 * heads * dim, device="cuda").to(DT) for _ in range(3)]
