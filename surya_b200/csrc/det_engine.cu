@@ -148,6 +148,21 @@ int sb_det_forward(sb_det_engine* e, const void* pixel_values, int in_f32, int B
         const void* srcs[4]; int hs[4], ws[4];
         for (int j = 0; j < op.n_src; ++j) { srcs[j] = e->bufs[op.src[j]]; hs[j] = e->dims[op.src[j]].H; ws[j] = e->dims[op.src[j]].W; }
         od = {hs[0], ws[0], op.cout};
+        // decode head: UPCAT -> 1x1 fuse conv (ReLU) -> classifier collapse into one kernel when the shapes are the default head's
+        if (i + 2 < e->ops.size()) {
+          const sb_det_op& fz = e->ops[i + 1];
+          const sb_det_op& cl = e->ops[i + 2];
+          if (fz.op == SB_DOP_PW && fz.src[0] == op.dst && fz.act == ACT_RELU && fz.res < 0 && fz.b >= 0 && cl.op == SB_DOP_CLS &&
+              cl.src[0] == fz.dst && fz.cin == op.cout &&
+              det_head_fused_ok(op.n_src, op.cin, cl.cout, fz.cin, fz.cout, hs, ws, od.H, od.W)) {
+            CK(det_head_fused(dt, srcs, hs, ws, op.src_off, op.n_src, op.cin, e->w[fz.w], static_cast<const float*>(e->w[fz.b]),
+                              e->w[cl.w], e->w[cl.b], logits, B, od.H, od.W, st));
+            e->dims[op.dst] = od;
+            e->dims[fz.dst] = {od.H, od.W, fz.cout};
+            i += 2;
+            continue;
+          }
+        }
         if (!fits(op.dst, od.H, od.W, od.C)) { set_error("det: buffer %d too small", op.dst); return -4; }
         CK(det_upsample_cat(dt, srcs, hs, ws, op.src_off, op.n_src, op.cin, e->bufs[op.dst], B, od.H, od.W, st));
         break;

@@ -71,6 +71,12 @@ struct ConvArgs {
 };
 int conv_igemm(const ConvArgs& a, cudaStream_t st);
 
+// Fused decode head (det_head.cu): upsample + concat + fuse conv + ReLU + classifier + sigmoid in one tcgen05 kernel.
+bool det_head_fused_ok(int n_src, int CS, int n_out, int cin, int cout, const int* hs, const int* ws, int HO, int WO);
+int det_head_fused(int dtype, const void* const* srcs, const int* hs, const int* ws, const int* ch_off, int n_src, int CS,
+                   const void* fuse_w, const float* fuse_bias, const void* cls_w, const void* cls_b, void* logits, int B, int HO,
+                   int WO, cudaStream_t st);
+
 // Detection-path CUDA-core kernels (det_ops.cu).
 int det_stem_conv(int dtype, const void* in, int in_f32, const float* w, const float* bias, void* out, int B, int H,
                   int W, int cout, cudaStream_t st);

@@ -336,3 +336,43 @@ def test_ocr_pipeline_end_to_end_tiny(built_lib):
     _report("ocr_pipeline_tiny", {"pages": 5, "lines": n_lines, "timings_s": {k: round(v, 4) for k, v in timings.items()}})
     rec.close()
     det.close()
+
+
+def _head_logits(size, B, seed):
+    from surya_b200.config import det_default
+    from surya_b200.detection import DetEngine
+    from surya_b200.synth import det_normalize, det_state_dict, det_synthetic_pages
+
+    cfg = det_default()
+    eng = DetEngine(cfg, det_state_dict(cfg, seed=0), torch.float16, max_batch=B, max_hw=size)
+    x = det_normalize(det_synthetic_pages(B, max(size), seed=seed, text_like=True)[:, : size[0], : size[1]])
+    out = eng.forward(x.cuda()).float().cpu()
+    eng.close()
+    return out
+
+
+@pytest.mark.parametrize("size", [(512, 512), (320, 448)])
+def test_fused_decode_head_equals_unfused_ops(built_lib, size, tmp_path):
+    """det_head.cu (upsample + concat + fuse conv + ReLU + classifier + sigmoid in one tcgen05 kernel) against the op sequence
+    upsample_cat -> gemm -> classifier it replaces ($SB_DET_FUSED_HEAD=0, read once per process, hence the subprocess).  Same
+    rounding points; only the fp32 summation order of the 512-long classifier dot differs, so heatmaps agree to an fp16 ulp.
+    320x448 gives an 80x112 head: partial tiles in both directions."""
+    import os
+    import subprocess
+    import sys
+
+    if os.environ.get("SB_DET_FUSED_HEAD") == "0":
+        pytest.skip("inside the unfused run")
+    fused = _head_logits(size, 2, 5)
+    path = tmp_path / "unfused.pt"
+    code = (f"import sys, torch; sys.path.insert(0, {str(ROOT)!r}); sys.path.insert(0, {str(ROOT / 'tests')!r});"
+            f"import test_det_gpu as t; torch.save(t._head_logits({size!r}, 2, 5), {str(path)!r})")
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SB_DET_FUSED_HEAD="0"), capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    unfused = torch.load(path)
+    assert fused.shape == unfused.shape == (2, 2, size[0] // 4, size[1] // 4)
+    diff = (fused - unfused).abs()
+    frac_equal = (diff == 0).float().mean().item()
+    print(f"fused head vs unfused ops {size}: max |diff| {diff.max().item():.3g}, identical {100 * frac_equal:.2f} %")
+    assert diff.max().item() <= 2 ** -10 and frac_equal > 0.98
