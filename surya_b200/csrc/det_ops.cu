@@ -9,6 +9,7 @@
 //                  channel concat in reversed order (:703-716)
 //   classifier     1x1 conv 512->2 + bias + sigmoid, NCHW output (:720, :747)
 //   upsample_nchw  DetectionPredictor's x4 bilinear upsample to fp32 (surya/detection/__init__.py:120-132)
+#include "gemm_epilogue.cuh"
 #include "ops.cuh"
 #include "sb_ptx.cuh"
 
@@ -16,7 +17,10 @@
 
 namespace sb {
 
-__device__ __forceinline__ float hardswish_f(float x) { return x * fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) / 6.0f; }
+// x * min(max(x + 3, 0), 6) * (1/6) in fp32: the expression of ATen's CUDA kernel (ActivationHardswishKernel.cu) and of the GEMM
+// epilogue (act_ct<ACT_HARDSWISH>).  Round 1 divided by 6 here (ATen's CPU form): a true fp32 division is ~8 instructions plus a
+// slow-path call per value, which made the epilogue of the depthwise kernel twice as long as its convolution.
+__device__ __forceinline__ float hardswish_f(float x) { return x * fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f); }
 
 // ------------------------------------------------------------------------------------------------ stem conv
 // in: NCHW [B,3,H,W] (T or float); w: fp32 [32][r][s][c] (27 per output channel, BN folded); out NHWC [B,H/2,W/2,CO].
@@ -173,15 +177,14 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const T* __restrict__ in
       for (int y = 0; y < TY; ++y) {
         const int oy = oy0 + y;
         if (oy >= Ho) break;
-        uint4 pack;
-        T* pe = reinterpret_cast<T*>(&pack);
+        uint32_t pk[4];                              // pairwise conversions: one F2FP per two values and rounding point
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float v = rnd<T>(acc[y][j] + bv[j]);
-          if (act == ACT_HARDSWISH) v = hardswish_f(v);
-          pe[j] = from_f<T>(v);
+        for (int j = 0; j < 8; j += 2) {
+          uint32_t t = Pk<T>::pack(acc[y][j] + bv[j], acc[y][j + 1] + bv[j + 1]);
+          if (act == ACT_HARDSWISH) t = Pk<T>::pack(hardswish_f(Pk<T>::lo(t)), hardswish_f(Pk<T>::hi(t)));
+          pk[j >> 1] = t;
         }
-        *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * C + c8) = pack;
+        *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * C + c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
     }
   }
@@ -224,6 +227,12 @@ int det_dwconv(int dtype, const void* in, const void* w, const float* bias, void
 // qkv_a / qkv_b: token-major [B*HW, 3*heads*DIM] (plain qkv and aggregated qkv); head h of scale s reads channels
 // [h*3*DIM, (h+1)*3*DIM) = (q | k | v).  out: [B*HW, 2*heads*DIM], channel = (s*heads + h)*DIM + d.
 // One CTA per (image, scale*heads + h).  fp32 throughout; rounded to T once at the end (reference: .float() ... .to(dtype)).
+// Round 2 re-tiling (profiles/r02_det_kernels_ncu.md: the first version was shared-memory bound, L1/TEX 88 %, 2.5 FMA per LDS in
+// phase 1 and one broadcast LDS.128 per 4 FMA in phase 2):
+//   phase 1  kv[i][j] = sum_t relu(k[t][i]) * [v[t] | 1][j]: thread = (2 rows i, 8 columns j, one quarter of each token tile):
+//            3 shared loads per 18 FMA; the four token-quarters meet in shared memory in a fixed order;
+//   phase 2  out[t] = relu(q[t]) kv: thread = (4 tokens, 8 columns): 2 LDS.128 + 1 LDS.32 per 36 FMA; every thread also carries
+//            the denominator column of its tokens, and multiplies by 1 / (den + eps) (one division per token instead of 32).
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256, 2) lite_mla_kernel(const T* __restrict__ qkv_a, const T* __restrict__ qkv_b,
                                                        T* __restrict__ out, int HW, int heads, float eps) {
@@ -233,74 +242,113 @@ __global__ void __launch_bounds__(256, 2) lite_mla_kernel(const T* __restrict__ 
   __shared__ __align__(16) float kv[DIM * DVP];
   __shared__ __align__(16) float tk[TT][DIM];
   __shared__ __align__(16) float tv[TT][DIM];
+  __shared__ __align__(16) float part[4][DIM * DVP];
   const int b = blockIdx.x, hh = blockIdx.y;
   const int scale = hh / heads, h = hh % heads;
   const int ld = 3 * heads * DIM;
   const T* src = (scale == 0 ? qkv_a : qkv_b) + static_cast<size_t>(b) * HW * ld + h * 3 * DIM;
   const int tid = threadIdx.x;
-  // ---- phase 1: kv[i][j] = sum_t relu(k[t][i]) * [v[t] | 1][j]; thread = (i, 4 consecutive j); j-group 0 also owns the ones column
-  const int ki = tid >> 3, vj = (tid & 7) * 4;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a1s = 0.f;
+  // ---- phase 1
+  const int tq = tid >> 6, ip = (tid & 63) >> 2, jq = tid & 3;
+  float acc0[8], acc1[8], ones0 = 0.f, ones1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
   for (int t0 = 0; t0 < HW; t0 += TT) {
     __syncthreads();
 #pragma unroll
     for (int rep = 0; rep < (TT * 8) / 256; ++rep) {
       const int i = tid + rep * 256;
-      const int t = i >> 3, part = i & 7;        // parts 0..3 = k, 4..7 = v (k | v are 128 contiguous bytes per token)
+      const int t = i >> 3, pt = i & 7;          // parts 0..3 = k, 4..7 = v (k | v are 128 contiguous bytes per token)
       uint4 u = make_uint4(0u, 0u, 0u, 0u);
-      if (t0 + t < HW) u = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(t0 + t) * ld + DIM + part * 8);
+      if (t0 + t < HW) u = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(t0 + t) * ld + DIM + pt * 8);
       const T* e = reinterpret_cast<const T*>(&u);
       float f[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = to_f<T>(e[j]);
-      if (part < 4) {
+      if (pt < 4) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
       }
-      float* dstp = part < 4 ? &tk[t][part * 8] : &tv[t][(part - 4) * 8];
+      float* dstp = pt < 4 ? &tk[t][pt * 8] : &tv[t][(pt - 4) * 8];
       *reinterpret_cast<float4*>(dstp) = make_float4(f[0], f[1], f[2], f[3]);
       *reinterpret_cast<float4*>(dstp + 4) = make_float4(f[4], f[5], f[6], f[7]);
     }
     __syncthreads();
-#pragma unroll 8
-    for (int t = 0; t < TT; ++t) {               // rows past HW were staged as zeros
-      const float kx = tk[t][ki];
-      const float4 v4 = *reinterpret_cast<const float4*>(&tv[t][vj]);
-      a0 += kx * v4.x; a1 += kx * v4.y; a2 += kx * v4.z; a3 += kx * v4.w;
-      a1s += kx;
+#pragma unroll 4
+    for (int tt = 0; tt < TT / 4; ++tt) {        // rows past HW were staged as zeros
+      const int t = tq * (TT / 4) + tt;
+      const float2 kx = *reinterpret_cast<const float2*>(&tk[t][2 * ip]);
+      const float4 va = *reinterpret_cast<const float4*>(&tv[t][8 * jq]);
+      const float4 vb = *reinterpret_cast<const float4*>(&tv[t][8 * jq + 4]);
+      const float vv[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc0[j] += kx.x * vv[j]; acc1[j] += kx.y * vv[j]; }
+      ones0 += kx.x;
+      ones1 += kx.y;
     }
   }
-  *reinterpret_cast<float4*>(&kv[ki * DVP + vj]) = make_float4(a0, a1, a2, a3);
-  if ((tid & 7) == 0) { kv[ki * DVP + DIM] = a1s; kv[ki * DVP + DIM + 1] = 0.f; kv[ki * DVP + DIM + 2] = 0.f; kv[ki * DVP + DIM + 3] = 0.f; }
+  {
+    float* p0 = &part[tq][(2 * ip) * DVP + 8 * jq];
+    float* p1 = p0 + DVP;
+    *reinterpret_cast<float4*>(p0) = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
+    *reinterpret_cast<float4*>(p0 + 4) = make_float4(acc0[4], acc0[5], acc0[6], acc0[7]);
+    *reinterpret_cast<float4*>(p1) = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+    *reinterpret_cast<float4*>(p1 + 4) = make_float4(acc1[4], acc1[5], acc1[6], acc1[7]);
+    if (jq == 0) {
+      float* o0 = &part[tq][(2 * ip) * DVP + DIM];
+      *reinterpret_cast<float4*>(o0) = make_float4(ones0, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(o0 + DVP) = make_float4(ones1, 0.f, 0.f, 0.f);
+    }
+  }
   __syncthreads();
-  // ---- phase 2: out[t] = relu(q[t]) kv; out[:-1] / (out[-1] + eps); one token per thread, kv rows broadcast from smem
+  for (int e = tid; e < DIM * DVP; e += 256) kv[e] = ((part[0][e] + part[1][e]) + part[2][e]) + part[3][e];
+  __syncthreads();
+  // ---- phase 2
   T* dst = out + static_cast<size_t>(b) * HW * (2 * heads * DIM) + (scale * heads + h) * DIM;
   const int ldo = 2 * heads * DIM;
-  for (int t = tid; t < HW; t += 256) {
-    uint4 qa[DIM / 8];
+  const int js = tid & 3;
+  for (int g = tid >> 2; g * 4 < HW; g += 64) {
+    const int t0 = g * 4;
+    float oa[4][8], den[4];
 #pragma unroll
-    for (int d = 0; d < DIM / 8; ++d) qa[d] = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(t) * ld + d * 8);
-    float oa[DVP];
+    for (int k = 0; k < 4; ++k) {
+      den[k] = 0.f;
 #pragma unroll
-    for (int j = 0; j < DVP; ++j) oa[j] = 0.f;
-#pragma unroll
-    for (int i = 0; i < DIM; ++i) {
-      const float x = fmaxf(to_f<T>(reinterpret_cast<const T*>(&qa[i >> 3])[i & 7]), 0.f);
-#pragma unroll
-      for (int j4 = 0; j4 < DVP / 4; ++j4) {
-        const float4 k4 = *reinterpret_cast<const float4*>(&kv[i * DVP + j4 * 4]);
-        oa[j4 * 4 + 0] += x * k4.x; oa[j4 * 4 + 1] += x * k4.y; oa[j4 * 4 + 2] += x * k4.z; oa[j4 * 4 + 3] += x * k4.w;
-      }
-      if (i & 1) asm volatile("" ::: "memory");   // keep ptxas from hoisting all 288 kv loads (register blow-up)
+      for (int j = 0; j < 8; ++j) oa[k][j] = 0.f;
     }
-    const float da = oa[DIM] + eps;
+#pragma unroll 1
+    for (int c = 0; c < DIM / 8; ++c) {
+      uint4 qv[4];
 #pragma unroll
-    for (int d = 0; d < DIM; d += 8) {
+      for (int k = 0; k < 4; ++k) {
+        const int t = min(t0 + k, HW - 1);
+        qv[k] = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(t) * ld + c * 8);
+      }
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) {
+        const int i = c * 8 + ii;
+        const float4 ka = *reinterpret_cast<const float4*>(&kv[i * DVP + 8 * js]);
+        const float4 kb = *reinterpret_cast<const float4*>(&kv[i * DVP + 8 * js + 4]);
+        const float kd = kv[i * DVP + DIM];
+        const float kk[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float x = fmaxf(to_f<T>(reinterpret_cast<const T*>(&qv[k])[ii]), 0.f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) oa[k][j] += x * kk[j];
+          den[k] += x * kd;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (t0 + k >= HW) break;
+      const float r = 1.0f / (den[k] + eps);
       uint4 pa;
       T* ea = reinterpret_cast<T*>(&pa);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ea[j] = from_f<T>(oa[d + j] / da);
-      *reinterpret_cast<uint4*>(dst + static_cast<size_t>(t) * ldo + d) = pa;
+      for (int j = 0; j < 8; ++j) ea[j] = from_f<T>(oa[k][j] * r);
+      *reinterpret_cast<uint4*>(dst + static_cast<size_t>(t0 + k) * ldo + 8 * js) = pa;
     }
   }
 }

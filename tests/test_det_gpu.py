@@ -70,12 +70,13 @@ def test_dwconv(built_lib, ks, stride, C, hw):
     assert (out.float() - ref).abs().max().item() < 4e-3
 
 
-def test_grouped_pw_and_lite_mla(built_lib):
+@pytest.mark.parametrize("HW", [300, 301, 1024, 67])
+def test_grouped_pw_and_lite_mla(built_lib, HW):
     from surya_b200 import ops
 
     dtype = torch.float16
     g = torch.Generator(device="cuda").manual_seed(0)
-    B, HW, heads, dim = 2, 300, 16, 32
+    B, heads, dim = 2, 16, 32
     C = 3 * heads * dim
     a = torch.randn(B * HW, C, device="cuda", generator=g).to(dtype)
     w = (torch.randn(C, 32, device="cuda", generator=g) * 32 ** -0.5).to(dtype)
