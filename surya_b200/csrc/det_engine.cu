@@ -101,6 +101,19 @@ int sb_det_forward(sb_det_engine* e, const void* pixel_values, int in_f32, int B
       case SB_DOP_CONV: {
         od = {(in.H + 2 * op.pad - op.k) / op.stride + 1, (in.W + 2 * op.pad - op.k) / op.stride + 1, op.cout};
         if (!fits(op.dst, od.H, od.W, od.C)) { set_error("det: buffer %d too small", op.dst); return -4; }
+        // FusedMBConv: 3x3 expand (Hardswish) directly followed by its 1x1 project -> one back-to-back GEMM kernel
+        if (i + 1 < e->ops.size() && op.res < 0 && op.b >= 0) {
+          const sb_det_op& pj = e->ops[i + 1];
+          if (pj.op == SB_DOP_PW && pj.src[0] == op.dst && pj.cin == op.cout && pj.b >= 0 &&
+              fmb_fused_ok(op.cin, op.cout, pj.cout, op.k, op.stride, op.pad, op.act, pj.act) && fits(pj.dst, od.H, od.W, pj.cout)) {
+            CK(fmb_fused(dt, in_ptr, e->w[op.w], static_cast<const float*>(e->w[op.b]), e->w[pj.w], static_cast<const float*>(e->w[pj.b]),
+                         pj.res >= 0 ? e->bufs[pj.res] : nullptr, e->bufs[pj.dst], B, in.H, in.W, op.cin, op.cout, pj.cout, op.stride, st));
+            e->dims[op.dst] = od;
+            e->dims[pj.dst] = {od.H, od.W, pj.cout};
+            ++i;
+            continue;
+          }
+        }
         ConvArgs a;
         a.dtype = dt; a.in = in_ptr; a.weight = e->w[op.w]; a.bias = op.b >= 0 ? static_cast<const float*>(e->w[op.b]) : nullptr;
         a.residual = res; a.out = e->bufs[op.dst]; a.n_img = B; a.H = in.H; a.W = in.W; a.Cin = op.cin; a.Cout = op.cout;

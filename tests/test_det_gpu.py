@@ -353,27 +353,29 @@ def _head_logits(size, B, seed):
 
 
 @pytest.mark.parametrize("size", [(512, 512), (320, 448)])
-def test_fused_decode_head_equals_unfused_ops(built_lib, size, tmp_path):
-    """det_head.cu (upsample + concat + fuse conv + ReLU + classifier + sigmoid in one tcgen05 kernel) against the op sequence
-    upsample_cat -> gemm -> classifier it replaces ($SB_DET_FUSED_HEAD=0, read once per process, hence the subprocess).  Same
-    rounding points; only the fp32 summation order of the 512-long classifier dot differs, so heatmaps agree to an fp16 ulp.
-    320x448 gives an 80x112 head: partial tiles in both directions."""
+@pytest.mark.parametrize("switch", ["SB_DET_FUSED_HEAD", "SB_FMB_FUSED"])
+def test_fused_kernels_equal_unfused_ops(built_lib, switch, size, tmp_path):
+    """The fused tcgen05 kernels against the op sequences they replace (switch = 1 / 0, read once per process, hence the subprocesses):
+      SB_DET_FUSED_HEAD  det_head.cu (upsample + concat + fuse conv + ReLU + classifier + sigmoid) vs upsample_cat -> gemm ->
+                         classifier: same rounding points, only the fp32 summation order of the 512-long classifier dot differs;
+      SB_FMB_FUSED       conv_fmb.cu (3x3 expand + Hardswish + 1x1 project + shortcut, back-to-back GEMM) vs conv_igemm -> gemm:
+                         same rounding points and the same k order.
+    Heatmaps must agree to one fp16 ulp.  320x448 gives partial tiles in both directions at every stage."""
     import os
     import subprocess
     import sys
 
-    if os.environ.get("SB_DET_FUSED_HEAD") == "0":
-        pytest.skip("inside the unfused run")
-    fused = _head_logits(size, 2, 5)
-    path = tmp_path / "unfused.pt"
-    code = (f"import sys, torch; sys.path.insert(0, {str(ROOT)!r}); sys.path.insert(0, {str(ROOT / 'tests')!r});"
-            f"import test_det_gpu as t; torch.save(t._head_logits({size!r}, 2, 5), {str(path)!r})")
-    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SB_DET_FUSED_HEAD="0"), capture_output=True, text=True,
-                       timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    unfused = torch.load(path)
+    outs = {}
+    for val in ("1", "0"):
+        path = tmp_path / f"variant{val}.pt"
+        code = (f"import sys, torch; sys.path.insert(0, {str(ROOT)!r}); sys.path.insert(0, {str(ROOT / 'tests')!r});"
+                f"import test_det_gpu as t; torch.save(t._head_logits({size!r}, 2, 5), {str(path)!r})")
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **{switch: val}), capture_output=True, text=True, timeout=240)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[val] = torch.load(path)
+    fused, unfused = outs["1"], outs["0"]
     assert fused.shape == unfused.shape == (2, 2, size[0] // 4, size[1] // 4)
     diff = (fused - unfused).abs()
     frac_equal = (diff == 0).float().mean().item()
-    print(f"fused head vs unfused ops {size}: max |diff| {diff.max().item():.3g}, identical {100 * frac_equal:.2f} %")
+    print(f"{switch}=1 vs 0 at {size}: max |diff| {diff.max().item():.3g}, identical {100 * frac_equal:.2f} %")
     assert diff.max().item() <= 2 ** -10 and frac_equal > 0.98
