@@ -44,10 +44,6 @@ struct HeadParams {
   void* out;                        // T NCHW [B, 2, HO*WO]
 };
 
-__device__ __forceinline__ float head_bilerp(float hy, float ly, float hx, float lx, float a, float b, float c, float d) {
-  // same expression as upsample_cat_kernel (det_ops.cu): hy * (hx * a + lx * b) + ly * (hx * c + lx * d), default contraction
-  return hy * (hx * a + lx * b) + ly * (hx * c + lx * d);
-}
 
 template <typename T>
 __global__ void __launch_bounds__(512, 1)
@@ -171,27 +167,49 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tma_id, const __grid_const
         const float ry = static_cast<float>(hs) / hp.HO, rx = static_cast<float>(ws) / hp.WO;
         mbar_wait(&aempty_bar[kb], aph ^ 1);
         uint8_t* dst = s_a + kb * A_BYTES;
-#pragma unroll 2
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 16 + rsub;                     // tile row = pixel (r / 16, r % 16)
-          const int oy = min(oy0 + (r >> 4), hp.HO - 1), ox = min(ox0 + (r & 15), hp.WO - 1);
-          // torch upsample_bilinear2d, align_corners=False: src = (dst + 0.5) * (in/out) - 0.5, clamped at 0
-          const float sy = fmaxf((oy + 0.5f) * ry - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * rx - 0.5f, 0.f);
-          const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
-          const int y1 = y0 + (y0 < hs - 1 ? 1 : 0), x1 = x0 + (x0 < ws - 1 ? 1 : 0);
-          const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
-          const uint4 v00 = __ldg(reinterpret_cast<const uint4*>(base + (y0 * ws + x0) * hp.CS));
-          const uint4 v01 = __ldg(reinterpret_cast<const uint4*>(base + (y0 * ws + x1) * hp.CS));
-          const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(base + (y1 * ws + x0) * hp.CS));
-          const uint4 v11 = __ldg(reinterpret_cast<const uint4*>(base + (y1 * ws + x1) * hp.CS));
-          const T *e00 = reinterpret_cast<const T*>(&v00), *e01 = reinterpret_cast<const T*>(&v01);
-          const T *e10 = reinterpret_cast<const T*>(&v10), *e11 = reinterpret_cast<const T*>(&v11);
-          uint4 pack;
-          T* pe = reinterpret_cast<T*>(&pack);
+        // two batches of four pixel rows: 16 independent 16-byte loads in flight per thread before the first blend.  The x / y
+        // weights of an integer up-sampling ratio (2, 4, 8) are multiples of 1/16, exact in the 16-bit storage type, so the blend
+        // runs on FHFMA without converting the loaded values: p = lx*b + hx*a, q = lx*d + hx*c (both exact products + one
+        // rounding each, identical to the fp32 expression), then hy*p + ly*q in fp32.
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint4 v00[4], v01[4], v10[4], v11[4];
+          float lyv[4], lxv[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            pe[j] = from_f<T>(head_bilerp(hy, ly, hx, lx, to_f<T>(e00[j]), to_f<T>(e01[j]), to_f<T>(e10[j]), to_f<T>(e11[j])));
-          *reinterpret_cast<uint4*>(dst + r * 128 + ((c ^ (r & 7)) << 4)) = pack;
+          for (int u = 0; u < 4; ++u) {
+            const int r = (half * 4 + u) * 16 + rsub;           // tile row = pixel (r / 16, r % 16)
+            const int oy = min(oy0 + (r >> 4), hp.HO - 1), ox = min(ox0 + (r & 15), hp.WO - 1);
+            // torch upsample_bilinear2d, align_corners=False: src = (dst + 0.5) * (in/out) - 0.5, clamped at 0
+            const float sy = fmaxf((oy + 0.5f) * ry - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * rx - 0.5f, 0.f);
+            const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+            const int y1 = y0 + (y0 < hs - 1 ? 1 : 0), x1 = x0 + (x0 < ws - 1 ? 1 : 0);
+            lyv[u] = sy - y0; lxv[u] = sx - x0;
+            v00[u] = __ldg(reinterpret_cast<const uint4*>(base + (y0 * ws + x0) * hp.CS));
+            v01[u] = __ldg(reinterpret_cast<const uint4*>(base + (y0 * ws + x1) * hp.CS));
+            v10[u] = __ldg(reinterpret_cast<const uint4*>(base + (y1 * ws + x0) * hp.CS));
+            v11[u] = __ldg(reinterpret_cast<const uint4*>(base + (y1 * ws + x1) * hp.CS));
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = (half * 4 + u) * 16 + rsub;
+            const float ly = lyv[u], lx = lxv[u], hy = 1.f - ly, hx = 1.f - lx;
+            const unsigned short lxh = bits_of<T>(from_f<T>(lx)), hxh = bits_of<T>(from_f<T>(hx));
+            const unsigned short *e00 = reinterpret_cast<const unsigned short*>(&v00[u]), *e01 = reinterpret_cast<const unsigned short*>(&v01[u]);
+            const unsigned short *e10 = reinterpret_cast<const unsigned short*>(&v10[u]), *e11 = reinterpret_cast<const unsigned short*>(&v11[u]);
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              float o2[2];
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {
+                const float p_ = fma16<T>(lxh, e01[j + jj], fma16<T>(hxh, e00[j + jj], 0.f));
+                const float q_ = fma16<T>(lxh, e11[j + jj], fma16<T>(hxh, e10[j + jj], 0.f));
+                o2[jj] = __fmaf_rn(ly, q_, __fmul_rn(hy, p_));
+              }
+              pk[j >> 1] = Pk<T>::pack(o2[0], o2[1]);
+            }
+            *reinterpret_cast<uint4*>(dst + r * 128 + ((c ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -269,7 +287,13 @@ bool det_head_fused_ok(int n_src, int CS, int n_out, int cin, int cout, const in
   if (en < 0) { const char* e = getenv("SB_DET_FUSED_HEAD"); en = (e && e[0] == '0') ? 0 : 1; }
   if (!en || n_src != 4 || CS != 128 || n_out != 2 || cin != 512 || cout != 512) return false;
   int ident = 0;
-  for (int i = 0; i < n_src; ++i) ident += (hs[i] == HO && ws[i] == WO);
+  for (int i = 0; i < n_src; ++i) {
+    if (hs[i] == HO && ws[i] == WO) { ++ident; continue; }
+    // integer up-sampling ratios up to 8: the bilinear weights are then multiples of 1/16 (exact in fp16 / bf16, see the builders)
+    if (hs[i] <= 0 || ws[i] <= 0 || HO % hs[i] || WO % ws[i]) return false;
+    const int fy = HO / hs[i], fx = WO / ws[i];
+    if ((fy != 2 && fy != 4 && fy != 8) || (fx != 2 && fx != 4 && fx != 8)) return false;
+  }
   return ident == 1;
 }
 

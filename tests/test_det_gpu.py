@@ -366,14 +366,15 @@ def test_fused_kernels_equal_unfused_ops(built_lib, switch, size, tmp_path):
     import sys
 
     outs = {}
-    for val in ("1", "0"):
+    on = "2" if switch == "SB_FMB_FUSED" else "1"      # 2 = also the Cin = 32 instance, which is off by default (not faster)
+    for val in (on, "0"):
         path = tmp_path / f"variant{val}.pt"
         code = (f"import sys, torch; sys.path.insert(0, {str(ROOT)!r}); sys.path.insert(0, {str(ROOT / 'tests')!r});"
                 f"import test_det_gpu as t; torch.save(t._head_logits({size!r}, 2, 5), {str(path)!r})")
         r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **{switch: val}), capture_output=True, text=True, timeout=240)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         outs[val] = torch.load(path)
-    fused, unfused = outs["1"], outs["0"]
+    fused, unfused = outs[on], outs["0"]
     assert fused.shape == unfused.shape == (2, 2, size[0] // 4, size[1] // 4)
     diff = (fused - unfused).abs()
     frac_equal = (diff == 0).float().mean().item()
