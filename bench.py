@@ -338,7 +338,9 @@ def detection_bench(dev, peaks, world, steps, warmup):
     B, S = 32, 1024
     cfg = det_default()
     eng = DetEngine(cfg, det_state_dict(cfg, 0), torch.float16, device=dev, max_batch=B, max_hw=(S, S))
-    x_host = det_normalize(det_synthetic_pages(B, S, seed=1234)).half().pin_memory()
+    pages_u8 = det_synthetic_pages(B, S, seed=1234)                       # uint8 [B, S, S, 3]: what the reference's processor receives
+    u8_host = (pages_u8 if torch.is_tensor(pages_u8) else torch.from_numpy(pages_u8)).contiguous().pin_memory()
+    x_host = det_normalize(pages_u8).half().pin_memory()
     x = x_host.to(dev)
     out_host = torch.empty((B, 2, S, S), dtype=torch.float32).pin_memory()
 
@@ -367,7 +369,7 @@ def detection_bench(dev, peaks, world, steps, warmup):
         torch.cuda.synchronize()
 
     def e2e_front():      # post-processing front half on the device: 16-bit text map + mask + thresholds come back
-        detect_text_front_host(eng, x_host, chunk=8)
+        detect_text_front_host(eng, u8_host, chunk=16)
         torch.cuda.synchronize()
 
     for _ in range(max(3, warmup)):
@@ -399,10 +401,11 @@ def detection_bench(dev, peaks, world, steps, warmup):
            "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "pages/s", "h2d_bytes_per_step": x_host.numel() * 2,
                    "d2h_bytes_per_step": out_host.numel() * 4,
                    "api": "surya_b200.detection.detect_pages_host (pinned fp16 NCHW pages -> fp32 full-res heatmaps on host; chunks of 8 pipelined over 3 streams)"},
-           "e2e_front": {"value": B * world / (ms_front * 1e-3), "unit": "pages/s", "h2d_bytes_per_step": x_host.numel() * 2,
+           "e2e_front": {"value": B * world / (ms_front * 1e-3), "unit": "pages/s", "h2d_bytes_per_step": u8_host.numel(),
                          "d2h_bytes_per_step": B * S * S * 3 + B * 16,
-                         "api": "surya_b200.detection.detect_text_front_host (pinned fp16 pages -> fp16 text map + uint8 mask + dynamic "
-                                "thresholds per page; upsample / top-10% mean / binarisation on the device)"},
+                         "api": "surya_b200.detection.detect_text_front_host (pinned uint8 pages, normalised on the device -> fp16 text map "
+                                "+ uint8 mask + dynamic thresholds per page; upsample / top-10% mean / binarisation on the device; chunks "
+                                "of 16 pipelined over 3 streams — tools/bench_det_e2e.py: smaller chunks lose more in the forward than the overlap wins)"},
            "config": {"workload": f"detection: {B} synthetic {S}x{S} pages per GPU, EfficientViT-L seg forward (default config)",
                       "dtype": "f16"},
            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",

@@ -106,7 +106,7 @@ class OcrPipeline:
     """detect -> crop -> recognise over the B200 engines.  `run(pages)` takes uint8 pages [N, H, W, 3] (H, W = the detection
     processor size) and returns (lines grouped per page, timing breakdown in seconds)."""
 
-    def __init__(self, det: DetEngine, rec: RecEngine, rec_batch: int = 256, max_tokens: int = 128, det_chunk: int = 8,
+    def __init__(self, det: DetEngine, rec: RecEngine, rec_batch: int = 256, max_tokens: int = 128, det_chunk: int = 16,
                  workers: int = 16, math_mode: bool = True):
         self.det, self.rec = det, rec
         self.runner = RecognitionRunner(rec, batch_size=rec_batch, max_tokens=max_tokens)
