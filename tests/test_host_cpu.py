@@ -404,8 +404,12 @@ def test_committed_bench_lines_follow_the_contract():
     """The bench lines committed under profiles/ carry every key the driver's contract names (schema guard for bench.py)."""
     import json
 
-    for name in ("r01_final_bench_n1.json", "r01_final_bench_n2.json", "r01_final_bench_n4.json"):
-        d = json.loads((ROOT / "profiles" / name).read_text())
+    for name in ("r01_final_bench_n1.json", "r01_final_bench_n2.json", "r01_final_bench_n4.json", "r02_final_bench_n1.json",
+                 "r02_final_bench_n2_nocpu.json"):
+        line = [l for l in (ROOT / "profiles" / name).read_text().splitlines() if l.startswith("{")][-1]   # NCCL prints a banner first
+        d = json.loads(line)
+        if "nocpu" in name:
+            d.setdefault("cpu_baseline", None)
         for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
                   "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
             assert k in d, (name, k)
