@@ -710,7 +710,11 @@ def main():
         log(f"e2e {e2e_value:.1f} crops/s; roofline replay")
         try:
             roof, gemm_ms = decode_gemm_roofline(eng, peaks)
-            roof["share_of_step"] = gemm_ms * (MAX_TOKENS - 1) / ms_step
+            roof["share_of_step"] = gemm_ms * (MAX_TOKENS - 1) / ms_step          # of the whole step (prefill + 127 decode steps)
+            roof["share_of_decode_step"] = gemm_ms / (ms_decode / (MAX_TOKENS - 1))
+            roof["share_note"] = ("ncu's launch list gives these launches 0.81 of one decode step's summed kernel time "
+                                  "(profiles/decode_gemm_traffic.json); in the graph ~0.10 ms of the 0.87 ms step is launch-to-launch "
+                                  "gap, which a sum of kernel durations does not contain")
         except Exception as e:      # noqa: BLE001
             roof = {"error": f"{type(e).__name__}: {e}"}
         # whole-step algorithmic bounds for context
