@@ -49,7 +49,7 @@ fmb_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   constexpr uint32_t TMEM_COLS = 512;                                // acc1: 2 x 128, acc2: COUT at column 256
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // array + offset keeps the shared address space (STS / LDS, not generic ST / LD)
   uint8_t* s_1 = smem;
   uint8_t* s_a2 = s_1 + STAGES * S1_BYTES;
   uint8_t* s_w2 = s_a2 + 2 * A2_BYTES;

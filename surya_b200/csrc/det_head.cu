@@ -55,7 +55,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tma_id, const __grid_const
   constexpr uint32_t TMEM_COLS = 512;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // array + offset keeps the shared address space (STS / LDS, not generic ST / LD)
   uint8_t* s_a = smem;                                  // 8 x 16 KB
   uint8_t* s_w = s_a + HEAD_KB * A_BYTES;               // 2 x 32 KB
   float* s_bias = reinterpret_cast<float*>(s_w + W_STAGES * W_BYTES);      // [512]

@@ -99,7 +99,7 @@ template <typename T>
 __global__ void __launch_bounds__(384, 1) gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   constexpr int BM = 128, BK = 64;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // array + offset keeps the shared address space (STS / LDS, not generic ST / LD)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + CH_STAGES * CH_SLOT_BYTES);
   uint64_t* empty_bar = full_bar + CH_STAGES;
   uint64_t* tfull_bar = empty_bar + CH_STAGES;

@@ -55,7 +55,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   constexpr int N_UNITS = BN / 8;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // array + offset keeps the shared address space (STS / LDS, not generic ST / LD)
   // STAGES (<= 8) is a launch parameter: as many pipeline stages as fit beside the receive buffer — the main loop needs
   // ~150 KB in flight per SM to run at the SM's L2 read-port rate (profiles/r01_gemm_decode_microbench.md)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
