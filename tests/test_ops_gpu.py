@@ -85,6 +85,32 @@ def test_gemm_epilogue(built_lib, dtype, act):
 
 
 @pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("M,N,K,act,res", [(80000, 1024, 256, "hardswish", False), (75011, 512, 128, "gelu", True),
+                                           (76800, 256, 192, "relu", False)])
+def test_gemm_two_ctas_per_sm_config(built_lib, dtype, M, N, K, act, res):
+    """The 128 x 128, 2-stage, two-CTAs-per-SM configuration for short-K GEMMs with an activation (gemm_tcgen05.cu two_cta_ok,
+    opt-in with SB_GEMM_2CTA=1 because it measured slower): bit-identical to a forced 128 x 256 tile (same per-element arithmetic,
+    same k order) and right against the fp32 restatement.  Without the switch this compares the default heuristic with the forced
+    tile, which must be bit-identical too."""
+    from surya_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M % 97 + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.08).to(dtype)
+    bias = torch.randn(N, device="cuda", generator=g).to(dtype).float()
+    r = torch.randn(M, N, device="cuda", generator=g).to(dtype) if res else None
+    out = ops.gemm(a, w, bias=bias, residual=r, act=act)
+    forced = ops.gemm(a, w, bias=bias, residual=r, act=act, force_bn=256)
+    torch.cuda.synchronize()
+    assert torch.equal(out, forced)
+    rows = torch.randint(0, M, (2048,), device="cuda", generator=g)
+    lin = (a[rows].float() @ w.float().t() + bias).to(dtype)
+    y = _act_ref(lin.float(), act).to(dtype)
+    ref = (y.float() + r[rows].float()).to(dtype) if res else y
+    _close(out[rows], ref, dtype, ulps=3.0, what=f"2-CTA gemm {act}", scale=lin.float().abs() if not res else torch.maximum(lin.float().abs(), r[rows].float().abs()))
+
+
+@pytest.mark.parametrize("dtype", DT)
 def test_gemm_swiglu(built_lib, dtype):
     from surya_b200 import ops
 
