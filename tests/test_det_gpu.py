@@ -378,5 +378,5 @@ def test_fused_kernels_equal_unfused_ops(built_lib, switch, size, tmp_path):
     assert fused.shape == unfused.shape == (2, 2, size[0] // 4, size[1] // 4)
     diff = (fused - unfused).abs()
     frac_equal = (diff == 0).float().mean().item()
-    print(f"{switch}=1 vs 0 at {size}: max |diff| {diff.max().item():.3g}, identical {100 * frac_equal:.2f} %")
+    print(f"{switch}={on} vs 0 at {size}: max |diff| {diff.max().item():.3g}, identical {100 * frac_equal:.2f} %")
     assert diff.max().item() <= 2 ** -10 and frac_equal > 0.98
