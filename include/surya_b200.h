@@ -296,6 +296,13 @@ int sb_rmsnorm_adetr(int dtype, const void* x, int ldx, const void* w, void* y, 
                      void* stream);
 /* nn.LayerNorm (donut/encoder.py:117,163,544-548; layout/model/decoder.py:73). */
 int sb_layernorm(int dtype, const void* x, const void* w, const void* b, void* y, int rows, int C, float eps, void* stream);
+/* ocr_error — Embeddings.forward of DistilBertForSequenceClassification (surya/ocr_error/model/encoder.py:60-91):
+ * y[r] = LayerNorm(T(word[ids[r]] + ptab[pos[r]])) for the PACKED real tokens of a right-padded batch; ids / pos are int32 device
+ * arrays of `rows` entries (the host plan drops the pad positions, which the reference computes and then masks, :171-175).  The
+ * rest of the model runs on sb_gemm (q/k/v fused, out_lin + residual, lin1 + GELU, lin2 + residual, pre_classifier + ReLU),
+ * sb_attn_varlen (non-causal, one segment per text), sb_layernorm and sb_small_head (classifier): surya_b200/ocr_error.py. */
+int sb_embed_pos_layernorm(int dtype, const int* ids, const int* pos, const void* word, const void* ptab, const void* w,
+                           const void* b, void* y, int rows, int C, float eps, void* stream);
 /* im2col of the patch-embedding Conv2d(k = stride = P) (donut/encoder.py:228-230): NCHW -> [B*gh*gw, Kp], col = c*P*P+ky*P+kx;
  * gh = ceil(H/P), gw = ceil(W/P), a partial last patch is zero filled (DonutSwinPatchEmbeddings.maybe_pad, :232-239). */
 int sb_patch_gather(int dtype, const void* in, int in_f32, void* out, int B, int Cin, int H, int W, int P, int Kp, void* stream);

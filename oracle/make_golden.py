@@ -270,10 +270,30 @@ def make_swin_window_padding_golden():
     print(f"[golden] swin_window_padding: enc {tuple(ref_enc.shape)} absmax {ref_enc.abs().max():.3f}")
 
 
+def make_ocr_error_golden():
+    """Reference DistilBertForSequenceClassification (surya/ocr_error/model/encoder.py:697-766, eager attention, fp32 CPU) on seeded
+    right-padded batches: logits, [CLS] hidden state and the predictor's argmax labels (surya/ocr_error/__init__.py:55-57)."""
+    from surya_b200.config import ocr_error_default, ocr_error_tiny
+    from surya_b200.synth import ocr_error_state_dict, ocr_error_synthetic_batch
+
+    for kind, cfg, n, max_len, seed in (("tiny", ocr_error_tiny(), 12, 40, 3), ("default", ocr_error_default(), 16, 96, 3)):
+        sd = ocr_error_state_dict(cfg, seed=0)
+        m = ref_shim.build_reference_ocr_error_model(cfg, sd)
+        ids, mask = ocr_error_synthetic_batch(cfg, n, max_len, seed=seed)
+        with torch.inference_mode():
+            logits = m(ids, attention_mask=mask).logits.float()
+            hidden = m.distilbert(ids, attention_mask=mask)[0].float()
+        g = {"input_ids": ids, "attention_mask": mask, "logits": logits, "cls_hidden": hidden[:, 0].clone(), "labels": logits.argmax(1),
+             "meta": {"reference": "VikParuchuri/surya@80e9a7e DistilBertForSequenceClassification, eager attention, fp32 CPU",
+                      "n": n, "max_len": max_len, "seed": seed, "kind": kind}}
+        torch.save(g, GOLDEN / f"ocr_error_{kind}.pt")
+        print(f"[golden] ocr_error_{kind}: logits {tuple(logits.shape)} labels={g['labels'].tolist()}")
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
-    which = set(sys.argv[1:]) or {"rec", "det", "layout", "table", "trace"}
+    which = set(sys.argv[1:]) or {"rec", "det", "layout", "table", "trace", "ocr_error"}
     if "layout" in which:
         make_layout_golden()
     if "table" in which:
@@ -284,6 +304,8 @@ def main():
         make_det_golden()
     if "trace" in which:
         make_predictor_trace_golden()
+    if "ocr_error" in which:
+        make_ocr_error_golden()
     if "rec" not in which:
         return
     for kind, cfg, steps in (("tiny", tiny_rec(), 32), ("synrec", syn_rec(), 40)):

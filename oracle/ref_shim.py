@@ -44,6 +44,23 @@ def install() -> None:
             inv = 1.0 / (base ** (torch.arange(0, dim, 2, dtype=torch.int64).to(device=device, dtype=torch.float) / dim))
             return inv, 1.0
         ROPE_INIT_FUNCTIONS["default"] = _default_rope
+    # (7) surya.ocr_error: config.py:5 imports transformers.onnx.OnnxConfig (removed in 5.x; only subclassed by an
+    # export helper) and tokenizer.py:9 imports three unicode helpers that moved to transformers.tokenization_python
+    if "transformers.onnx" not in sys.modules:
+        try:
+            __import__("transformers.onnx")
+        except Exception:
+            onnx = types.ModuleType("transformers.onnx")
+            onnx.OnnxConfig = type("OnnxConfig", (), {})
+            sys.modules["transformers.onnx"] = onnx
+    import transformers.tokenization_utils as tu
+    try:
+        import transformers.tokenization_python as tp
+        for name in ("_is_control", "_is_punctuation", "_is_whitespace"):
+            if not hasattr(tu, name) and hasattr(tp, name):
+                setattr(tu, name, getattr(tp, name))
+    except Exception:
+        pass
     # (6) optional host deps of surya.input that are absent in this image
     for mod in ("pypdfium2", "filetype"):
         if mod not in sys.modules:
@@ -142,4 +159,23 @@ def build_reference_det_model(cfg, state_dict):
     m = EfficientViTForSemanticSegmentation(EfficientViTConfig()).eval()
     missing, unexpected = m.load_state_dict(state_dict, strict=False)
     assert not [k for k in missing if "num_batches_tracked" not in k] and not unexpected, (missing, unexpected)
+    return m
+
+
+def build_reference_ocr_error_model(cfg, state_dict):
+    """Reference DistilBertForSequenceClassification (surya/ocr_error/model/encoder.py:697) with the synthetic weights, eager
+    attention (the reference's CPU path).  get_head_mask left transformers' PreTrainedModel in 5.x: neutralised on the reference's
+    base class like for Donut-Swin (the predictor never passes a head mask; None entries skip the multiply, encoder.py:182-183)."""
+    install()
+    from surya.ocr_error.model.config import DistilBertConfig
+    from surya.ocr_error.model.encoder import DistilBertForSequenceClassification, DistilBertPreTrainedModel
+
+    DistilBertPreTrainedModel.get_head_mask = lambda self, head_mask, n, *a, **k: [None] * n
+    c = DistilBertConfig(vocab_size=cfg.vocab_size, max_position_embeddings=cfg.max_position_embeddings, n_layers=cfg.n_layers,
+                         n_heads=cfg.n_heads, dim=cfg.dim, hidden_dim=cfg.hidden_dim, pad_token_id=cfg.pad_token_id,
+                         num_labels=cfg.num_labels)
+    c._attn_implementation = "eager"
+    m = DistilBertForSequenceClassification(c).eval()
+    missing, unexpected = m.load_state_dict(state_dict, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
     return m

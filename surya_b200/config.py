@@ -229,3 +229,30 @@ def layout_tiny() -> LayoutConfig:
     enc = SwinConfig(image_size=(256, 256), depths=(2, 2, 2, 2), encoder_length=64)
     dec = AdetrConfig(num_hidden_layers=2)
     return LayoutConfig(encoder=enc, decoder=dec)
+
+
+# ------------------------------------------------------------------------------------------------ ocr_error (DistilBERT)
+@dataclass
+class OcrErrorConfig:
+    """Mirror of DistilBertConfig (surya/ocr_error/model/config.py:13-52) for DistilBertForSequenceClassification."""
+    vocab_size: int = 30522
+    max_position_embeddings: int = 512
+    n_layers: int = 6
+    n_heads: int = 12
+    dim: int = 768
+    hidden_dim: int = 3072
+    num_labels: int = 2
+    pad_token_id: int = 0
+    layer_norm_eps: float = 1e-12   # nn.LayerNorm(eps=1e-12) in Embeddings / TransformerBlock (encoder.py:54, 417, 420)
+
+    def to_dict(self) -> dict:
+        return asdict(self)
+
+
+def ocr_error_default() -> OcrErrorConfig:
+    return OcrErrorConfig()
+
+
+def ocr_error_tiny() -> OcrErrorConfig:
+    """Two layers, 4 heads of 64, small vocabulary: fast CPU oracle tests."""
+    return OcrErrorConfig(vocab_size=1000, max_position_embeddings=128, n_layers=2, n_heads=4, dim=256, hidden_dim=512)

@@ -153,6 +153,10 @@ int sb_rmsnorm_adetr(int dtype, const void* x, int ldx, const void* w, void* y, 
 int sb_layernorm(int dtype, const void* x, const void* w, const void* b, void* y, int rows, int C, float eps, void* stream) {
   return layernorm(dtype, x, w, b, y, rows, C, eps, static_cast<cudaStream_t>(stream));
 }
+int sb_embed_pos_layernorm(int dtype, const int* ids, const int* pos, const void* word, const void* ptab, const void* w,
+                           const void* b, void* y, int rows, int C, float eps, void* stream) {
+  return embed_pos_layernorm(dtype, ids, pos, word, ptab, w, b, y, rows, C, eps, static_cast<cudaStream_t>(stream));
+}
 int sb_patch_gather(int dtype, const void* in, int in_f32, void* out, int B, int Cin, int H, int W, int P, int Kp, void* stream) {
   return patch_gather(dtype, in, in_f32, out, B, Cin, H, W, P, Kp, static_cast<cudaStream_t>(stream));
 }

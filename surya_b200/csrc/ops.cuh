@@ -120,6 +120,10 @@ int box_next_token(const float* bbox, const float* const* heads, const int* head
                    const int* hist_base, int hist_T, long long* hist_tok, float* hist_bbox, float* const* hist_heads,
                    unsigned char* hist_done, cudaStream_t st);
 
+// ocr_error path (ocr_error_ops.cu): Embeddings.forward of DistilBERT over packed real tokens.
+int embed_pos_layernorm(int dtype, const int* ids, const int* pos, const void* word, const void* ptab, const void* w, const void* b,
+                        void* y, int rows, int C, float eps, cudaStream_t st);
+
 // Single-token decode attention over the slot KV cache, fused with RoPE(q,k) and the in-place cache append.
 //   qkv[b] = [q(nh*d) | k(nkv*d) | v(nkv*d)] for batch row b; slot[b], pos[b] (= number of cached tokens) on device.
 //   cache layout: [slot][kv_head][s_max][d]; writes rotated k / v at index pos[b], then attends over 0..pos[b].

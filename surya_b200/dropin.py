@@ -81,3 +81,9 @@ def table_rec_predictor(model: Any, processor: Any, **kw):
     """`TableRecPredictor` over B200TableRecModel (surya/table_rec/__init__.py:22-331)."""
     mod = importlib.import_module("surya.table_rec")
     return _subclass(mod.TableRecPredictor, model, processor, "B200TableRecPredictor")(**kw)
+
+
+def ocr_error_predictor(model: Any, processor: Any, **kw):
+    """`OCRErrorPredictor` over B200DistilBert (surya/ocr_error/__init__.py:14-62); `processor` is the reference's tokenizer."""
+    mod = importlib.import_module("surya.ocr_error")
+    return _subclass(mod.OCRErrorPredictor, model, processor, "B200OCRErrorPredictor")(**kw)

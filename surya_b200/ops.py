@@ -288,6 +288,17 @@ def layernorm(x, w, b, eps=1e-5):
     return out
 
 
+def embed_pos_layernorm(ids, pos, word, ptab, w, b, eps=1e-12):
+    """LayerNorm(word[ids] + ptab[pos]) over packed int32 token rows (sb_embed_pos_layernorm; ocr_error Embeddings)."""
+    lib = _lib.load()
+    assert ids.dtype == torch.int32 and pos.dtype == torch.int32 and ids.numel() == pos.numel()
+    n, C = ids.numel(), word.shape[1]
+    out = torch.empty((n, C), device=word.device, dtype=word.dtype)
+    check(lib.sb_embed_pos_layernorm(dt_code(word.dtype), ptr(ids), ptr(pos), ptr(word), ptr(ptab), ptr(w), ptr(b), ptr(out),
+                                     c_int(n), c_int(C), c_float(eps), stream_ptr()), "sb_embed_pos_layernorm")
+    return out
+
+
 def patch_gather(pixels, P, Kp, dtype):
     lib = _lib.load()
     B, C, H, W = pixels.shape

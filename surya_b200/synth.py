@@ -304,3 +304,48 @@ def layout_synthetic_pages(n: int, size=(768, 768), seed: int = 1234) -> torch.T
     mean = np.array((0.485, 0.456, 0.406), dtype=np.float32)
     std = np.array((0.229, 0.224, 0.225), dtype=np.float32)
     return torch.from_numpy(np.ascontiguousarray(((x - mean) / std).transpose(0, 3, 1, 2)))
+
+
+# ------------------------------------------------------------------------------------------------ ocr_error (DistilBERT)
+def ocr_error_state_dict(cfg, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """fp32 state dict for DistilBertForSequenceClassification (names as in surya/ocr_error/model/encoder.py:48-58, 94-117,
+    381-389, 408-420, 697-706).  Linear weights N(0, 0.7 / sqrt(fan_in)) keep every sub-layer's output near unit RMS so the two
+    class logits are O(1) and differ between texts; embeddings N(0, 1) / N(0, 0.3)."""
+    sd: Dict[str, torch.Tensor] = {}
+
+    def lin(name, n_out, n_in, scale=0.7):
+        sd[name + ".weight"] = _normal(name + ".weight", (n_out, n_in), scale / n_in ** 0.5, seed)
+        sd[name + ".bias"] = _normal(name + ".bias", (n_out,), 0.05, seed)
+
+    e = "distilbert.embeddings."
+    sd[e + "word_embeddings.weight"] = _normal(e + "word_embeddings.weight", (cfg.vocab_size, cfg.dim), 1.0, seed)
+    sd[e + "word_embeddings.weight"][cfg.pad_token_id] = 0.0          # nn.Embedding(padding_idx=pad) row
+    sd[e + "position_embeddings.weight"] = _normal(e + "position_embeddings.weight", (cfg.max_position_embeddings, cfg.dim), 0.3, seed)
+    sd.update(_ln(e + "LayerNorm", cfg.dim, seed))
+    for i in range(cfg.n_layers):
+        b = f"distilbert.transformer.layer.{i}."
+        for n in ("q_lin", "k_lin", "v_lin", "out_lin"):
+            lin(b + "attention." + n, cfg.dim, cfg.dim, 2.0 if n in ("q_lin", "k_lin") else 1.5)
+        sd.update(_ln(b + "sa_layer_norm", cfg.dim, seed))
+        lin(b + "ffn.lin1", cfg.hidden_dim, cfg.dim)
+        lin(b + "ffn.lin2", cfg.dim, cfg.hidden_dim)
+        sd.update(_ln(b + "output_layer_norm", cfg.dim, seed))
+    lin("pre_classifier", cfg.dim, cfg.dim, 1.0)
+    lin("classifier", cfg.num_labels, cfg.dim, 4.0)
+    # zero-sum classifier rows: the post-ReLU pooled vector has a large common mean that would otherwise pick one label for every text
+    sd["classifier.weight"] -= sd["classifier.weight"].mean(dim=1, keepdim=True)
+    return sd
+
+
+def ocr_error_synthetic_batch(cfg, n: int, max_len: int = 64, seed: int = 0, min_len: int = 3):
+    """Right-padded (input_ids int64 [n, L], attention_mask int64 [n, L]) like the tokenizer call of OCRErrorPredictor
+    (surya/ocr_error/__init__.py:28-30: padding='longest'): seeded lengths in [min_len, max_len], at least one row of full length,
+    [CLS]-like id 101 % vocab first, pad id after the end."""
+    g = _gen("ocr_error_batch", seed)
+    lens = torch.randint(min_len, max_len + 1, (n,), generator=g)
+    lens[int(torch.randint(0, n, (1,), generator=g))] = max_len
+    ids = torch.randint(1, cfg.vocab_size, (n, max_len), generator=g, dtype=torch.int64)
+    ids[:, 0] = 101 % cfg.vocab_size
+    mask = (torch.arange(max_len)[None, :] < lens[:, None]).to(torch.int64)
+    ids = torch.where(mask.bool(), ids, torch.full_like(ids, cfg.pad_token_id))
+    return ids, mask
