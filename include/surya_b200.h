@@ -223,6 +223,22 @@ int sb_rec_decode_steps(sb_rec_engine* eng, long long* ids_io, const int* slot, 
  * as one persistent sb_gemm_chain launch instead of four launches (same results up to the down projection's fp32 summation order:
  * the separate path uses the split-K kernel for it). */
 int sb_rec_set_option(sb_rec_engine* eng, const char* name, int value);
+
+/* Device-side scheduler state of the continuous-batching loop: the stop rules of
+ * RecognitionPredictor.prediction_loop (surya/recognition/__init__.py:568-601 — EOS / PAD, len >= max_tokens,
+ * detect_repeat_token of surya/recognition/util.py:59-69) evaluated by a kernel after every step of sb_rec_decode_steps instead of
+ * a per-token loop on the host.  All arrays are caller-owned DEVICE memory of `batch` rows (ring: batch x max_repeats):
+ *   gen_count  tokens generated so far per row (seed 1 after prefill: the prefill token counts);
+ *   ring       the row's last max_repeats tokens, token i at slot i % max_repeats (seed slot 0 with the prefill token);
+ *   row_done   sticky stop flag (seed 1 for idle rows, 0 for running rows);
+ *   n_valid    out: per row, how many steps of the current sb_rec_decode_steps call belong to it (1 + index of its stopping step);
+ *   n_active   out (may be NULL): rows still running after the last step.
+ * gen_count == NULL switches the rules off again.  Changing the state invalidates the captured decode graph. */
+int sb_rec_set_sched(sb_rec_engine* eng, int* gen_count, long long* ring, unsigned char* row_done, int* n_valid, int* n_active,
+                     int max_tokens, int max_repeats);
+/* One evaluation of the same rules on explicit histories ([T, batch] layouts of sb_rec_decode_steps) for host step `step`. */
+int sb_rec_stop_rules(const long long* tok_hist, const unsigned char* done_hist, int step, int batch, int* gen_count, long long* ring,
+                      unsigned char* row_done, int* n_valid, int* n_active, int max_tokens, int max_repeats, void* stream);
 /* Parity taps: copy `bytes` of a named workspace ("feat" = merged image features in window order before the
  * 2-D position embedding, "x", "xl", "logits", "qkv") into dst (device). */
 int sb_rec_debug_copy(sb_rec_engine* eng, const char* name, void* dst, size_t bytes, void* stream);

@@ -146,6 +146,12 @@ int sb_small_head(int dtype, const void* x, int ldx, const void* w, const void* 
                     static_cast<cudaStream_t>(stream));
 }
 
+int sb_rec_stop_rules(const long long* tok_hist, const unsigned char* done_hist, int step, int batch, int* gen_count, long long* ring,
+                      unsigned char* row_done, int* n_valid, int* n_active, int max_tokens, int max_repeats, void* stream) {
+  return stop_rules(tok_hist, done_hist, nullptr, step, batch, gen_count, ring, row_done, n_valid, n_active, max_tokens, max_repeats,
+                    static_cast<cudaStream_t>(stream));
+}
+
 int sb_rmsnorm_adetr(int dtype, const void* x, int ldx, const void* w, void* y, int ldy, int rows, int H, float eps,
                      void* stream) {
   return rmsnorm(dtype, x, ldx, w, y, ldy, rows, H, eps, nullptr, static_cast<cudaStream_t>(stream), 1);

@@ -293,6 +293,73 @@ int decode_tail(int dtype, const DecodeTailArgs& a, cudaStream_t st) {
   return launch_ok();
 }
 
+// ------------------------------------------------------------------------------------------ device-side stop rules
+// The per-row scheduler state of the continuous-batching loop on the device: after every greedy step the stop
+// rules of RecognitionPredictor.prediction_loop (surya/recognition/__init__.py:568-601: EOS / PAD, max_tokens, detect_repeat_token)
+// are evaluated here instead of in a per-token Python loop on the host.  One thread per batch row:
+//   gen_count[r]   tokens generated for the row's prompt so far (the prefill token counts: the host seeds 1)
+//   ring[r][R]     the row's last R = max_repeats tokens (slot = index % R; the host seeds slot 0 with the prefill token)
+//   row_done[r]    sticky: a stop rule fired (or the row is idle); such rows keep stepping like every row of the reference's
+//                  batch does, their tokens are not counted
+//   n_valid[r]     steps of the current host round trip whose outputs belong to the row (1 + index of its stopping step)
+//   n_active[0]    rows still running after this step (one int for the host to poll)
+// detect_repeat_token (surya/recognition/util.py:59-69): with at least R tokens, u = distinct values among the last R; stop when
+// u <= 5 and the last u tokens equal the u tokens before them.
+constexpr int STOP_MAX_RING = 64;
+
+__global__ void __launch_bounds__(256) stop_rules_kernel(const long long* __restrict__ tok_hist, const unsigned char* __restrict__ done_hist,
+                                                         const int* __restrict__ step_dev, int step_host, int B, int* __restrict__ gen_count,
+                                                         long long* __restrict__ ring, unsigned char* __restrict__ row_done,
+                                                         int* __restrict__ n_valid, int* __restrict__ n_active, int max_tokens, int R) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ int s_active;
+  if (threadIdx.x == 0) s_active = 0;
+  __syncthreads();
+  const int s = step_dev ? (*step_dev - 1) : step_host;        // the step decode_tail has just written
+  for (int r = threadIdx.x; r < B; r += blockDim.x) {
+    if (row_done[r]) continue;
+    const size_t ho = static_cast<size_t>(s) * B + r;
+    const long long tok = tok_hist[ho];
+    const int cnt = gen_count[r] + 1;
+    gen_count[r] = cnt;
+    long long* rg = ring + static_cast<size_t>(r) * R;
+    rg[(cnt - 1) % R] = tok;
+    bool stop = (done_hist[ho] != 0) || (cnt >= max_tokens);
+    if (!stop && cnt >= R) {
+      // last_n[j] for j = 0..R-1 (oldest first) lives at ring slot (cnt + j) % R
+      int u = 0;
+      for (int j = 0; j < R && u <= 5; ++j) {
+        const long long v = rg[(cnt + j) % R];
+        bool seen = false;
+        for (int k = 0; k < j; ++k) seen |= (rg[(cnt + k) % R] == v);
+        u += seen ? 0 : 1;
+      }
+      if (u <= 5 && 2 * u <= R) {          // a window shorter than 2u: Python's last_n[-2u:-u] is shorter than last_n[-u:], never equal
+        bool same = true;
+        for (int j = 0; j < u; ++j) same &= (rg[(cnt + R - u + j) % R] == rg[(cnt + R - 2 * u + j) % R]);
+        stop = same;
+      }
+    }
+    n_valid[r] = s + 1;
+    if (stop) row_done[r] = 1;
+    else atomicAdd(&s_active, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && n_active) *n_active = s_active;
+}
+
+int stop_rules(const long long* tok_hist, const unsigned char* done_hist, const int* step_dev, int step_host, int B, int* gen_count,
+               long long* ring, unsigned char* row_done, int* n_valid, int* n_active, int max_tokens, int max_repeats,
+               cudaStream_t st) {
+  if (B <= 0) return 0;
+  if (!tok_hist || !done_hist || !gen_count || !ring || !row_done || !n_valid) { set_error("stop_rules: null argument"); return -1; }
+  if (max_repeats < 2 || max_repeats > STOP_MAX_RING) { set_error("stop_rules: max_repeats %d outside [2, %d]", max_repeats, STOP_MAX_RING); return -2; }
+  launch_pdl(stop_rules_kernel, dim3(1), dim3(256), 0, st, tok_hist, done_hist, step_dev, step_host, B, gen_count, ring, row_done,
+             n_valid, n_active, max_tokens, max_repeats);
+  return launch_ok();
+}
+
 // ------------------------------------------------------------------------------------------ gather + pad rows
 // dst[i, 0:K] = src[perm[i], 0:K] (converted from SrcT), dst[i, K:Kp] = 0.
 template <typename T, typename SrcT>

@@ -25,6 +25,11 @@ struct DecodeTailArgs {
 };
 int decode_tail(int dtype, const DecodeTailArgs& a, cudaStream_t st);
 
+// Stop rules of the recognition decode loop evaluated on the device after a step (ops.cu: stop_rules_kernel).
+int stop_rules(const long long* tok_hist, const unsigned char* done_hist, const int* step_dev, int step_host, int B, int* gen_count,
+               long long* ring, unsigned char* row_done, int* n_valid, int* n_active, int max_tokens, int max_repeats,
+               cudaStream_t st);
+
 int gather_pad_rows(int dtype, const void* src, int src_is_f32, int lds, const int* perm, void* dst, int ldd, int rows,
                     int K, int Kp, cudaStream_t st);
 int rope_vision(int dtype, void* qkv, int ld, const int* pos_rc, const float* inv_freq, int n_tok, int nh, int d,

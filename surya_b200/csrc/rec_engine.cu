@@ -55,6 +55,9 @@ struct sb_rec_engine {
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   const void* graph_key[8] = {nullptr};
+  // device-side stop rules (sb_rec_set_sched): caller-owned per-row state, evaluated by stop_rules_kernel after every loop step
+  int* sc_gen = nullptr; long long* sc_ring = nullptr; unsigned char* sc_done = nullptr; int* sc_valid = nullptr; int* sc_active = nullptr;
+  int sc_max_tokens = 0, sc_max_repeats = 0;
 
   const void* W(int idx) const { return w[idx]; }
   const void* WE(int layer, int k) const { return w[SB_RW_ENC_BASE + layer * SB_RWE_STRIDE + k]; }
@@ -185,7 +188,13 @@ static int run_heads(sb_rec_engine* e, void* hidden, int rows, const HeadOut& o,
     t.ids_io = o.ids_io; t.pos_io = o.pos_io;
     if (!t.bbox && o.bbox_hist) t.bbox = e->st_bbox;   // the tail computes boxes when any box output is requested
   }
-  return decode_tail(c.dtype, t, st);
+  CK(decode_tail(c.dtype, t, st));
+  if (o.loop && e->sc_gen) {
+    if (!o.tok_hist || !o.done_hist) { set_error("device-side stop rules need the token and done histories"); return -9; }
+    CK(stop_rules(o.tok_hist, o.done_hist, e->st_step, 0, rows, e->sc_gen, e->sc_ring, e->sc_done, e->sc_valid, e->sc_active,
+                  e->sc_max_tokens, e->sc_max_repeats, st));
+  }
+  return 0;
 }
 
 static int run_decoder_prefill(sb_rec_engine* e, const long long* ids, int n_tok, const int* feat_row, const int* hidx,
@@ -432,6 +441,7 @@ int sb_rec_decode_steps(sb_rec_engine* e, long long* ids_io, const int* slot, in
   } rejoin{hop, e->own_stream, caller, e->ev_out};
   if (cudaMemsetAsync(e->st_step, 0, sizeof(int), st) != cudaSuccess ||
       cudaMemsetAsync(e->st_counter, 0, sizeof(unsigned int), st) != cudaSuccess) { cudaGetLastError(); set_error("memset failed"); return -3; }
+  if (e->sc_valid && cudaMemsetAsync(e->sc_valid, 0, sizeof(int) * batch, st) != cudaSuccess) { cudaGetLastError(); set_error("memset failed"); return -3; }
   // the first step's input embeddings; every later step finds them written by the previous step's tail kernel
   CK(embed_rows(e->c.dtype, ids_io, e->W(SB_RW_EMBED), e->x, e->c.dec_hidden, batch, e->c.dec_hidden, st));
   HeadOut ho;
@@ -470,6 +480,23 @@ int sb_rec_decode_steps(sb_rec_engine* e, long long* ids_io, const int* slot, in
     if (cudaGraphLaunch(e->graph_exec, st) != cudaSuccess) { cudaGetLastError(); set_error("cudaGraphLaunch failed"); return -7; }
     count_launches(e->graph_nodes);
   }
+  return 0;
+}
+
+int sb_rec_set_sched(sb_rec_engine* e, int* gen_count, long long* ring, unsigned char* row_done, int* n_valid, int* n_active,
+                     int max_tokens, int max_repeats) {
+  if (!e) { set_error("sb_rec_set_sched: null engine"); return -1; }
+  if (gen_count && (!ring || !row_done || !n_valid || max_tokens <= 0 || max_repeats < 2 || max_repeats > 64)) {
+    set_error("sb_rec_set_sched: incomplete state (ring / row_done / n_valid) or max_tokens %d / max_repeats %d out of range", max_tokens,
+              max_repeats);
+    return -2;
+  }
+  const bool same = e->sc_gen == gen_count && e->sc_ring == ring && e->sc_done == row_done && e->sc_valid == n_valid &&
+                    e->sc_active == n_active && e->sc_max_tokens == max_tokens && e->sc_max_repeats == max_repeats;
+  if (!same && e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }   // the captured step changes
+  e->sc_gen = gen_count; e->sc_ring = gen_count ? ring : nullptr; e->sc_done = gen_count ? row_done : nullptr;
+  e->sc_valid = gen_count ? n_valid : nullptr; e->sc_active = gen_count ? n_active : nullptr;
+  e->sc_max_tokens = gen_count ? max_tokens : 0; e->sc_max_repeats = gen_count ? max_repeats : 0;
   return 0;
 }
 

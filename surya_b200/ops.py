@@ -200,6 +200,17 @@ def embed_rows(ids, embed):
     return out
 
 
+def rec_stop_rules(tok_hist, done_hist, step, gen_count, ring, row_done, n_valid, n_active, max_tokens, max_repeats=40):
+    """One evaluation of the decode loop's stop rules for host step `step` (sb_rec_stop_rules); state tensors update in place."""
+    lib = _lib.load()
+    B = gen_count.numel()
+    assert tok_hist.dtype == torch.int64 and done_hist.dtype == torch.uint8 and tok_hist.shape[1] == B
+    assert gen_count.dtype == torch.int32 and ring.dtype == torch.int64 and row_done.dtype == torch.uint8 and n_valid.dtype == torch.int32
+    assert ring.shape == (B, max_repeats) and ring.is_contiguous() and tok_hist.is_contiguous() and done_hist.is_contiguous()
+    check(lib.sb_rec_stop_rules(ptr(tok_hist), ptr(done_hist), c_int(step), c_int(B), ptr(gen_count), ptr(ring), ptr(row_done),
+                                ptr(n_valid), ptr(n_active), c_int(max_tokens), c_int(max_repeats), stream_ptr()), "sb_rec_stop_rules")
+
+
 def argmax_score(logits, eos, pad):
     lib = _lib.load()
     rows, V = logits.shape

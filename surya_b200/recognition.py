@@ -409,6 +409,19 @@ class RecEngine:
                                            c_int(1 if use_graph else 0), stream_ptr()), "sb_rec_decode_steps")
         return hist
 
+    def set_sched(self, state: Optional[dict], max_tokens: int = 0, max_repeats: int = 40):
+        """Device-side stop rules for decode_steps (sb_rec_set_sched).  state: dict of device tensors
+        gen (int32 [B]), ring (int64 [B, max_repeats]), done (uint8 [B]), valid (int32 [B]), active (int32 [1]); None = off."""
+        if state is None:
+            check(self.lib.sb_rec_set_sched(self._h, c_void_p(0), c_void_p(0), c_void_p(0), c_void_p(0), c_void_p(0), c_int(0), c_int(0)),
+                  "sb_rec_set_sched")
+            return
+        assert state["gen"].dtype == torch.int32 and state["ring"].dtype == torch.int64 and state["done"].dtype == torch.uint8
+        assert state["valid"].dtype == torch.int32 and state["active"].dtype == torch.int32
+        assert state["ring"].shape == (state["gen"].numel(), max_repeats) and state["ring"].is_contiguous()
+        check(self.lib.sb_rec_set_sched(self._h, ptr(state["gen"]), ptr(state["ring"]), ptr(state["done"]), ptr(state["valid"]),
+                                        ptr(state["active"]), c_int(max_tokens), c_int(max_repeats)), "sb_rec_set_sched")
+
     def debug_tensor(self, name: str, rows: int, cols: int) -> torch.Tensor:
         """Copy of an engine workspace (parity taps): feat / x / xl / logits / qkv."""
         out = torch.empty((rows, cols), dtype=self.dtype, device=self.device)
@@ -644,8 +657,16 @@ class RecognitionRunner:
 
     min_prefill_ratio = 0.2
 
-    def __init__(self, engine: RecEngine, batch_size: int = 256, max_tokens: int = 128, poll: int = 8):
+    MAX_REPEATS = 40     # detect_repeat_token's default window (surya/recognition/util.py:59)
+
+    def __init__(self, engine: RecEngine, batch_size: int = 256, max_tokens: int = 128, poll: int = 8, stop_rules: str = "device"):
+        """stop_rules: "device" (default) — EOS / PAD / max_tokens / detect_repeat_token are evaluated by a kernel after every decode
+        step (sb_rec_set_sched) and the host reads one count per row and round trip; "host" — the per-token Python loop of the
+        reference.  Both give identical results (tests/test_rec_gpu.py::test_device_stop_rules_equal_host_rules)."""
+        if stop_rules not in ("device", "host"):
+            raise ValueError("stop_rules must be 'device' or 'host'")
         self.engine, self.batch_size, self.max_tokens, self.poll = engine, batch_size, max_tokens, max(1, poll)
+        self.stop_rules = stop_rules
 
     def preprocess(self, crops: Sequence[np.ndarray], math_mode: bool = True, workers: Optional[int] = None):
         """Host side of SuryaOCRProcessor for one crop each (scale_to_fit -> resize to x28 -> normalise -> merge-block-major
@@ -729,6 +750,21 @@ class RecognitionRunner:
         ids_io, pos_host, slot_host = bufs["ids_io"], bufs["pos_host"], bufs["slot_host"]
         pos_io, slot_t, hist = bufs["pos_io"], bufs["slot_t"], bufs["hist"]
         ids_io.fill_(cfg.pad_token_id)
+        # device-side stop rules: per-row generated-token count, last-40-token ring and sticky done flag live on the
+        # device and are advanced by stop_rules_kernel after every step; the host reads one count + one flag per row and round trip
+        sched = None
+        if self.stop_rules == "device" and not fixed_steps:
+            sched = bufs.get("sched")
+            if sched is None:
+                sched = {"gen": torch.zeros(Bsz, dtype=torch.int32, device=dev),
+                         "ring": torch.zeros((Bsz, self.MAX_REPEATS), dtype=torch.int64, device=dev),
+                         "done": torch.ones(Bsz, dtype=torch.uint8, device=dev),
+                         "valid": torch.zeros(Bsz, dtype=torch.int32, device=dev),
+                         "active": torch.zeros(1, dtype=torch.int32, device=dev),
+                         "gen_host": torch.zeros(Bsz, dtype=torch.int32).pin_memory(),
+                         "done_host": torch.ones(Bsz, dtype=torch.uint8).pin_memory()}
+                bufs["sched"] = sched
+            eng.set_sched(sched, self.max_tokens, self.MAX_REPEATS)
 
         def finish(row):
             eng.release_slots([row_slot[row]])
@@ -765,7 +801,10 @@ class RecognitionRunner:
                     except Exception:
                         eng.release_slots(new_slots)
                         raise
-                    ids_io[torch.tensor(rows, dtype=torch.int64, device=dev)] = out["next_ids"]
+                    rows_t = torch.tensor(rows, dtype=torch.int64, device=dev)
+                    ids_io[rows_t] = out["next_ids"]
+                    if sched is not None:           # the prefill token is token 0 of the row's repeat window
+                        sched["ring"][rows_t, 0] = out["tok"]
                     tok_h, sc_h, bb_h = out["tok"].cpu().numpy(), out["score"].cpu().numpy(), out["bbox"].cpu().numpy()
                     for j, (r, p) in enumerate(zip(rows, take)):
                         row_prompt[r], row_slot[r] = p, new_slots[j]
@@ -785,8 +824,26 @@ class RecognitionRunner:
                         slot_host[r] = row_slot[r]
                     pos_io.copy_(pos_host, non_blocking=True)
                     slot_t.copy_(slot_host, non_blocking=True)
+                    if sched is not None:
+                        for r in range(Bsz):
+                            p = row_prompt[r]
+                            sched["gen_host"][r] = 0 if p is None else len(tokens[p])
+                            sched["done_host"][r] = 1 if p is None else 0
+                        sched["gen"].copy_(sched["gen_host"], non_blocking=True)
+                        sched["done"].copy_(sched["done_host"], non_blocking=True)
                     eng.decode_steps(ids_io, slot_t, pos_io, n, hist=hist, max_pos=int(pos_host.max()))
                     th, sh, bh = hist["tok"][:n].cpu().numpy(), hist["score"][:n].cpu().numpy(), hist["bbox"][:n].cpu().numpy()
+                    if sched is not None:
+                        valid_h, done_h = sched["valid"].cpu().numpy(), sched["done"].cpu().numpy()
+                        for r in active:             # the device already applied the stop rules: take each row's valid prefix
+                            p = row_prompt[r]
+                            k, m = len(tokens[p]), int(valid_h[r])
+                            tokens[p].extend(th[:m, r].tolist())
+                            scores[p].extend(sh[:m, r].tolist())
+                            bboxes[p, k:k + m] = bh[:m, r]
+                            if done_h[r]:
+                                finish(r)
+                        continue
                     for r in active:
                         p = row_prompt[r]
                         if fixed_steps:           # no stop rules to evaluate: unpack the whole chunk at once
@@ -808,7 +865,7 @@ class RecognitionRunner:
                                 stop = full
                             else:
                                 stop = tokens[p][-1] in (cfg.eos_token_id, cfg.pad_token_id) or full or \
-                                    detect_repeat_token(tokens[p])
+                                    detect_repeat_token(tokens[p], self.MAX_REPEATS)
                             if stop:
                                 finish(r)
                                 break
@@ -817,6 +874,8 @@ class RecognitionRunner:
                 if row_prompt[r] is not None:
                     finish(r)
             eng.release_slots([scratch])
+            if sched is not None:
+                eng.set_sched(None)          # the state tensors belong to this runner: never leave the engine pointing at them
         return tokens, scores, bboxes
 
     def run(self, crops: Sequence[np.ndarray], math_mode: bool = True, fixed_steps: bool = False):

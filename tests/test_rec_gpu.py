@@ -474,3 +474,101 @@ def test_empty_single_and_ragged_batches(built_lib):
     for i in range(len(crops)):
         assert tok[i] == alone[i][0][0] and sc[i] == alone[i][1][0] and np.array_equal(bb[i], alone[i][2][0]), i
     eng.close()
+
+
+@pytest.mark.parametrize("R,max_tokens,poll", [(40, 100, 8), (40, 60, 1), (6, 1000, 5), (2, 50, 7)])
+def test_stop_rules_kernel_matches_python_rules(built_lib, R, max_tokens, poll):
+    """stop_rules_kernel (EOS / PAD flag, max_tokens, detect_repeat_token) against the host rules of
+    RecognitionRunner (mirror of surya/recognition/__init__.py:585-598 + util.py:59-69) on crafted token streams — integer work,
+    exact: per round trip the valid-step count, the sticky done flag, the generated count and the active-row count."""
+    from surya_b200 import ops
+    from surya_b200.recognition import detect_repeat_token
+
+    rng = np.random.default_rng(R * 1000 + max_tokens)
+    T_total, EOS = 130, 1
+    streams = []
+    streams.append(rng.permutation(5000)[:T_total] + 10)                                  # all distinct: only max_tokens stops it
+    s1 = rng.permutation(5000)[:T_total] + 10; s1[17] = EOS; streams.append(s1)           # EOS at step 17
+    streams.append(np.full(T_total, 77))                                                  # one token for ever
+    s3 = rng.permutation(5000)[:T_total] + 10; s3[10:] = np.tile([5, 6, 7], T_total)[:T_total - 10]; streams.append(s3)
+    s4 = rng.permutation(5000)[:T_total] + 10; s4[3:] = np.tile([11, 12, 13, 14, 15], T_total)[:T_total - 3]; streams.append(s4)
+    streams.append(np.tile([21, 22, 23, 24, 25, 26], T_total)[:T_total])                  # period 6: u = 6 > 5, never a repeat stop
+    streams.append(rng.integers(10, 5000, T_total))                                       # idle row (row_done seeded 1)
+    s7 = np.tile([31, 32], T_total)[:T_total].copy(); s7[45] = 999; streams.append(s7)     # period 2 with one glitch
+    s8 = rng.integers(10, 14, T_total); streams.append(s8)                                 # 4 symbols at random: u <= 5, rarely periodic
+    B = len(streams)
+    first = rng.integers(10, 5000, B)                                                      # the prefill tokens
+    first[2], first[7] = 77, 32
+    idle = [6]
+    toks = np.stack(streams, 1).astype(np.int64)                                           # [T_total, B]
+    dones = (toks == EOS).astype(np.uint8)
+
+    # host rules, token by token
+    hist = [[int(first[r])] for r in range(B)]
+    alive = [r not in idle for r in range(B)]
+    dev = "cuda"
+    gen = torch.tensor([0 if r in idle else 1 for r in range(B)], dtype=torch.int32, device=dev)
+    ring = torch.zeros((B, R), dtype=torch.int64, device=dev)
+    ring[:, 0] = torch.from_numpy(first).to(dev)
+    row_done = torch.tensor([1 if r in idle else 0 for r in range(B)], dtype=torch.uint8, device=dev)
+    valid = torch.zeros(B, dtype=torch.int32, device=dev)
+    active = torch.zeros(1, dtype=torch.int32, device=dev)
+    t0 = 0
+    while t0 < T_total and any(alive):
+        n = min(poll, T_total - t0)
+        th = torch.from_numpy(toks[t0:t0 + n]).contiguous().to(dev)
+        dh = torch.from_numpy(dones[t0:t0 + n]).contiguous().to(dev)
+        valid.zero_()
+        for s in range(n):
+            ops.rec_stop_rules(th, dh, s, gen, ring, row_done, valid, active, max_tokens, R)
+        torch.cuda.synchronize()
+        exp_valid = [0] * B
+        for r in range(B):
+            if not alive[r]:
+                continue
+            for s in range(n):
+                hist[r].append(int(toks[t0 + s, r]))
+                exp_valid[r] = s + 1
+                if hist[r][-1] == EOS or len(hist[r]) >= max_tokens or detect_repeat_token(hist[r], R):
+                    alive[r] = False
+                    break
+        assert valid.cpu().tolist() == exp_valid, f"chunk at {t0}: valid {valid.cpu().tolist()} vs {exp_valid}"
+        assert row_done.cpu().tolist() == [0 if a else 1 for a in alive], f"chunk at {t0}: done flags"
+        assert gen.cpu().tolist() == [0 if r in idle else len(hist[r]) for r in range(B)], f"chunk at {t0}: generated counts"
+        assert int(active.item()) == sum(alive)
+        t0 += n
+    assert not any(alive) or max_tokens > T_total
+    if R == 40 and max_tokens == 100:
+        assert len(hist[2]) == 40 and len(hist[1]) == 19 and len(hist[0]) == 100 and len(hist[5]) == 100      # the rules all fired
+
+
+@pytest.mark.parametrize("max_repeats,steps,poll", [(40, 24, 5), (2, 30, 8), (3, 12, 1)])
+def test_device_stop_rules_equal_host_rules(built_lib, max_repeats, steps, poll):
+    """RecognitionRunner with the stop rules on the device (default) returns exactly what the per-token host loop returns: tokens,
+    scores and boxes of every crop, for several polling intervals / repeat windows (a window of 2 makes the repeat rule fire on
+    the synthetic model's occasional double tokens)."""
+    from surya_b200.config import tiny_rec
+    from surya_b200.recognition import RecognitionRunner
+    from surya_b200.synth import rec_state_dict, rec_synthetic_crops
+
+    dtype = torch.float16
+    cfg = tiny_rec()
+    sd = rec_state_dict(cfg, seed=0)
+    crops = [rec_synthetic_crops(1, 48, 256 + 37 * i, seed=100 + i)[0] for i in range(11)]
+    eng = _engine(cfg, sd, dtype, max_slots=8, s_max=256, max_patches=4096, max_tokens=1024)
+    out = {}
+    for mode in ("host", "device"):
+        runner = RecognitionRunner(eng, batch_size=4, max_tokens=steps, poll=poll, stop_rules=mode)
+        runner.MAX_REPEATS = max_repeats
+        out[mode] = runner.run(crops)
+    th, sh, bh = out["host"]
+    td, sd_, bd = out["device"]
+    assert td == th
+    assert all(np.array_equal(np.asarray(a, np.float32), np.asarray(b, np.float32)) for a, b in zip(sd_, sh))
+    assert np.array_equal(bd, bh)
+    lens = [len(t) for t in th]
+    _report(f"stop_rules_R{max_repeats}_T{steps}", {"lengths": lens})
+    # a fixed-steps run right after a device-rules run must not see the rules any more (the engine state was reset)
+    fixed = RecognitionRunner(eng, batch_size=4, max_tokens=steps, poll=poll).run(crops[:3], fixed_steps=True)[0]
+    assert all(len(t) == steps for t in fixed)
+    eng.close()
