@@ -224,6 +224,17 @@ int sb_rec_decode_steps(sb_rec_engine* eng, long long* ids_io, const int* slot, 
  * the separate path uses the split-K kernel for it). */
 int sb_rec_set_option(sb_rec_engine* eng, const char* name, int value);
 
+/* Recognition crop preprocessing on the device: SuryaOCRProcessor.scale_to_fit (cv2 INTER_LANCZOS4 when the pixel
+ * count is outside [168*168, 1024*256], surya/common/surya/processor/__init__.py:140-178) + _process_and_tile (cv2 INTER_CUBIC to the
+ * next multiple of patch*merge, x*(1/255) in double, (x - mean)/std in float, merge-block-major tiles, :180-230) for n_crops uint8 HWC
+ * crops packed in `crops_u8` (device).  desc: n_crops x 9 int32 (device) = {byte offset of the crop, h, w, nh, nw (size after
+ * scale_to_fit, = h, w when it does not apply), hb, wb (multiples of patch*merge), float offset of the crop's [nh, nw, 3] intermediate
+ * in `scratch`, first tile row}; the host computes the sizes with the reference's own Python arithmetic.  tiles: fp32
+ * [rows, ld_tiles >= 3*patch*patch] (device), exactly the `image_tiles` sb_rec_prefill takes with tiles_f32 = 1.  mean3 / std3: host. */
+int sb_rec_preprocess(const unsigned char* crops_u8, const int* desc, int n_crops, int max_nh, int max_nw, int max_hb, int max_wb,
+                      int any_scale_to_fit, float* scratch, float* tiles, int ld_tiles, int patch, int merge, const float* mean3,
+                      const float* std3, void* stream);
+
 /* Device-side scheduler state of the continuous-batching loop: the stop rules of
  * RecognitionPredictor.prediction_loop (surya/recognition/__init__.py:568-601 — EOS / PAD, len >= max_tokens,
  * detect_repeat_token of surya/recognition/util.py:59-69) evaluated by a kernel after every step of sb_rec_decode_steps instead of

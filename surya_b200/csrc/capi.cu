@@ -146,6 +146,13 @@ int sb_small_head(int dtype, const void* x, int ldx, const void* w, const void* 
                     static_cast<cudaStream_t>(stream));
 }
 
+int sb_rec_preprocess(const unsigned char* crops_u8, const int* desc, int n_crops, int max_nh, int max_nw, int max_hb, int max_wb,
+                      int any_scale_to_fit, float* scratch, float* tiles, int ld_tiles, int patch, int merge, const float* mean3,
+                      const float* std3, void* stream) {
+  return rec_preprocess(crops_u8, desc, n_crops, max_nh, max_nw, max_hb, max_wb, any_scale_to_fit, scratch, tiles, ld_tiles, patch, merge,
+                        mean3, std3, static_cast<cudaStream_t>(stream));
+}
+
 int sb_rec_stop_rules(const long long* tok_hist, const unsigned char* done_hist, int step, int batch, int* gen_count, long long* ring,
                       unsigned char* row_done, int* n_valid, int* n_active, int max_tokens, int max_repeats, void* stream) {
   return stop_rules(tok_hist, done_hist, nullptr, step, batch, gen_count, ring, row_done, n_valid, n_active, max_tokens, max_repeats,

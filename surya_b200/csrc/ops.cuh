@@ -125,6 +125,11 @@ int box_next_token(const float* bbox, const float* const* heads, const int* head
                    const int* hist_base, int hist_T, long long* hist_tok, float* hist_bbox, float* const* hist_heads,
                    unsigned char* hist_done, cudaStream_t st);
 
+// Recognition crop preprocessing on the device (preproc.cu): uint8 crops -> Lanczos4 scale_to_fit -> cubic resize to x28 -> normalise ->
+// merge-block-major fp32 tiles.  desc: n_crops x 9 int32 on the device; mean / std3: 3 host floats each.
+int rec_preprocess(const unsigned char* crops, const int* desc, int n_crops, int max_nh, int max_nw, int max_hb, int max_wb, int any_stage1,
+                   float* scratch, float* tiles, int ld_tiles, int patch, int merge, const float* mean, const float* std3, cudaStream_t st);
+
 // ocr_error path (ocr_error_ops.cu): Embeddings.forward of DistilBERT over packed real tokens.
 int embed_pos_layernorm(int dtype, const int* ids, const int* pos, const void* word, const void* ptab, const void* w, const void* b,
                         void* y, int rows, int C, float eps, cudaStream_t st);

@@ -627,6 +627,56 @@ def tile_image(image: np.ndarray, patch: int = 14, merge: int = 2) -> Tuple[np.n
     return np.ascontiguousarray(x).reshape(gh * gw, 3 * patch * patch), (1, gh, gw)
 
 
+def fit_size(h: int, w: int, max_size=(1024, 256), min_size=(168, 168)) -> Tuple[int, int]:
+    """(h, w) after SuryaOCRProcessor.scale_to_fit (processor/__init__.py:148-174) — the reference's own float arithmetic."""
+    cur, mx, mn = w * h, max_size[0] * max_size[1], min_size[0] * min_size[1]
+    if cur > mx:
+        s = (mx / cur) ** 0.5
+        return math.floor(h * s), math.floor(w * s)
+    if cur < mn:
+        s = (mn / cur) ** 0.5
+        return math.ceil(h * s), math.ceil(w * s)
+    return h, w
+
+
+PP_DESC = 9     # int32 words per crop in sb_rec_preprocess's descriptor table
+
+
+def build_preprocess_plan(crops: Sequence[np.ndarray], cfg: RecConfig, max_size=(1024, 256)) -> dict:
+    """Host plan of the device preprocessing path (sb_rec_preprocess): uint8 HWC crops packed back to back (16-byte
+    aligned), one descriptor per crop {byte offset, h, w, size after scale_to_fit, size rounded up to patch*merge, scratch offset,
+    first tile row} and the tile grids — only sizes are computed here, with the reference's arithmetic; every pixel is touched on
+    the device."""
+    P, m = cfg.vision_encoder.patch_size, cfg.merge_size
+    factor = P * m
+    desc = np.zeros((len(crops), PP_DESC), dtype=np.int32)
+    grids, off, scratch, row = [], 0, 0, 0
+    for i, c in enumerate(crops):
+        c = np.asarray(c)
+        if c.ndim != 3 or c.shape[2] != 3 or c.shape[0] == 0 or c.shape[1] == 0:
+            raise _lib.SuryaB200Error(f"crop {i}: expected a non-empty [h, w, 3] image, got shape {c.shape}")
+        if c.dtype != np.uint8:
+            raise _lib.SuryaB200Error(f"crop {i}: the device preprocessing path takes uint8 pixels (page slices), got {c.dtype}")
+        h, w = c.shape[:2]
+        nh, nw = fit_size(h, w, max_size)
+        hb, wb = math.ceil(nh / factor) * factor, math.ceil(nw / factor) * factor
+        desc[i] = (off, h, w, nh, nw, hb, wb, scratch, row)
+        grids.append((1, hb // P, wb // P))
+        off += (h * w * 3 + 15) // 16 * 16
+        if (nh, nw) != (h, w):
+            scratch += nh * nw * 3
+        row += (hb // P) * (wb // P)
+        if off >= 2 ** 31 or scratch >= 2 ** 31:
+            raise _lib.SuryaB200Error("device preprocessing: more than 2 GiB of crops in one call; split the batch")
+    packed = np.zeros(max(off, 16), dtype=np.uint8)
+    for i, c in enumerate(crops):
+        o, h, w = int(desc[i, 0]), int(desc[i, 1]), int(desc[i, 2])
+        packed[o:o + h * w * 3] = np.ascontiguousarray(c).reshape(-1)
+    mx = tuple(int(desc[:, k].max()) if len(crops) else 0 for k in (3, 4, 5, 6))
+    return {"packed": packed, "desc": desc.reshape(-1), "grids": grids, "n_rows": row, "scratch_floats": scratch,
+            "any_stage1": int(scratch > 0), "max": mx}
+
+
 def prompt_tokens(cfg: RecConfig, n_image_tokens: int, math_mode: bool = True, text_ids: Sequence[int] = ()) -> np.ndarray:
     """Token layout of one ocr_with_boxes prompt (processor/__init__.py:247-248, 260-274, 312)."""
     ids = [cfg.image_token_id] * n_image_tokens + list(cfg.register_token_ids[: cfg.num_register_tokens])
@@ -694,6 +744,34 @@ class RecognitionRunner:
             with ThreadPoolExecutor(max_workers=workers) as ex:
                 res = list(ex.map(one, crops))
         return [r[0] for r in res], [r[1] for r in res], [r[2] for r in res]
+
+    def preprocess_device(self, crops: Sequence[np.ndarray], math_mode: bool = True):
+        """Device side of SuryaOCRProcessor for uint8 crops: ONE pinned uint8 upload (3 B / pixel), then
+        sb_rec_preprocess does scale_to_fit (Lanczos4), the resize to x28 (cubic), normalisation and tiling on the GPU and leaves the
+        fp32 tiles in HBM, where run_preprocessed's prefill reads them.  Same return contract as preprocess(), tiles as one packed
+        CUDA tensor."""
+        eng, cfg = self.engine, self.engine.cfg
+        dev = eng.device
+        P, m = cfg.vision_encoder.patch_size, cfg.merge_size
+        plan = build_preprocess_plan(crops, cfg)
+        seqs = [prompt_tokens(cfg, g[1] * g[2] // m ** 2, math_mode) for g in plan["grids"]]
+        if not crops:
+            return torch.zeros((0, 3 * P * P), dtype=torch.float32, device=dev), [], []
+        host = torch.from_numpy(plan["packed"]).pin_memory()
+        desc_h = torch.from_numpy(plan["desc"]).pin_memory()
+        packed = host.to(dev, non_blocking=True)
+        desc = desc_h.to(dev, non_blocking=True)
+        tiles = torch.empty((plan["n_rows"], 3 * P * P), dtype=torch.float32, device=dev)
+        scratch = torch.empty(max(plan["scratch_floats"], 1), dtype=torch.float32, device=dev)
+        mean = (ctypes.c_float * 3)(*IMAGE_MEAN.tolist())
+        std = (ctypes.c_float * 3)(*IMAGE_STD.tolist())
+        mx = plan["max"]
+        check(eng.lib.sb_rec_preprocess(ptr(packed), ptr(desc), c_int(len(crops)), c_int(mx[0]), c_int(mx[1]), c_int(mx[2]), c_int(mx[3]),
+                                        c_int(plan["any_stage1"]), ptr(scratch), ptr(tiles), c_int(tiles.stride(0)), c_int(P), c_int(m),
+                                        mean, std, stream_ptr()), "sb_rec_preprocess")
+        # the pinned staging buffers must outlive the asynchronous copies: keep them until the next call
+        self._pp_keep = (host, desc_h, packed, desc, scratch)
+        return tiles, plan["grids"], seqs
 
     def run_preprocessed(self, tiles, grids, seqs, fixed_steps: bool = False):
         """tiles: per-crop list of [P_i, patch_dim] arrays, or ONE packed [sum P_i, patch_dim] array / torch tensor in crop
@@ -878,6 +956,10 @@ class RecognitionRunner:
                 eng.set_sched(None)          # the state tensors belong to this runner: never leave the engine pointing at them
         return tokens, scores, bboxes
 
-    def run(self, crops: Sequence[np.ndarray], math_mode: bool = True, fixed_steps: bool = False):
-        tiles, grids, seqs = self.preprocess(crops, math_mode)
+    def run(self, crops: Sequence[np.ndarray], math_mode: bool = True, fixed_steps: bool = False, preprocess: str = "host"):
+        """preprocess: "host" — the OpenCV thread pool (any pixel dtype); "device" — uint8 crops, resized / normalised / tiled by
+        sb_rec_preprocess on the GPU (equal to the OpenCV path to float32 rounding, tests/test_preproc_gpu.py)."""
+        if preprocess not in ("host", "device"):
+            raise ValueError("preprocess must be 'host' or 'device'")
+        tiles, grids, seqs = self.preprocess_device(crops, math_mode) if preprocess == "device" else self.preprocess(crops, math_mode)
         return self.run_preprocessed(tiles, grids, seqs, fixed_steps=fixed_steps)
