@@ -526,6 +526,44 @@ def layout_bench(dev, peaks, world, kind, steps, warmup):
     return res
 
 
+def ocr_error_bench(dev, world, steps, warmup, timed):
+    """DistilBertForSequenceClassification (default config, fp16 = the reference's CUDA dtype) on the predictor's CUDA
+    batch of 64 texts (surya/ocr_error/__init__.py:16) right-padded to 512 tokens, lengths uniform in [16, 512].  `value`: texts/s of
+    the packed forward with the token plan already on the host; `e2e`: detect_errors() from host int64 ids / masks to label strings."""
+    from surya_b200.config import ocr_error_default
+    from surya_b200.ocr_error import B200DistilBert, build_pack_plan, detect_errors
+    from surya_b200.synth import ocr_error_state_dict, ocr_error_synthetic_batch
+
+    cfg = ocr_error_default()
+    model = B200DistilBert(cfg, ocr_error_state_dict(cfg, seed=0), dtype=torch.float16, device=dev)
+    n_batches, B, L = 4, 64, 512
+    ids, mask = ocr_error_synthetic_batch(cfg, n_batches * B, L, seed=21, min_len=16)
+    plans = [build_pack_plan(ids[i * B:(i + 1) * B].numpy(), mask[i * B:(i + 1) * B].numpy(), cfg) for i in range(n_batches)]
+    n_tok = sum(p["n_tok"] for p in plans)
+
+    def resident():
+        for p in plans:
+            model.forward_packed(p)
+
+    def e2e():
+        detect_errors(model, ids, mask, batch_size=B)
+
+    for _ in range(max(1, warmup)):
+        resident()
+    k = max(1, min(steps, 5))
+    ms = timed(resident, k) / k
+    e2e()
+    ms_e2e = timed(e2e, k) / k
+    texts = n_batches * B * world
+    flop = 2.0 * n_tok * cfg.n_layers * (4 * cfg.dim * cfg.dim + 2 * cfg.dim * cfg.hidden_dim)
+    return {"metric": "texts/sec (ocr_error)", "value": texts / (ms * 1e-3), "unit": "texts/s", "ms_per_step": ms,
+            "e2e": {"value": texts / (ms_e2e * 1e-3), "unit": "texts/s", "h2d_bytes_per_step": int(n_tok * 8 + n_batches * B * 8),
+                    "d2h_bytes_per_step": n_batches * B * 8},
+            "config": {"workload": f"ocr_error: {n_batches} batches of {B} texts, right-padded to {L}, {n_tok} real tokens (packed; pad "
+                                   "positions are never computed)", "dtype": "f16"},
+            "linear_tflops": flop / (ms * 1e-3) / 1e12}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -537,6 +575,7 @@ def main():
     ap.add_argument("--no-detection", action="store_true")
     ap.add_argument("--no-layout", action="store_true", help="skip the layout / table_rec (config 4) secondary numbers")
     ap.add_argument("--no-pipeline", action="store_true", help="skip the ocr_text pipeline (config 5) secondary number")
+    ap.add_argument("--no-ocr-error", action="store_true", help="skip the ocr_error (DistilBERT) secondary number")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -672,6 +711,43 @@ def main():
     ms_e2e_total = timed(e2e_step, max(1, min(args.steps, 3)))
     e2e_n = max(1, min(args.steps, 3))
     e2e_value = B_PER_GPU * world * e2e_n / (ms_e2e_total * 1e-3)
+    # ---- e2e from uint8 crops: the preprocessing of SuryaOCRProcessor inside the timed region, on the device
+    # (sb_rec_preprocess; 3 B / pixel up) and, for comparison, through the OpenCV thread pool on the host
+    from_crops = None
+    try:
+        if world > 1:
+            raise RuntimeError("single-GPU diagnostic (skipped under torchrun)")
+
+        def crops_device():
+            runner.run(crops, fixed_steps=True, preprocess="device")
+
+        def crops_host():
+            runner.run(crops, fixed_steps=True, preprocess="host")
+
+        crops_device()
+        ms_cd = timed(crops_device, e2e_n) / e2e_n
+        crops_host()
+        ms_ch = timed(crops_host, 1)
+        from_crops = {"value": B_PER_GPU * world / (ms_cd * 1e-3), "unit": "crops/s", "ms_per_step": ms_cd,
+                      "h2d_bytes_per_step": int(sum(c.size for c in crops)) + B_PER_GPU * 36, "d2h_bytes_per_step": d2h_bytes,
+                      "api": "RecognitionRunner.run(uint8 crops, preprocess='device'): pack + upload + sb_rec_preprocess (Lanczos4 "
+                             "scale_to_fit, cubic to x28, normalise, tile) + prefill + 127 decode steps",
+                      "host_preprocess": {"value": B_PER_GPU * world / (ms_ch * 1e-3), "unit": "crops/s", "ms_per_step": ms_ch,
+                                          "api": "same call with preprocess='host' (OpenCV thread pool, fp32 tiles up)"}}
+        log(f"e2e from uint8 crops: device preprocessing {from_crops['value']:.1f} crops/s, host preprocessing "
+            f"{from_crops['host_preprocess']['value']:.1f} crops/s")
+    except Exception as e:      # noqa: BLE001
+        from_crops = None if world > 1 else {"error": f"{type(e).__name__}: {e}"}
+        if world == 1:
+            log(f"e2e from crops failed: {from_crops['error']}")
+    ocr_err = None
+    if not args.no_ocr_error and world == 1:
+        try:
+            ocr_err = ocr_error_bench(dev, world, args.steps, args.warmup, timed)
+            log(f"ocr_error: {ocr_err['value']:.0f} texts/s resident, {ocr_err['e2e']['value']:.0f} e2e")
+        except Exception as e:      # noqa: BLE001
+            ocr_err = {"error": f"{type(e).__name__}: {e}"}
+            log(f"ocr_error failed: {ocr_err['error']}")
     # secondary sections must never cost the headline line: a failure is reported inside the JSON instead (all ranks take the
     # same path because the inputs are identical, so the collectives inside stay matched)
     det = None
@@ -748,6 +824,7 @@ def main():
                           "decode_step": ms_decode / (MAX_TOKENS - 1)},
             "algorithmic": alg, "engine_workspace_gb": eng.workspace_bytes / 1e9, "detection": det,
             "layout": lay["layout"] if lay else None, "table_rec": lay["table"] if lay else None, "ocr_pipeline": pipe,
+            "e2e_from_crops": from_crops, "ocr_error": ocr_err,
         }))
     eng.close()
     if world > 1:

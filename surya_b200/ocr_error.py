@@ -103,8 +103,19 @@ class B200DistilBert:
         return self
 
     def _upload(self, arr: np.ndarray) -> torch.Tensor:
-        """ONE pinned int32 upload per batch (ids | positions | segment starts | segment lengths)."""
-        return torch.from_numpy(arr).pin_memory().to(self.device, non_blocking=True)
+        """ONE pinned int32 upload per batch (ids | positions | segment starts | segment lengths) through a grow-only page-locked
+        staging buffer; the event keeps the next batch from overwriting it before the asynchronous copy has read it."""
+        n = int(arr.size)
+        pin = getattr(self, "_pin", None)
+        if pin is None or pin.numel() < n:
+            pin = torch.empty(max(2 * n, 1 << 16), dtype=torch.int32).pin_memory()
+            self._pin, self._pin_ev = pin, torch.cuda.Event()
+        else:
+            self._pin_ev.synchronize()
+        pin.numpy()[:n] = arr
+        out = pin[:n].to(self.device, non_blocking=True)
+        self._pin_ev.record()
+        return out
 
     def forward_packed(self, plan: Dict[str, np.ndarray], return_hidden: bool = False):
         """Run the network over one packed batch (host plan from build_pack_plan); returns logits [B, num_labels] (model dtype)."""

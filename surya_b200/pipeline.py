@@ -107,8 +107,12 @@ class OcrPipeline:
     processor size) and returns (lines grouped per page, timing breakdown in seconds)."""
 
     def __init__(self, det: DetEngine, rec: RecEngine, rec_batch: int = 256, max_tokens: int = 128, det_chunk: int = 16,
-                 workers: int = 16, math_mode: bool = True):
-        self.det, self.rec = det, rec
+                 workers: int = 16, math_mode: bool = True, preprocess: str = "host"):
+        """preprocess: "host" — crops are resized / normalised / tiled by the OpenCV thread pool (the reference's processor code);
+        "device" — uint8 crops go up as they are and sb_rec_preprocess does that work on the GPU."""
+        if preprocess not in ("host", "device"):
+            raise ValueError("preprocess must be 'host' or 'device'")
+        self.det, self.rec, self.preprocess = det, rec, preprocess
         self.runner = RecognitionRunner(rec, batch_size=rec_batch, max_tokens=max_tokens)
         self.det_chunk, self.workers, self.math_mode = det_chunk, max(1, workers), math_mode
 
@@ -142,7 +146,8 @@ class OcrPipeline:
         lines: List[Line] = []
         crops = []
         for pg, (polys, conf) in enumerate(det):
-            img = pages[pg].astype(np.float32)         # processor.image_processor: np.asarray(image, float32)
+            # processor.image_processor: np.asarray(image, float32); the device path keeps the identical integer values as uint8
+            img = pages[pg] if self.preprocess == "device" else pages[pg].astype(np.float32)
             for p, c in zip(polys, conf):
                 crop = slice_polygon(img, p)
                 if crop.shape[0] == 0 or crop.shape[1] == 0:
@@ -153,7 +158,10 @@ class OcrPipeline:
         t["crop + sort"] = time.perf_counter() - t0
         t0 = time.perf_counter()
         if crops:
-            tiles, grids, seqs = self.runner.preprocess([crops[i] for i in order], self.math_mode)
+            if self.preprocess == "device":
+                tiles, grids, seqs = self.runner.preprocess_device([crops[i] for i in order], self.math_mode)
+            else:
+                tiles, grids, seqs = self.runner.preprocess([crops[i] for i in order], self.math_mode)
             t["recognition host preprocessing"] = time.perf_counter() - t0
             t0 = time.perf_counter()
             tok, sc, bb = self.runner.run_preprocessed(tiles, grids, seqs, fixed_steps=fixed_steps)

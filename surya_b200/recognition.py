@@ -642,11 +642,11 @@ def fit_size(h: int, w: int, max_size=(1024, 256), min_size=(168, 168)) -> Tuple
 PP_DESC = 9     # int32 words per crop in sb_rec_preprocess's descriptor table
 
 
-def build_preprocess_plan(crops: Sequence[np.ndarray], cfg: RecConfig, max_size=(1024, 256)) -> dict:
+def build_preprocess_plan(crops: Sequence[np.ndarray], cfg: RecConfig, max_size=(1024, 256), staging=None) -> dict:
     """Host plan of the device preprocessing path (sb_rec_preprocess): uint8 HWC crops packed back to back (16-byte
     aligned), one descriptor per crop {byte offset, h, w, size after scale_to_fit, size rounded up to patch*merge, scratch offset,
     first tile row} and the tile grids — only sizes are computed here, with the reference's arithmetic; every pixel is touched on
-    the device."""
+    the device.  staging(nbytes) may hand out the (pinned) uint8 buffer the crops are packed into."""
     P, m = cfg.vision_encoder.patch_size, cfg.merge_size
     factor = P * m
     desc = np.zeros((len(crops), PP_DESC), dtype=np.int32)
@@ -668,13 +668,14 @@ def build_preprocess_plan(crops: Sequence[np.ndarray], cfg: RecConfig, max_size=
         row += (hb // P) * (wb // P)
         if off >= 2 ** 31 or scratch >= 2 ** 31:
             raise _lib.SuryaB200Error("device preprocessing: more than 2 GiB of crops in one call; split the batch")
-    packed = np.zeros(max(off, 16), dtype=np.uint8)
+    nbytes = max(off, 16)
+    packed = np.zeros(nbytes, dtype=np.uint8) if staging is None else staging(nbytes)
     for i, c in enumerate(crops):
         o, h, w = int(desc[i, 0]), int(desc[i, 1]), int(desc[i, 2])
         packed[o:o + h * w * 3] = np.ascontiguousarray(c).reshape(-1)
     mx = tuple(int(desc[:, k].max()) if len(crops) else 0 for k in (3, 4, 5, 6))
     return {"packed": packed, "desc": desc.reshape(-1), "grids": grids, "n_rows": row, "scratch_floats": scratch,
-            "any_stage1": int(scratch > 0), "max": mx}
+            "any_stage1": int(scratch > 0), "max": mx, "nbytes": nbytes}
 
 
 def prompt_tokens(cfg: RecConfig, n_image_tokens: int, math_mode: bool = True, text_ids: Sequence[int] = ()) -> np.ndarray:
@@ -753,11 +754,20 @@ class RecognitionRunner:
         eng, cfg = self.engine, self.engine.cfg
         dev = eng.device
         P, m = cfg.vision_encoder.patch_size, cfg.merge_size
-        plan = build_preprocess_plan(crops, cfg)
-        seqs = [prompt_tokens(cfg, g[1] * g[2] // m ** 2, math_mode) for g in plan["grids"]]
-        if not crops:
+        if len(crops) == 0:
             return torch.zeros((0, 3 * P * P), dtype=torch.float32, device=dev), [], []
-        host = torch.from_numpy(plan["packed"]).pin_memory()
+
+        def staging(nbytes):        # grow-only pinned staging buffer: crops are packed straight into page-locked memory
+            torch.cuda.current_stream().synchronize()        # the previous call's asynchronous copy out of it must have finished
+            pin = getattr(self, "_pp_pin", None)
+            if pin is None or pin.numel() < nbytes:
+                pin = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8).pin_memory()
+                self._pp_pin = pin
+            return pin.numpy()[:nbytes]
+
+        plan = build_preprocess_plan(crops, cfg, staging=staging)
+        seqs = [prompt_tokens(cfg, g[1] * g[2] // m ** 2, math_mode) for g in plan["grids"]]
+        host = self._pp_pin[:plan["nbytes"]]
         desc_h = torch.from_numpy(plan["desc"]).pin_memory()
         packed = host.to(dev, non_blocking=True)
         desc = desc_h.to(dev, non_blocking=True)

@@ -72,7 +72,7 @@ def test_device_preprocess_matches_restatement_and_cv2(built_lib):
         assert ec <= 2 * TOL_255 * NORM, f"crop {i} {crop.shape}: {ec / NORM:.2e} (0..255 scale) off the cv2 host path"
         row += n
     assert row == tiles.shape[0]
-    _report("tiles", {"max_err_vs_restatement_255": worst_o / NORM, "max_err_vs_cv2_255": worst_c / NORM, "crops": len(crops)})
+    _report("tiles", {"max_err_vs_restatement_255": float(worst_o / NORM), "max_err_vs_cv2_255": float(worst_c / NORM), "crops": len(crops)})
     eng.close()
 
 
@@ -110,7 +110,7 @@ def test_device_preprocess_at_bench_size(built_lib):
     torch.cuda.synchronize()
     assert tiles.shape == (256 * 160, 588) and all(tuple(g) == (1, 4, 40) for g in grids)
     t = tiles.cpu().numpy()
-    assert np.isfinite(t).all() and t.min() > -3.5 and t.max() < 4.0
+    assert np.isfinite(t).all() and t.min() > -6.0 and t.max() < 6.0       # Lanczos / cubic overshoot on noise is not clipped (float images)
     for i in (0, 100, 255):
         o_tiles, _ = P.process_crop(crops[i])
         assert np.abs(t[i * 160:(i + 1) * 160] - o_tiles).max() <= 2 * TOL_255 * NORM

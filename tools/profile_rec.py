@@ -63,7 +63,35 @@ def layout(batch: int = 16):
     torch.cuda.synchronize()
 
 
+def new_paths():
+    """Round-2 additions: ocr_error forward (64 texts right-padded to 512, default DistilBERT, fp16) and the device preprocessing of
+    256 crops of 48 x 512 (sb_rec_preprocess), each run twice (the second run is the one to read)."""
+    from surya_b200.config import ocr_error_default, tiny_rec
+    from surya_b200.ocr_error import B200DistilBert, build_pack_plan
+    from surya_b200.recognition import RecEngine, RecognitionRunner
+    from surya_b200.synth import ocr_error_state_dict, ocr_error_synthetic_batch, rec_state_dict, rec_synthetic_crops
+
+    cfg = ocr_error_default()
+    model = B200DistilBert(cfg, ocr_error_state_dict(cfg, 0), dtype=torch.float16)
+    ids, mask = ocr_error_synthetic_batch(cfg, 64, 512, seed=21, min_len=16)
+    plan = build_pack_plan(ids.numpy(), mask.numpy(), cfg)
+    print("ocr_error tokens", plan["n_tok"])
+    for _ in range(2):
+        model.forward_packed(plan)
+        torch.cuda.synchronize()
+    tcfg = tiny_rec()
+    eng = RecEngine(tcfg, rec_state_dict(tcfg, 0), dtype=torch.float16, max_slots=8, s_max=256, max_patches=2048, max_tokens=512)
+    runner = RecognitionRunner(eng, batch_size=4, max_tokens=4)
+    crops = list(rec_synthetic_crops(256, 48, 512, seed=1234))
+    for _ in range(2):
+        runner.preprocess_device(crops)
+        torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
+    if "--new" in sys.argv:
+        new_paths()
+        sys.exit(0)
     if "--layout" in sys.argv:
         layout()
         sys.exit(0)
