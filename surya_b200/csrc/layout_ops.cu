@@ -507,28 +507,45 @@ __global__ void __launch_bounds__(128) attn_single_query_kernel(const T* __restr
   float tmax[G];
 #pragma unroll
   for (int gq = 0; gq < G; ++gq) tmax[gq] = -INFINITY;
-  for (int j = tid; j < n_keys; j += 128) {
-    const uint4* kr = reinterpret_cast<const uint4*>(kb + j * ts);
-    float acc[G];
+  // The kernel is a latency chain, not a bandwidth problem (64 CTAs x 4 warps, 147 KB of K / V each): every global load of a thread's
+  // next key used to wait for the arithmetic of the previous one.  Keys are therefore taken KU at a time with all their row loads
+  // issued first; the multiply-add order per accumulator is unchanged, so results are bit-identical to the one-key-at-a-time loop.
+  constexpr int KU = 2;
+  for (int j0 = tid; j0 < n_keys; j0 += 128 * KU) {
+    uint4 kv[KU][VPR];
 #pragma unroll
-    for (int gq = 0; gq < G; ++gq) acc[gq] = 0.f;
+    for (int u = 0; u < KU; ++u) {
+      const int j = j0 + u * 128;
+      if (j < n_keys) {
+        const uint4* kr = reinterpret_cast<const uint4*>(kb + j * ts);
 #pragma unroll
-    for (int c = 0; c < VPR; ++c) {
-      const uint4 u = kr[c];
-      const unsigned short* kb16 = reinterpret_cast<const unsigned short*>(&u);
-#pragma unroll
-      for (int gq = 0; gq < G; ++gq) {      // FHFMA: 16-bit q and k, fp32 accumulate, no conversions (bit-identical to fmaf on floats)
-        const uint4 qv = *reinterpret_cast<const uint4*>(q_t + gq * HD + c * 8);
-        const unsigned short* qb = reinterpret_cast<const unsigned short*>(&qv);
-#pragma unroll
-        for (int x = 0; x < 8; ++x) acc[gq] = fma16<T>(qb[x], kb16[x], acc[gq]);
+        for (int c = 0; c < VPR; ++c) kv[u][c] = kr[c];
       }
     }
 #pragma unroll
-    for (int gq = 0; gq < G; ++gq) {
-      const float sv = acc[gq] * scale;
-      sc[gq * n_keys + j] = sv;
-      tmax[gq] = fmaxf(tmax[gq], sv);
+    for (int u = 0; u < KU; ++u) {
+      const int j = j0 + u * 128;
+      if (j >= n_keys) break;
+      float acc[G];
+#pragma unroll
+      for (int gq = 0; gq < G; ++gq) acc[gq] = 0.f;
+#pragma unroll
+      for (int c = 0; c < VPR; ++c) {
+        const unsigned short* kb16 = reinterpret_cast<const unsigned short*>(&kv[u][c]);
+#pragma unroll
+        for (int gq = 0; gq < G; ++gq) {      // FHFMA: 16-bit q and k, fp32 accumulate, no conversions (bit-identical to fmaf on floats)
+          const uint4 qv = *reinterpret_cast<const uint4*>(q_t + gq * HD + c * 8);
+          const unsigned short* qb = reinterpret_cast<const unsigned short*>(&qv);
+#pragma unroll
+          for (int x = 0; x < 8; ++x) acc[gq] = fma16<T>(qb[x], kb16[x], acc[gq]);
+        }
+      }
+#pragma unroll
+      for (int gq = 0; gq < G; ++gq) {
+        const float sv = acc[gq] * scale;
+        sc[gq * n_keys + j] = sv;
+        tmax[gq] = fmaxf(tmax[gq], sv);
+      }
     }
   }
 #pragma unroll
@@ -559,14 +576,25 @@ __global__ void __launch_bounds__(128) attn_single_query_kernel(const T* __restr
     for (int gq = 0; gq < G; ++gq)
 #pragma unroll
       for (int x = 0; x < 8; ++x) acc[gq][x] = 0.f;
-    for (int j = kg; j < n_keys; j += NKG) {
-      const uint4 u = *reinterpret_cast<const uint4*>(vb + j * ts + chunk * 8);
-      const unsigned short* vb16 = reinterpret_cast<const unsigned short*>(&u);
+    constexpr int VU = 6;                       // V rows in flight per thread (576 keys / 16 key groups = 6 rounds of 6)
+    for (int j0 = kg; j0 < n_keys; j0 += NKG * VU) {
+      uint4 vv[VU];
 #pragma unroll
-      for (int gq = 0; gq < G; ++gq) {
-        const unsigned short pb = bits_of<T>(from_f<T>(sc[gq * n_keys + j] / s_l[gq]));
+      for (int u = 0; u < VU; ++u) {
+        const int j = j0 + u * NKG;
+        if (j < n_keys) vv[u] = *reinterpret_cast<const uint4*>(vb + j * ts + chunk * 8);
+      }
 #pragma unroll
-        for (int x = 0; x < 8; ++x) acc[gq][x] = fma16<T>(pb, vb16[x], acc[gq][x]);
+      for (int u = 0; u < VU; ++u) {
+        const int j = j0 + u * NKG;
+        if (j >= n_keys) break;
+        const unsigned short* vb16 = reinterpret_cast<const unsigned short*>(&vv[u]);
+#pragma unroll
+        for (int gq = 0; gq < G; ++gq) {
+          const unsigned short pb = bits_of<T>(from_f<T>(sc[gq * n_keys + j] / s_l[gq]));
+#pragma unroll
+          for (int x = 0; x < 8; ++x) acc[gq][x] = fma16<T>(pb, vb16[x], acc[gq][x]);
+        }
       }
     }
 #pragma unroll
