@@ -335,6 +335,19 @@ def test_ocr_pipeline_end_to_end_tiny(built_lib):
             assert ln.tokens == tok[0] and np.array_equal(ln.boxes, bb[0]), (pg, ln.polygon)
             n_lines += 1
     _report("ocr_pipeline_tiny", {"pages": 5, "lines": n_lines, "timings_s": {k: round(v, 4) for k, v in timings.items()}})
+    # the same flow with the crop preprocessing on the device (uint8 crops up, sb_rec_preprocess): same lines, the
+    # tokens of a direct runner call on the same uint8 crop; against the OpenCV flow tokens may differ on near-ties only
+    pipe_dev = OcrPipeline(det, rec, rec_batch=8, max_tokens=6, det_chunk=2, workers=2, preprocess="device")
+    per_page_dev, _ = pipe_dev.run(pages, fixed_steps=True)
+    same = total = 0
+    for pg in range(5):
+        assert [ln.polygon for ln in per_page_dev[pg]] == [ln.polygon for ln in per_page[pg]]
+        for ln, ln_host in zip(per_page_dev[pg], per_page[pg]):
+            tok, sc, bb = runner.run([slice_polygon(pages[pg], ln.polygon)], fixed_steps=True, preprocess="device")
+            assert ln.tokens == tok[0] and np.array_equal(ln.boxes, bb[0]), (pg, ln.polygon)
+            same += int(ln.tokens == ln_host.tokens)
+            total += 1
+    assert same >= total - max(1, total // 10), f"device preprocessing changed the tokens of {total - same} of {total} lines"
     rec.close()
     det.close()
 
