@@ -166,3 +166,24 @@ def detect_errors(model: B200DistilBert, input_ids, attention_mask, batch_size: 
     if not preds:
         return []
     return [ID2LABEL[int(p)] for p in torch.cat(preds).cpu().tolist()]
+
+
+def sharded_error_labels(model, input_ids, attention_mask, batch_size: int = 64, device=None) -> List[str]:
+    """Multi-GPU form of detect_errors (texts are independent units): every rank classifies its contiguous share of
+    the texts and the argmax ids of ALL texts are all-gathered in text order (one int64 per text on the wire).  Works under any
+    torch.distributed backend (NCCL on the GPU box, gloo in tests/test_shard_cpu.py); world size 1 is detect_errors."""
+    from . import shard
+
+    ids = input_ids.detach().cpu().numpy() if isinstance(input_ids, torch.Tensor) else np.asarray(input_ids)
+    mask = attention_mask.detach().cpu().numpy() if isinstance(attention_mask, torch.Tensor) else np.asarray(attention_mask)
+    n = int(ids.shape[0])
+    if n == 0:
+        return []
+    inv = {v: k for k, v in ID2LABEL.items()}
+
+    def run_local(lo, hi):
+        labels = detect_errors(model, ids[lo:hi], mask[lo:hi], batch_size)
+        return torch.tensor([inv[x] for x in labels], dtype=torch.int64)
+
+    out = shard.sharded_pages(run_local, n, device=device, result_meta=((), torch.int64))
+    return [ID2LABEL[int(p)] for p in out.cpu().tolist()]

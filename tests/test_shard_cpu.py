@@ -183,3 +183,45 @@ def test_gather_step_results_world2():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res)
+
+
+class _FakeErrModel:
+    """Stands in for B200DistilBert on CPU: label = parity of the first real token after [CLS] (deterministic, text-local)."""
+    from surya_b200.config import ocr_error_tiny as _cfg
+    cfg = _cfg()
+
+    def forward_packed(self, plan):
+        first = torch.tensor([int(plan["ids"][s + 1]) % 2 if n > 1 else 0 for s, n in zip(plan["seq_start"], plan["seq_len"])])
+        return torch.nn.functional.one_hot(first, 2).float()
+
+
+def _err_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from surya_b200.ocr_error import sharded_error_labels
+    from surya_b200.synth import ocr_error_synthetic_batch
+
+    ids, mask = ocr_error_synthetic_batch(_FakeErrModel.cfg, 11, 24, seed=9)
+    q.put((rank, sharded_error_labels(_FakeErrModel(), ids, mask, batch_size=4)))
+    dist.destroy_process_group()
+
+
+def test_sharded_error_labels_world2_matches_single_process():
+    """ocr_error over 2 ranks (gloo): 11 texts split 6 / 5, labels all-gathered in text order == the single-process loop."""
+    from surya_b200.ocr_error import detect_errors, sharded_error_labels
+    from surya_b200.synth import ocr_error_synthetic_batch
+
+    ids, mask = ocr_error_synthetic_batch(_FakeErrModel.cfg, 11, 24, seed=9)
+    ref = detect_errors(_FakeErrModel(), ids, mask, batch_size=4)
+    assert sharded_error_labels(_FakeErrModel(), ids, mask, batch_size=4) == ref and len(set(ref)) == 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_err_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, labels in res:
+        assert labels == ref, f"rank {rank}"
