@@ -405,7 +405,7 @@ def test_committed_bench_lines_follow_the_contract():
     import json
 
     for name in ("r01_final_bench_n1.json", "r01_final_bench_n2.json", "r01_final_bench_n4.json", "r02_final_bench_n1.json",
-                 "r02_final_bench_n2_nocpu.json", "r02_final_bench_n4_nocpu.json"):
+                 "r02_final_bench_n2_nocpu.json", "r02_final_bench_n4_nocpu.json", "r02b_final_bench_n1.json"):
         line = [l for l in (ROOT / "profiles" / name).read_text().splitlines() if l.startswith("{")][-1]   # NCCL prints a banner first
         d = json.loads(line)
         if "nocpu" in name:
