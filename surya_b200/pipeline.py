@@ -146,12 +146,16 @@ class OcrPipeline:
         lines: List[Line] = []
         crops = []
         for pg, (polys, conf) in enumerate(det):
-            # processor.image_processor: np.asarray(image, float32); the device path keeps the identical integer values as uint8
-            img = pages[pg] if self.preprocess == "device" else pages[pg].astype(np.float32)
+            # processor.image_processor converts the whole page with np.asarray(image, float32) before slicing; slicing / masking the
+            # uint8 page first and converting only the crop gives the identical float values (integers, pad value 255) without
+            # touching 12 MB per page; the device path keeps the crop as uint8
+            img = pages[pg]
             for p, c in zip(polys, conf):
                 crop = slice_polygon(img, p)
                 if crop.shape[0] == 0 or crop.shape[1] == 0:
                     continue
+                if self.preprocess != "device":
+                    crop = crop.astype(np.float32)
                 lines.append(Line(page=pg, polygon=p, confidence=c))
                 crops.append(crop)
         order = sorted(range(len(crops)), key=lambda i: -crops[i].shape[1])     # longest first (recognition/__init__.py:848)
