@@ -498,10 +498,6 @@ __global__ void __launch_bounds__(128) attn_single_query_kernel(const T* __restr
   float* sc = red + NKG * G * HD;                    // [G][n_keys]
   __shared__ float s_red[4][G];
   __shared__ float s_m[G], s_l[G];
-  // programmatic dependent launch: this grid may start under the tail of the cross-q GEMM, and by triggering at once it lets the
-  // out-projection GEMM behind it start and prefetch its weights; nothing is read or written before the wait
-  pdl_trigger();
-  pdl_wait();
   const int b = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const T* qr = q + static_cast<size_t>(b) * ldq + kvh * G * HD;
   for (int i = tid; i < G * HD; i += 128) q_t[i] = qr[i];
@@ -631,7 +627,7 @@ static int launch_sq(const void* q, int ldq, const void* K, const void* V, long 
     }
     attr = smem;
   }
-  launch_pdl(kern, dim3(B, nkv), dim3(128), smem, st, (const T*)q, ldq, (const T*)K, (const T*)V, bs, hs, ts, (T*)out, ldo, n_keys, scale);
+  kern<<<dim3(B, nkv), 128, smem, st>>>((const T*)q, ldq, (const T*)K, (const T*)V, bs, hs, ts, (T*)out, ldo, n_keys, scale);
   return launch_ok();
 }
 
