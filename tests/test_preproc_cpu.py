@@ -55,3 +55,24 @@ def test_preprocess_plan():
     assert plan["max"] == (max(d[3] for d in desc), max(d[4] for d in desc), max(d[5] for d in desc), max(d[6] for d in desc))
     with pytest.raises(Exception):
         build_preprocess_plan([np.zeros((0, 5, 3), np.uint8)], cfg)
+
+
+def test_crop_chain_pinned_to_the_reference_processor():
+    """The restatement against the reference's OWN SuryaOCRProcessor (scale_to_fit + _process_and_tile, imported unmodified from
+    /root/reference; skipped where it is not mounted): same grids, tiles equal to float32 rounding of the OpenCV resizes."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("/root/reference is only mounted in the build container")
+    from oracle import ref_predictors as RP
+
+    RP.install_predictors()
+    cfg = tiny_rec()
+    proc = RP.synthetic_ocr_processor(cfg)
+    rng = np.random.default_rng(11)
+    for h, w in ((48, 512), (40, 300), (300, 2000), (20, 60), (56, 560), (97, 1403)):
+        crop = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        img = proc.scale_to_fit(np.asarray(crop, dtype=np.float32), (1024, 256))
+        ref_tiles, ref_grid = proc._process_and_tile(img)
+        tiles, grid = P.process_crop(crop, cfg.vision_encoder.patch_size, cfg.merge_size)
+        assert tuple(int(g) for g in ref_grid) == tuple(grid)
+        assert np.abs(tiles - ref_tiles.numpy()).max() <= 2 * TOL_255 / 255 / 0.224, (h, w)
