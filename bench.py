@@ -15,6 +15,12 @@ decoder 12 x 1280, GQA 16/4, vocab 65 792), bf16, greedy decode max_tokens = 128
   cpu_baseline : oracle port (fp32 PyTorch restatement of the reference modules) on this box's host cores,
                  bounded sample, rank 0 only
 
+Secondary objects in the same JSON line (never in the headline region; a failure is reported inside the object): `detection`
+(config 3), `layout` / `table_rec` (config 4), `ocr_pipeline` (config 5, with device and with host crop preprocessing),
+`e2e_from_crops` (recognition from uint8 crops with SuryaOCRProcessor's resizes / normalisation / tiling inside the timed region:
+sb_rec_preprocess on the device vs the OpenCV thread pool; N = 1 only), `ocr_error` (DistilBERT classifier; N = 1 only),
+`gpu_eager_baseline` (the reference algorithm in PyTorch eager on the same GPU).
+
 Multi-GPU (torchrun, one rank per GPU): replicas over independent crop batches (weak scaling); one NCCL
 broadcast of the packed weights at init, one all_gather of the result tensors per step.
 `--impl reference` times the reference algorithm's CPU path (the oracle port: /root/reference is not on the GPU
