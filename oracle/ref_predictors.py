@@ -161,6 +161,62 @@ class OracleRecEngine:
         return self._pack(torch.cat(lms, 0), torch.cat(bbs, 0))
 
 
+    # -- device-loop surface of RecEngine (sb_rec_decode_steps / sb_rec_set_sched), so that RecognitionRunner's scheduling logic
+    #    runs on the CPU exactly as it runs over the CUDA engine (tests/test_runner_cpu.py)
+    def set_sched(self, state, max_tokens: int = 0, max_repeats: int = 40):
+        self.sched = None if state is None else (state, int(max_tokens), int(max_repeats))
+
+    def decode_steps(self, ids_io, slot, pos_io, n_steps, hist=None, use_graph=True, max_pos=None):
+        cfg, B = self.cfg, ids_io.numel()
+        if max_pos is not None and max_pos + n_steps > self.s_max:
+            raise RuntimeError("decode would run past s_max")
+        sched = getattr(self, "sched", None)
+        if sched is not None:
+            sched[0]["valid"].zero_()
+        for s in range(n_steps):
+            live = [b for b in range(B) if int(slot[b]) in self.caches]
+            hist["tok"][s].fill_(cfg.pad_token_id)
+            hist["score"][s].zero_()
+            hist["bbox"][s].zero_()
+            hist["done"][s].fill_(1)
+            if live:
+                idx = torch.tensor(live, dtype=torch.long)
+                out = self.decode(ids_io[idx], slot[idx], pos_io[idx])
+                hist["tok"][s, idx], hist["score"][s, idx] = out["tok"], out["score"]
+                hist["bbox"][s, idx], hist["done"][s, idx] = out["bbox"], out["done"]
+                ids_io[idx] = out["next_ids"]
+            pos_io += 1
+            if sched is not None:
+                stop_rules_step(hist["tok"], hist["done"], s, *[sched[0][k] for k in ("gen", "ring", "done", "valid", "active")],
+                                sched[1], sched[2])
+        return hist
+
+
+def stop_rules_step(tok_hist, done_hist, s, gen, ring, row_done, n_valid, n_active, max_tokens, R):
+    """Python mirror of stop_rules_kernel (surya_b200/csrc/ops.cu): the stop rules of RecognitionPredictor.prediction_loop
+    (surya/recognition/__init__.py:585-598, util.py:59-69) on the per-row scheduler state, one call per decode step."""
+    active = 0
+    for r in range(gen.numel()):
+        if int(row_done[r]):
+            continue
+        tok = int(tok_hist[s, r])
+        cnt = int(gen[r]) + 1
+        gen[r] = cnt
+        ring[r, (cnt - 1) % R] = tok
+        stop = bool(done_hist[s, r]) or cnt >= max_tokens
+        if not stop and cnt >= R:
+            last = [int(ring[r, (cnt + j) % R]) for j in range(R)]          # oldest first
+            u = len(set(last))
+            if u <= 5 and 2 * u <= R:
+                stop = last[R - u:] == last[R - 2 * u: R - u]
+        n_valid[r] = s + 1
+        if stop:
+            row_done[r] = 1
+        else:
+            active += 1
+    n_active[0] = active
+
+
 # ------------------------------------------------------------------------------------------------ trace recording
 class TracingModel:
     """Wraps a B200SuryaModel: logs the inputs of every call the predictor makes and the tokens that came back."""

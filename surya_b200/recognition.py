@@ -696,6 +696,14 @@ def detect_repeat_token(tokens: List[int], max_repeats: int = 40) -> bool:
     return last_n[-u:] == last_n[-u * 2: -u]
 
 
+def _pin(t: torch.Tensor) -> torch.Tensor:
+    """Page-locked copy of a host tensor (asynchronous H2D / D2H); a no-op for device tensors, already pinned tensors, and in a
+    process without CUDA (the CPU tests drive the runner over the oracle engine)."""
+    if t.is_cuda or t.is_pinned() or not torch.cuda.is_available():
+        return t
+    return t.pin_memory()
+
+
 class RecognitionRunner:
     """Mirror of RecognitionPredictor.prediction_loop (surya/recognition/__init__.py:501-607) on engine slots.
 
@@ -802,12 +810,12 @@ class RecognitionRunner:
 
         def tiles_for(take):
             if packed is None:
-                return torch.from_numpy(np.concatenate([tiles[i] for i in take], 0)).pin_memory()
+                return _pin(torch.from_numpy(np.concatenate([tiles[i] for i in take], 0)))
             if all(b == a + 1 for a, b in zip(take, take[1:])):
                 tl = packed[row_off[take[0]]: row_off[take[-1] + 1]]
             else:
                 tl = torch.cat([packed[row_off[i]: row_off[i + 1]] for i in take], 0)
-            return tl if (tl.is_cuda or tl.is_pinned()) else tl.pin_memory()
+            return _pin(tl)
         tokens: List[List[int]] = [[] for _ in range(N)]
         scores: List[List[float]] = [[] for _ in range(N)]
         bboxes = np.zeros((N, self.max_tokens, 6), dtype=np.int64)
@@ -826,8 +834,8 @@ class RecognitionRunner:
         if bufs is None or bufs["key"] != (Bsz, T):
             bufs = {"key": (Bsz, T),
                     "ids_io": torch.empty((Bsz,), dtype=torch.int64, device=dev),
-                    "pos_host": torch.zeros(Bsz, dtype=torch.int32).pin_memory(),
-                    "slot_host": torch.zeros(Bsz, dtype=torch.int32).pin_memory(),
+                    "pos_host": _pin(torch.zeros(Bsz, dtype=torch.int32)),
+                    "slot_host": _pin(torch.zeros(Bsz, dtype=torch.int32)),
                     "pos_io": torch.zeros(Bsz, dtype=torch.int32, device=dev),
                     "slot_t": torch.zeros(Bsz, dtype=torch.int32, device=dev),
                     "hist": {"tok": torch.empty((T, Bsz), dtype=torch.int64, device=dev),
@@ -849,8 +857,8 @@ class RecognitionRunner:
                          "done": torch.ones(Bsz, dtype=torch.uint8, device=dev),
                          "valid": torch.zeros(Bsz, dtype=torch.int32, device=dev),
                          "active": torch.zeros(1, dtype=torch.int32, device=dev),
-                         "gen_host": torch.zeros(Bsz, dtype=torch.int32).pin_memory(),
-                         "done_host": torch.ones(Bsz, dtype=torch.uint8).pin_memory()}
+                         "gen_host": _pin(torch.zeros(Bsz, dtype=torch.int32)),
+                         "done_host": _pin(torch.ones(Bsz, dtype=torch.uint8))}
                 bufs["sched"] = sched
             eng.set_sched(sched, self.max_tokens, self.MAX_REPEATS)
 
@@ -906,20 +914,18 @@ class RecognitionRunner:
                     active = [r for r in range(Bsz) if row_prompt[r] is not None]
                     remaining = min(self.max_tokens - len(tokens[row_prompt[r]]) for r in active)
                     n = max(1, remaining if fixed_steps else min(self.poll, remaining))
-                    for r in range(Bsz):
-                        p = row_prompt[r]
-                        pos_host[r] = 0 if p is None else len(seqs[p]) + len(tokens[p]) - 1
-                        slot_host[r] = row_slot[r]
+                    # one vectorised write per (page-locked) staging array instead of a tensor element store per row; the previous
+                    # round trip's asynchronous copies out of them finished with its history read-back
+                    pos_host.numpy()[:] = [0 if p is None else len(seqs[p]) + len(tokens[p]) - 1 for p in row_prompt]
+                    slot_host.numpy()[:] = row_slot
                     pos_io.copy_(pos_host, non_blocking=True)
                     slot_t.copy_(slot_host, non_blocking=True)
                     if sched is not None:
-                        for r in range(Bsz):
-                            p = row_prompt[r]
-                            sched["gen_host"][r] = 0 if p is None else len(tokens[p])
-                            sched["done_host"][r] = 1 if p is None else 0
+                        sched["gen_host"].numpy()[:] = [0 if p is None else len(tokens[p]) for p in row_prompt]
+                        sched["done_host"].numpy()[:] = [1 if p is None else 0 for p in row_prompt]
                         sched["gen"].copy_(sched["gen_host"], non_blocking=True)
                         sched["done"].copy_(sched["done_host"], non_blocking=True)
-                    eng.decode_steps(ids_io, slot_t, pos_io, n, hist=hist, max_pos=int(pos_host.max()))
+                    eng.decode_steps(ids_io, slot_t, pos_io, n, hist=hist, max_pos=int(pos_host.numpy().max()))
                     th, sh, bh = hist["tok"][:n].cpu().numpy(), hist["score"][:n].cpu().numpy(), hist["bbox"][:n].cpu().numpy()
                     if sched is not None:
                         valid_h, done_h = sched["valid"].cpu().numpy(), sched["done"].cpu().numpy()
